@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""bench.py — edges/s through the fused gather-message-scatter layer (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+Workload (N=1 default) = BASELINE.json configs[1]: RGCN, synthetic Erdos-Renyi graph, 1M nodes /
+20M edges / 4 edge types, hidden_dim=256, one B200.  A "step" is ONE message-passing layer forward
+over the whole batch (every edge sends one message); value = edges / step time.  Inputs (1 GB node
+table) exceed the 126 MB L2, so no flush is needed between timed iterations.
+
+Printed JSON line keys: see the task contract; `roofline` is the algorithmic bytes of the layer
+(SURVEY.md §8d formula) over the device time of the layer, against MEASURED_PEAKS.json;
+`cpu_baseline` is the torch-CPU restatement of the reference op sequence (oracle/torch_cpu_port.py)
+on a bounded edge sample; `e2e` goes through the public layer API with pinned HOST buffers
+(H2D of node states + adjacency, prepare, layer, D2H of the result inside the timed region).
+Multi-GPU: every rank processes its own batch of the same shape (partitions of a disjoint-graph
+batch need no collective) -> "scaling": "weak".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (V, edges per type list, H, kind, description)
+    "cfg2": dict(V=1_000_000, E=[5_000_000] * 4, H=256, kind="rgcn",
+                 desc="RGCN synthetic Erdos-Renyi 1M nodes / 20M edges / 4 edge types, hidden_dim=256 "
+                      "(BASELINE.json configs[1])"),
+    "cfg1": dict(V=8000, E=[8000, 115_200, 115_200], H=320, kind="rgcn",
+                 desc="RGCN PPI-shaped hidden_dim=320, 3 edge types, 8000 nodes (BASELINE.json configs[0])"),
+    "tiny": dict(V=20_000, E=[100_000] * 4, H=256, kind="rgcn", desc="smoke-sized cfg2"),
+}
+METRIC = "edges/sec (fused gather-msg-scatter)"
+
+
+def algorithmic_bytes(V, E_list, D, H, normalize=True):
+    """sum_l E_l*(8+4D) + 4VH + 4*sum(weights) + 4LV."""
+    L = len(E_list)
+    return sum(E_list) * (8 + 4 * D) + 4 * V * H + 4 * L * D * H + (4 * L * V if normalize else 0)
+
+
+def make_inputs(wl, seed):
+    rng = np.random.default_rng(seed)
+    V, H = wl["V"], wl["H"]
+    adjs = []
+    for l, E in enumerate(wl["E"]):
+        if wl is WORKLOADS["cfg1"] and l == 0:
+            ids = np.arange(V, dtype=np.int32)
+            adjs.append(np.stack([ids, ids], axis=1))
+        else:
+            adjs.append(rng.integers(0, V, size=(E, 2), dtype=np.int32))
+    h = rng.random((V, H), dtype=np.float32) * 2.0 - 1.0           # U(-1,1): post-tanh range
+    lim = np.sqrt(6.0 / (H + H))
+    weights = [((rng.random((H, H), dtype=np.float32) * 2.0 - 1.0) * lim).astype(np.float32) for _ in wl["E"]]
+    return h, adjs, weights
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        try:
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            os.unlink(self.path)
+        except Exception:
+            return out
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, val in zip(names, r[5:9]):
+                    if val.strip().lower() == "active":
+                        reasons.add(name)
+            except Exception:
+                continue
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def dist_setup(n_gpus):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
+    return rank, world, local
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+# -------------------------------------------------------------------------------------------
+def run_cpu_port(wl, h, adjs, weights, sample_edges, steps, warmup, threads):
+    """Time the torch-CPU restatement of the reference op order on a bounded edge sample."""
+    import torch
+    from oracle.torch_cpu_port import rgcn_layer_reference_order
+    torch.set_num_threads(threads)
+    M = sum(a.shape[0] for a in adjs)
+    frac = min(1.0, sample_edges / M)
+    s_adjs = [torch.from_numpy(a[: max(1, int(round(a.shape[0] * frac)))]) for a in adjs]
+    ht = torch.from_numpy(h)
+    wt = [torch.from_numpy(w) for w in weights]
+    m_sample = sum(int(a.shape[0]) for a in s_adjs)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        rgcn_layer_reference_order(ht, s_adjs, wt)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    total = float(sum(times))
+    return m_sample * len(times) / total, m_sample, total / len(times)
+
+
+def reference_arm(args, wl, rank, world):
+    """--impl reference: the reference's CPU path (restated port; TF is not installable here)."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    h, adjs, weights = make_inputs(wl, seed=0)
+    M = sum(a.shape[0] for a in adjs)
+    # calibrate on a small sample, then size the per-step sample so the run ends within ~2 minutes
+    rate, _, _ = run_cpu_port(wl, h, adjs, weights, min(M, 200_000), 1, 1, threads)
+    budget_s = 120.0
+    sample = int(min(M, max(50_000, rate * budget_s / max(1, args.steps + args.warmup))))
+    eps, m_sample, t_step = run_cpu_port(wl, h, adjs, weights, sample, args.steps, args.warmup, threads)
+    sample_desc = (f"first {m_sample} of {M} edges (same V={wl['V']}, H={wl['H']}, L={len(wl['E'])}), 1 layer/step, "
+                   f"torch-CPU restatement of the reference op order (TensorFlow absent)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": eps, "unit": "edges/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "sample": sample_desc},
+        "cpu_baseline": {"value": eps, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": eps, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--path", default="auto")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    wl = WORKLOADS[args.workload]
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        reference_arm(args, wl, rank, world)
+        return
+
+    import torch
+    rank, world, local = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback exists)")
+    from tf2_gnn_b200 import _ffi
+    from tf2_gnn_b200.build import build_library
+    from tf2_gnn_b200.layers import MessagePassingInput, RGCN
+    from tf2_gnn_b200.runtime import PreparedBatch
+    build_library()
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    V, H, L = wl["V"], wl["H"], len(wl["E"])
+    M = sum(wl["E"])
+    h_np, adjs_np, w_np = make_inputs(wl, seed=rank)
+    # pinned host buffers (the e2e leg copies from / to these every step)
+    h_host = torch.from_numpy(h_np).pin_memory()
+    adj_host = [torch.from_numpy(a).pin_memory() for a in adjs_np]
+    out_host = torch.empty((V, H), dtype=torch.float32).pin_memory()
+
+    params = RGCN.get_default_hyperparameters()
+    params.update(hidden_dim=H, b200_path=args.path)
+    layer = RGCN(params)
+    layer.build(MessagePassingInput((None, H), tuple((None, 2) for _ in range(L))))
+    layer.set_weights_from_oracle_dict({"edge_mlps": [[w] for w in w_np]})
+
+    # ---- device-resident leg -------------------------------------------------------------
+    h_dev = h_host.to(dev)
+    adj_dev = tuple(a.to(dev) for a in adj_host)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    prepared = PreparedBatch(adj_dev, V)
+    torch.cuda.synchronize()
+    prepare_ms = (time.perf_counter() - t0) * 1e3
+    inp = MessagePassingInput(h_dev, adj_dev)
+    for _ in range(args.warmup):
+        out = layer(inp, prepared=prepared)
+    torch.cuda.synchronize()
+    barrier(world)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _ffi.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    torch.cuda.synchronize()
+    ev[0].record()
+    for i in range(args.steps):
+        out = layer(inp, prepared=prepared)
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    barrier(world)
+    launches = _ffi.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = max_over_ranks(total_ms, world)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = world * M * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end leg: public API with host buffers ------------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        host_inp = MessagePassingInput(h_host, tuple(adj_host))
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            o = layer(host_inp)
+            out_host.copy_(o, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier(world)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            o = layer(host_inp)               # H2D of h + adjacency, prepare (CSR), layer
+            out_host.copy_(o, non_blocking=True)  # D2H of the new node states
+            torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0, world)
+        e2e = {"value": world * M * e2e_steps / dt, "unit": "edges/s",
+               "h2d_bytes_per_step": int(h_host.numel() * 4 + sum(a.numel() * 4 for a in adj_host)),
+               "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps,
+               "ms_per_step": dt / e2e_steps * 1e3}
+
+    if rank != 0:
+        return
+    # ---- roofline: algorithmic bytes of the layer over its device time ---------------------
+    peak, peak_src = load_peaks()
+    alg = algorithmic_bytes(V, wl["E"], H, H)
+    achieved = alg / (ms_per_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
+                "kernel": "whole layer (edge_reduce_kernel + node-level GEMM + weight pack); see profiles/"}
+    cpu = None
+    if not args.skip_cpu_baseline:
+        threads = os.cpu_count() or 1
+        eps, m_sample, t_step = run_cpu_port(wl, h_np, adjs_np, w_np, min(M, 2_000_000), 2, 1, threads)
+        cpu = {"value": eps, "unit": "edges/s", "cores": threads, "kind": "port",
+               "sample": f"first {m_sample} of {M} edges on the full V={V} node table, 1 layer, 2 timed runs; "
+                         f"torch-CPU restatement of the reference op order (TensorFlow absent)"}
+    line = {
+        "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "nodes": V, "edges": M, "edge_types": L, "hidden_dim": H,
+                   "layers_per_step": 1, "path": args.path, "inputs_exceed_l2": V * H * 4 > 126e6,
+                   "l2_flush": "not needed: 1 GB node table >> 126 MB L2" if V * H * 4 > 126e6 else "none (fits L2)",
+                   "parallelism": f"dp{world} (independent batches, no collective)", "prepare_ms": prepare_ms},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "step_ms_min_max": [min(per_step), max(per_step)],
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,174 @@
+/*
+ * tfgnn_b200.h — C ABI of the B200-native tf2_gnn message-passing hot path.
+ *
+ * The reference (microsoft/tf2-gnn) is pure Python on TensorFlow: it has no FFI of its own.
+ * Each entry point below replaces a span of reference Python that runs once per layer (or once
+ * per batch) inside tf2_gnn.layers.GNN._internal_call; the span is cited next to it
+ * (paths relative to /root/reference/).  INTEGRATION.md shows the ctypes stub a maintainer
+ * adds on the reference side.
+ *
+ * Conventions
+ *   - Every data pointer is a DEVICE pointer (zero-copy from DLPack / tensor.data_ptr()).
+ *     The only host pointers are the small arrays of per-edge-type pointers / sizes, which
+ *     are read during the call and may be freed right after it returns.
+ *   - float32 node states / weights, int32 adjacency: [E,2] row-major [src,tgt] pairs
+ *     (message_passing.py:102-104,195-196; gnn.py:222-228).
+ *   - The caller owns all inputs, weights and the PRE-ALLOCATED output.  The library owns only
+ *     the opaque tfgnn_batch_t (CSR + scratch), released by tfgnn_b200_free_batch.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ *     stream).  No entry point synchronises the device except tfgnn_b200_prepare with
+ *     TFGNN_PREPARE_VALIDATE and tfgnn_b200_free_batch.
+ *   - Return value 0 = success; otherwise a TFGNN_ERR_* code and tfgnn_b200_last_error()
+ *     (thread-local) describes it.  There is NO CPU fallback anywhere in this library.
+ */
+#ifndef TFGNN_B200_H_
+#define TFGNN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFGNN_B200_ABI_VERSION 1
+#define TFGNN_MAX_EDGE_TYPES 32
+
+typedef struct tfgnn_batch tfgnn_batch_t;
+
+enum {
+  TFGNN_OK = 0,
+  TFGNN_ERR_INVALID_ARGUMENT = 1, /* maps to Python ValueError  */
+  TFGNN_ERR_CUDA = 2,             /* maps to Python RuntimeError */
+  TFGNN_ERR_UNSUPPORTED = 3,      /* maps to Python NotImplementedError (never a fallback) */
+  TFGNN_ERR_INDEX_OUT_OF_RANGE = 4 /* maps to Python IndexError (TF-CPU raises on bad ids) */
+};
+
+/* tf2_gnn/utils/param_helpers.py:7-19 */
+enum { TFGNN_AGG_SUM = 0, TFGNN_AGG_MEAN = 1, TFGNN_AGG_MAX = 2, TFGNN_AGG_SQRT_N = 3 };
+/* tf2_gnn/utils/param_helpers.py:22-42 ; activation.py:7-14 */
+enum {
+  TFGNN_ACT_NONE = 0, TFGNN_ACT_RELU = 1, TFGNN_ACT_TANH = 2, TFGNN_ACT_LEAKY_RELU = 3,
+  TFGNN_ACT_ELU = 4, TFGNN_ACT_SELU = 5, TFGNN_ACT_GELU = 6
+};
+/* layer flags */
+enum {
+  TFGNN_FLAG_NORMALIZE_BY_NUM_INCOMING = 1u << 0, /* gnn_edge_mlp.py:102-106 */
+  TFGNN_FLAG_ACT_BEFORE_AGGREGATION = 1u << 1,    /* message_passing.py:169-177 */
+  TFGNN_FLAG_USE_TARGET_STATE = 1u << 2           /* gnn_edge_mlp.py:93-98 */
+};
+/* execution path */
+enum {
+  TFGNN_PATH_AUTO = 0,
+  TFGNN_PATH_ATOMIC = 1,     /* per-edge red.global.add, no CSR use (evidence path)      */
+  TFGNN_PATH_SORTED = 2,     /* CSR segmented reduce + fp32 SIMT node-level GEMM         */
+  TFGNN_PATH_SORTED_TC = 3,  /* CSR segmented reduce + 3xTF32 tcgen05 node-level GEMM    */
+  TFGNN_PATH_FUSED_TC = 4    /* one kernel: gather-reduce -> tcgen05 -> activation       */
+};
+enum { TFGNN_PREPARE_VALIDATE = 1u << 0 };
+
+int tfgnn_b200_abi_version(void);
+const char* tfgnn_b200_last_error(void);
+
+/* Per-batch preprocessing, reused by every layer of the stack (the adjacency is layer-invariant:
+ * gnn.py:278,301).  Builds, per edge type, the edges sorted by target (CSR keyed by
+ * type*V + target) and with it the in-degree table that the reference recomputes every layer in
+ * calculate_type_to_num_incoming_edges (message_passing.py:190,230-263).
+ *   adj        host array of L device pointers, adj[l] = int32[num_edges[l], 2]
+ *   num_edges  host array of L edge counts (may be 0: graph_dataset.py:244)
+ * Edges whose src or tgt lies outside [0,V) are dropped; with TFGNN_PREPARE_VALIDATE the call
+ * synchronises the stream and returns TFGNN_ERR_INDEX_OUT_OF_RANGE instead. */
+int tfgnn_b200_prepare(const int32_t* const* adj, const int64_t* num_edges, int32_t num_edge_types,
+                       int64_t num_nodes, uint32_t prepare_flags, tfgnn_batch_t** out_batch,
+                       void* stream);
+int tfgnn_b200_free_batch(tfgnn_batch_t* batch);
+
+/* Introspection of the opaque batch (device pointers stay owned by the batch):
+ * row_ptr int32[L*V+1], src_sorted int32[num_valid_edges]. */
+int tfgnn_b200_batch_info(const tfgnn_batch_t* batch, int64_t* num_nodes, int32_t* num_edge_types,
+                          int64_t* num_edges_total, const int32_t** row_ptr,
+                          const int32_t** src_sorted);
+
+/* Copy the CSR into caller-owned device buffers (row_ptr_out int32[L*V+1], src_sorted_out
+ * int32[num_edges_total]); either may be NULL. */
+int tfgnn_b200_batch_export_csr(const tfgnn_batch_t* batch, int32_t* row_ptr_out,
+                                int32_t* src_sorted_out, void* stream);
+
+/* calculate_type_to_num_incoming_edges (message_passing.py:230-263): out = float32[L, V]. */
+int tfgnn_b200_in_degree(const tfgnn_batch_t* batch, float* out, void* stream);
+
+/* GNN_Edge_MLP / RGCN forward (gnn_edge_mlp.py:84-107 + message_passing.py:95-218):
+ *   out[v] = agg_{l, (u,v) in A_l} [ MLP_l(h_u [|| h_v]) / (c_{v,l}+1e-7) ]   with activation before
+ *   or after the aggregation.  RGCN = num_hidden_layers 0, no target state, normalise (rgcn.py:50-59).
+ *   mlp_weights  host array of L*(num_hidden_layers+1) device pointers, type-major; layer 0 is
+ *                [D_in, H] with D_in = D or 2D (rows [0,D) act on h_src, [D,2D) on h_tgt),
+ *                further layers [H, H]; no biases (test_RGCN.py:35-39).
+ *   h [V, D], out [V, H]. */
+int tfgnn_b200_edge_mlp_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
+                            const float* const* mlp_weights, int32_t num_hidden_layers, int32_t H,
+                            uint32_t flags, int32_t aggregation, int32_t activation, int32_t path,
+                            float* out, void* stream);
+
+/* RGCN convenience entry (rgcn.py:12-62): edge_mlp_fwd with 0 hidden layers, source state only. */
+int tfgnn_b200_rgcn_fwd(tfgnn_batch_t* batch, const float* h, int32_t D, const float* const* W,
+                        int32_t H, uint32_t flags, int32_t aggregation, int32_t activation,
+                        int32_t path, float* out, void* stream);
+
+/* GGNN (ggnn.py:68-89): edge-MLP messages (class default: 0 hidden layers, source state only,
+ * normalised), aggregation, NO message activation, then Keras GRUCell(units=H, reset_after=True):
+ * gru_kernel [H,3H] acts on the aggregated messages, gru_recurrent_kernel [H,3H] on the state h
+ * (D == H required, ggnn.py:30), gru_bias [2,3H]; gate order z,r,h. */
+int tfgnn_b200_ggnn_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
+                        const float* const* mlp_weights, int32_t num_hidden_layers, int32_t H,
+                        uint32_t flags, int32_t aggregation, const float* gru_kernel,
+                        const float* gru_recurrent_kernel, const float* gru_bias, int32_t path,
+                        float* out, void* stream);
+
+/* RGIN (rgin.py:88-106): edge MLP messages, aggregation, optional aggregation MLP
+ * (aggr_weights: host array of num_aggr_layers device pointers [H,H], may be NULL/0), activation. */
+int tfgnn_b200_rgin_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
+                        const float* const* mlp_weights, int32_t num_hidden_layers, int32_t H,
+                        uint32_t flags, int32_t aggregation, int32_t activation,
+                        const float* const* aggr_weights, int32_t num_aggr_layers, int32_t path,
+                        float* out, void* stream);
+
+/* GNN-FiLM (gnn_film.py:83-108): m = gamma_l(h_v) * EdgeMLP_l(...) + beta_l(h_v),
+ * [gamma|beta] = h_v F_l, film_weights: host array of L device pointers [D, 2H] (no hidden layers). */
+int tfgnn_b200_film_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
+                        const float* const* mlp_weights, int32_t num_hidden_layers,
+                        const float* const* film_weights, int32_t H, uint32_t flags,
+                        int32_t aggregation, int32_t activation, int32_t path, float* out,
+                        void* stream);
+
+/* RGAT (rgat.py:91-163): per-type projection W_l [D,H], attention a_l [K, 2H/K]; softmax over all
+ * incoming edges of all types jointly, per head; activation after. */
+int tfgnn_b200_rgat_fwd(tfgnn_batch_t* batch, const float* h, int32_t D, const float* const* W,
+                        const float* const* attention, int32_t H, int32_t num_heads,
+                        int32_t activation, int32_t path, float* out, void* stream);
+
+/* Node-level dense layer out = act(x W), x [V,K], W [K,N], no bias — the op behind every
+ * tf.keras.layers.Dense(use_bias=False) on the path (gnn.py:136-141,165-169) and the building
+ * block of the fp32-accurate node-level contractions.  path: 0 auto, 2 SIMT fp32, 3 tcgen05 3xTF32. */
+int tfgnn_b200_dense_fwd(const float* x, const float* W, float* out, int64_t V, int32_t K, int32_t N,
+                         int32_t activation, int32_t path, void* stream);
+
+/* The three stock ops of the reference's generic MessagePassing.call, for user-defined
+ * _message_function plugins (message_passing.py:64-93) and the literal per-edge path:
+ *   gather_rows               tf.nn.embedding_lookup            message_passing.py:197-206
+ *   unsorted_segment_reduce   tf.math.unsorted_segment_{sum,mean,max,sqrt_n}  :172-174
+ *   activation                get_activation_function(...)      :169-177
+ * ids / segment_ids are int32 with an element stride (2 addresses a column of an [E,2] list). */
+int tfgnn_b200_gather_rows(const float* table, int64_t num_rows, int32_t D, const int32_t* ids,
+                           int64_t ids_stride, int64_t n, float* out, void* stream);
+int tfgnn_b200_unsorted_segment_reduce(const float* data, const int32_t* segment_ids,
+                                       int64_t ids_stride, int64_t M, int32_t H,
+                                       int64_t num_segments, int32_t aggregation, float* out,
+                                       void* stream);
+int tfgnn_b200_activation(const float* x, int64_t n, int32_t activation, float* out, void* stream);
+
+/* Number of kernels this library has launched in the calling process (all threads). */
+int64_t tfgnn_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFGNN_B200_H_ */

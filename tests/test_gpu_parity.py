@@ -1,0 +1,348 @@
+"""Parity of the CUDA path (through the Python facade -> ctypes -> C ABI) against the oracle.
+
+Tolerance for node states (north_star: 1e-5 relative fp32): |got - ref64| <= 1e-5 * max|ref64|,
+where ref64 is the float64 evaluation of the oracle (norm-wise criterion, SURVEY.md §7: element-wise
+relative error is ill-defined next to ReLU zero crossings).  Index bookkeeping is bit-exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle import message_passing_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+LOWEST = np.finfo(np.float32).min
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def assert_states_close(got, ref64, tol=TOL):
+    got = np.asarray(got, dtype=np.float64)
+    ref64 = np.asarray(ref64, dtype=np.float64)
+    assert got.shape == ref64.shape
+    sentinel = ref64 <= LOWEST * 0.99  # unsorted_segment_max identity on empty segments
+    assert np.array_equal(sentinel, got <= LOWEST * 0.99)
+    r = np.where(sentinel, 0.0, ref64)
+    g = np.where(sentinel, 0.0, got)
+    scale = max(np.abs(r).max() if r.size else 0.0, 1e-30)
+    err = np.abs(g - r).max() if r.size else 0.0
+    assert err <= tol * scale, f"max abs err {err:.3e} > {tol:g} * {scale:.3e}"
+
+
+def random_graph(rng, V, L, edges_per_type, empty_type=None, hub=False, self_loops=False, dups=False):
+    adjs = []
+    for l in range(L):
+        E = int(edges_per_type if np.isscalar(edges_per_type) else edges_per_type[l])
+        if empty_type is not None and l == empty_type:
+            adjs.append(np.zeros((0, 2), np.int32))
+            continue
+        a = rng.integers(0, V, size=(E, 2)).astype(np.int32)
+        if hub and E:
+            a[: E // 2, 1] = V // 3  # half of the edges hit one target
+        if self_loops and l == 0:
+            ids = np.arange(V, dtype=np.int32)
+            a = np.stack([ids, ids], axis=1)
+        if dups and E >= 4:
+            a[1] = a[0]
+            a[3] = a[0]
+        adjs.append(a)
+    return adjs
+
+
+def make_layer(kind, params, D, L, weights):
+    from tf2_gnn_b200.layers import MessagePassingInput, get_message_passing_class
+    layer = get_message_passing_class(kind)(params)
+    layer.build(MessagePassingInput((None, D), tuple((None, 2) for _ in range(L))))
+    layer.set_weights_from_oracle_dict(weights)
+    return layer
+
+
+def run_case(kind, params, V, D, L, adjs, seed=0, path="auto"):
+    from tf2_gnn_b200.layers import MessagePassingInput
+    rng = np.random.default_rng(seed)
+    h = rng.uniform(-1, 1, (V, D)).astype(np.float32)
+    w = mo.make_weights(kind, params, D, L, rng)
+    params = dict(params, b200_path=path)
+    layer = make_layer(kind, params, D, L, w)
+    out = layer(MessagePassingInput(torch.from_numpy(h).cuda(), tuple(torch.from_numpy(a).cuda() for a in adjs)))
+    torch.cuda.synchronize()
+    assert tuple(out.shape) == (V, int(params["hidden_dim"])) and out.dtype == torch.float32
+    ref64 = mo.message_passing_forward(kind, params, w, h, adjs, dtype=np.float64)
+    assert_states_close(out.cpu().numpy(), ref64)
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# Golden vectors of the reference's own tests
+# ------------------------------------------------------------------------------------------
+def test_golden_pass_source_states(golden_dir):
+    """tf2_gnn/test/layers/test_message_passing.py:11-84 on the generic plugin path."""
+    _need_gpu()
+    from tf2_gnn_b200.layers import MessagePassing, MessagePassingInput
+
+    class PassSourceStates(MessagePassing):
+        def __init__(self):
+            params = super().get_default_hyperparameters()
+            params["message_activation_function"] = "relu"
+            params["aggregation_function"] = "sum"
+            super().__init__(params)
+
+        def _message_function(self, edge_source_states, edge_target_states, num_incoming_to_node_per_message,
+                              edge_type_idx, training):
+            return edge_source_states
+
+    with open(os.path.join(golden_dir, "message_passing_golden.json")) as f:
+        g = json.load(f)
+    for case in g["pass_source_states"]:
+        layer = PassSourceStates()
+        inp = MessagePassingInput(
+            node_embeddings=torch.tensor(case["node_embeddings"], dtype=torch.float32).cuda(),
+            adjacency_lists=tuple(torch.tensor(a, dtype=torch.int32).cuda() for a in case["adjacency_lists"]))
+        out = layer(inp, training=False)
+        expected = np.array(case["aggregated_states"], np.float32)
+        assert tuple(out.shape) == expected.shape
+        np.testing.assert_array_almost_equal(out.cpu().numpy(), expected)
+
+
+def test_golden_in_degree_doctest(golden_dir):
+    """message_passing.py:238-249 — exact."""
+    _need_gpu()
+    from tf2_gnn_b200.layers.message_passing import calculate_type_to_num_incoming_edges
+    with open(os.path.join(golden_dir, "message_passing_golden.json")) as f:
+        d = json.load(f)["in_degree_doctest"]
+    got = calculate_type_to_num_incoming_edges(
+        torch.zeros((d["num_nodes"], 3)).cuda(),
+        [torch.tensor(a, dtype=torch.int32).cuda() for a in d["adjacency_lists"]])
+    assert got.dtype == torch.float32
+    assert np.array_equal(got.cpu().numpy(), np.array(d["type_to_num_incoming_edges"], np.float32))
+
+
+def test_in_degree_on_process_adjacency_golden(golden_dir):
+    """In-degree of every golden processed adjacency (test/data/test_utils.py:50-115) — exact."""
+    _need_gpu()
+    from tf2_gnn_b200.layers.message_passing import calculate_type_to_num_incoming_edges
+    with open(os.path.join(golden_dir, "process_adjacency_lists_golden.json")) as f:
+        g = json.load(f)
+    for case in g["cases"]:
+        n = case["input"]["num_nodes"]
+        adjs = [torch.tensor(np.array(a, np.int32).reshape(-1, 2)).cuda() for a in case["adjacency_lists"]]
+        got = calculate_type_to_num_incoming_edges(torch.zeros((n, 1)).cuda(), adjs).cpu().numpy()
+        assert np.array_equal(got, np.array(case["type_to_num_incoming_edges"], np.float32).reshape(len(adjs), n))
+
+
+# ------------------------------------------------------------------------------------------
+# Index bookkeeping: bit-exact
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("V,L,E", [(1, 1, 1), (37, 3, 200), (5000, 4, 40000), (300, 2, 9000)])
+def test_csr_is_bit_exact(V, L, E):
+    _need_gpu()
+    from tf2_gnn_b200.runtime import PreparedBatch
+    rng = np.random.default_rng(V + L + E)
+    adjs = random_graph(rng, V, L, E, empty_type=1 if L > 2 else None, hub=True, dups=True)
+    pb = PreparedBatch([torch.from_numpy(a).cuda() for a in adjs], V)
+    row_ptr, src = (t.cpu().numpy() for t in pb.csr())
+    counts = np.concatenate([np.bincount(a[:, 1], minlength=V) for a in adjs])
+    expect_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    assert np.array_equal(row_ptr, expect_ptr)
+    for l, a in enumerate(adjs):
+        order = np.argsort(a[:, 1], kind="stable")
+        by_tgt = a[order]
+        for v in np.unique(a[:, 1])[:200]:
+            seg = src[row_ptr[l * V + v]: row_ptr[l * V + v + 1]]
+            ref = np.sort(by_tgt[by_tgt[:, 1] == v, 0])
+            assert np.array_equal(np.sort(seg), ref)
+            if len(seg) <= 256:
+                assert np.array_equal(seg, ref)  # canonical ascending order
+    indeg = pb.in_degree().cpu().numpy()
+    assert np.array_equal(indeg, mo.calculate_type_to_num_incoming_edges(V, adjs))
+
+
+def test_out_of_range_index_raises_with_validation():
+    _need_gpu()
+    from tf2_gnn_b200.runtime import PreparedBatch
+    adj = torch.tensor([[0, 1], [5, 1]], dtype=torch.int32).cuda()
+    with pytest.raises(IndexError):
+        PreparedBatch([adj], 3, validate=True)
+    pb = PreparedBatch([adj], 3, validate=False)  # dropped, like TF on GPU
+    assert pb.in_degree().cpu().numpy().tolist() == [[0.0, 1.0, 0.0]]
+
+
+# ------------------------------------------------------------------------------------------
+# RGCN (primary target)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("V,D,H,L,E,opts", [
+    (5, 3, 12, 3, 3, {}),                        # doctest-sized (scalar fallback kernels)
+    (64, 7, 7, 14, 50, {}),                      # test_RGCN.py shape case: 14 edge types, odd dims
+    (500, 64, 64, 3, 4000, dict(self_loops=True)),
+    (1000, 128, 128, 4, 6000, dict(hub=True, dups=True)),
+    (2000, 320, 320, 3, 20000, dict(self_loops=True)),   # PPI-like hidden size
+    (3000, 256, 256, 4, 15000, dict(empty_type=2)),      # cfg2-like hidden size, one empty type
+    (257, 100, 36, 2, 1000, {}),                 # D%4==0, H%4==0 but not tile multiples
+])
+@pytest.mark.parametrize("path", ["sorted", "auto"])
+def test_rgcn_parity(V, D, H, L, E, opts, path):
+    _need_gpu()
+    rng = np.random.default_rng(V * 7 + D)
+    adjs = random_graph(rng, V, L, E, **opts)
+    p = mo.default_hyperparameters("rgcn")
+    p["hidden_dim"] = H
+    run_case("rgcn", p, V, D, L, adjs, seed=V, path=path)
+
+
+def test_rgcn_atomic_path_matches():
+    _need_gpu()
+    rng = np.random.default_rng(5)
+    V, D, H, L = 1500, 128, 128, 3
+    adjs = random_graph(rng, V, L, 12000, hub=True)
+    p = mo.default_hyperparameters("rgcn")
+    p["hidden_dim"] = H
+    a = run_case("rgcn", p, V, D, L, adjs, seed=1, path="atomic")
+    b = run_case("rgcn", p, V, D, L, adjs, seed=1, path="sorted")
+    assert_states_close(a.cpu().numpy(), b.cpu().numpy().astype(np.float64))
+
+
+def test_rgcn_isolated_nodes_and_no_edges():
+    _need_gpu()
+    p = mo.default_hyperparameters("rgcn")
+    p["hidden_dim"] = 16
+    adjs = [np.zeros((0, 2), np.int32), np.array([[0, 1]], np.int32)]
+    out = run_case("rgcn", p, 10, 16, 2, adjs)
+    assert np.all(out.cpu().numpy()[2:] == 0.0)  # sigma(0) for nodes without incoming edges
+    run_case("rgcn", p, 10, 16, 2, [np.zeros((0, 2), np.int32)] * 2)
+
+
+def test_rgcn_is_deterministic_run_to_run():
+    _need_gpu()
+    from tf2_gnn_b200.layers import MessagePassingInput
+    rng = np.random.default_rng(3)
+    V, D, H, L = 4000, 128, 128, 3
+    adjs = [torch.from_numpy(a).cuda() for a in random_graph(rng, V, L, 60000, hub=True)]
+    h = torch.from_numpy(rng.uniform(-1, 1, (V, D)).astype(np.float32)).cuda()
+    p = mo.default_hyperparameters("rgcn")
+    p["hidden_dim"] = H
+    layer = make_layer("rgcn", p, D, L, mo.make_weights("rgcn", p, D, L, rng))
+    a = layer(MessagePassingInput(h, tuple(adjs))).cpu().numpy()
+    b = layer(MessagePassingInput(h, tuple(adjs))).cpu().numpy()
+    assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------
+# Edge-MLP family over its hyper-parameter grid
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("agg", ["sum", "mean", "max", "sqrt_n"])
+@pytest.mark.parametrize("act_before", [False, True])
+@pytest.mark.parametrize("use_target,normalize,n_hidden", [
+    (False, True, 0), (True, False, 0), (True, True, 0), (False, False, 1), (True, True, 1)])
+def test_edge_mlp_grid(agg, act_before, use_target, normalize, n_hidden):
+    _need_gpu()
+    rng = np.random.default_rng(11)
+    V, D, H, L = 300, 32, 48, 3
+    adjs = random_graph(rng, V, L, 2500, hub=True, dups=True)
+    p = mo.default_hyperparameters("gnn_edge_mlp")
+    p.update(hidden_dim=H, aggregation_function=agg, message_activation_before_aggregation=act_before,
+             use_target_state_as_input=use_target, normalize_by_num_incoming=normalize,
+             num_edge_MLP_hidden_layers=n_hidden, message_activation_function="tanh")
+    literal_only = n_hidden >= 1 and (agg == "max" or act_before)
+    if literal_only:
+        with pytest.raises(NotImplementedError):   # loud, never a silent fallback
+            run_case("gnn_edge_mlp", p, V, D, L, adjs)
+    else:
+        run_case("gnn_edge_mlp", p, V, D, L, adjs)
+
+
+@pytest.mark.parametrize("act", ["relu", "tanh", "leaky_relu", "elu", "selu", "gelu"])
+def test_activations(act):
+    _need_gpu()
+    rng = np.random.default_rng(2)
+    adjs = random_graph(rng, 200, 2, 1500)
+    p = mo.default_hyperparameters("rgcn")
+    p.update(hidden_dim=32, message_activation_function=act)
+    run_case("rgcn", p, 200, 32, 2, adjs)
+    p["message_activation_before_aggregation"] = True
+    run_case("rgcn", p, 200, 32, 2, adjs)
+
+
+def test_ggnn_parity():
+    _need_gpu()
+    rng = np.random.default_rng(4)
+    V, H, L = 700, 128, 5
+    adjs = random_graph(rng, V, L, 2100, self_loops=True)
+    p = mo.default_hyperparameters("ggnn")
+    p["hidden_dim"] = H
+    run_case("ggnn", p, V, H, L, adjs)
+    p["normalize_by_num_incoming"] = False   # PPI_GGNN.json:9
+    run_case("ggnn", p, V, H, L, adjs)
+
+
+@pytest.mark.parametrize("n_aggr", [None, 0, 2])
+def test_rgin_parity(n_aggr):
+    _need_gpu()
+    rng = np.random.default_rng(6)
+    V, D, H, L = 400, 64, 64, 3
+    adjs = random_graph(rng, V, L, 3000)
+    p = mo.default_hyperparameters("rgin")
+    p.update(hidden_dim=H, num_aggr_MLP_hidden_layers=n_aggr, normalize_by_num_incoming=True)
+    run_case("rgin", p, V, D, L, adjs)
+
+
+@pytest.mark.parametrize("use_target,act_before,agg", [(False, False, "sum"), (True, False, "sum"),
+                                                        (False, True, "sum"), (True, True, "max")])
+def test_film_parity(use_target, act_before, agg):
+    _need_gpu()
+    rng = np.random.default_rng(8)
+    V, D, H, L = 500, 64, 64, 4
+    adjs = random_graph(rng, V, L, 3000, hub=True)
+    p = mo.default_hyperparameters("gnn_film")
+    p.update(hidden_dim=H, use_target_state_as_input=use_target, message_activation_before_aggregation=act_before,
+             aggregation_function=agg, normalize_by_num_incoming=True)
+    run_case("gnn_film", p, V, D, L, adjs)
+
+
+# ------------------------------------------------------------------------------------------
+# Node-level dense and error behaviour
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("V,K,N", [(1, 1, 1), (130, 50, 17), (1000, 320, 320), (777, 96, 256)])
+def test_dense_fwd(V, K, N):
+    _need_gpu()
+    from tf2_gnn_b200 import _ffi
+    from tf2_gnn_b200.runtime import stream_ptr
+    rng = np.random.default_rng(V)
+    x = rng.uniform(-1, 1, (V, K)).astype(np.float32)
+    w = rng.uniform(-0.3, 0.3, (K, N)).astype(np.float32)
+    xt, wt = torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda()
+    out = torch.empty((V, N), dtype=torch.float32, device="cuda")
+    _ffi.check(_ffi.lib().tfgnn_b200_dense_fwd(xt.data_ptr(), wt.data_ptr(), out.data_ptr(), V, K, N,
+                                                _ffi.ACT["tanh"], 0, stream_ptr()))
+    assert_states_close(out.cpu().numpy(), np.tanh(x.astype(np.float64) @ w.astype(np.float64)))
+
+
+def test_unknown_names_raise_like_the_reference():
+    from tf2_gnn_b200.layers import get_message_passing_class
+    from tf2_gnn_b200.utils import get_activation_function, get_aggregation_function
+    with pytest.raises(ValueError):
+        get_message_passing_class("gcn2")
+    with pytest.raises(ValueError):
+        get_activation_function("linear")
+    with pytest.raises(ValueError):
+        get_aggregation_function("median")
+    assert get_message_passing_class("RGCN").__name__ == "RGCN"
+
+
+def test_launch_counter_moves():
+    _need_gpu()
+    from tf2_gnn_b200 import _ffi
+    before = _ffi.launch_count()
+    rng = np.random.default_rng(0)
+    p = mo.default_hyperparameters("rgcn")
+    p["hidden_dim"] = 32
+    run_case("rgcn", p, 100, 32, 2, random_graph(rng, 100, 2, 500))
+    assert _ffi.launch_count() > before

@@ -1,0 +1,270 @@
+// C-ABI entry points (include/tfgnn_b200.h): argument validation and the per-layer orchestration
+// of the edge-level (HBM-bound) and node-level (tensor-core / FFMA) kernels.
+//
+// Formulations (exact in real arithmetic; fp32 reassociation only — DESIGN.md §3):
+//   aggregate-then-transform  out = act( rn(v) * [A_0|..|A_{L-1}] [W_0;..;W_{L-1}] ),
+//                             A_l[v] = 1/(c_{v,l}+eps) * sum_{(u,v) in A_l} h_u
+//     valid when the message is linear in h_u and the aggregation is sum/mean/sqrt_n with the
+//     activation after it (RGCN/GGNN defaults, every PPI/QM9 RGCN config).
+//   transform-then-aggregate  P = h [W_0|..|W_{L-1}];  out[v] = agg_{l,e} f(P_l[src_e], v, l)
+//     for max-aggregation / activation-before-aggregation (per-edge non-linearity).
+//   hoisted hidden layer      A_l[v] = scale * sum_e relu(U^s_l h_u + U^t_l h_v); out = act(A W2cat)
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+#include "edge_reduce.cuh"
+#include "gemm.cuh"
+
+namespace tfgnn {
+
+std::atomic<long long> g_launch_count{0};
+static thread_local std::string t_last_error;
+static thread_local int t_last_code = 0;
+
+void set_error(int code, const std::string& msg) {
+  t_last_code = code;
+  t_last_error = msg;
+}
+int last_error_code() { return t_last_code; }
+
+int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
+  if (e == cudaSuccess) return 0;
+  set_error(TFGNN_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file +
+                                ":" + std::to_string(line) + ")");
+  return TFGNN_ERR_CUDA;
+}
+
+int unsupported(const std::string& msg) {
+  set_error(TFGNN_ERR_UNSUPPORTED, msg);
+  return TFGNN_ERR_UNSUPPORTED;
+}
+
+bool valid_act(int a) { return a >= TFGNN_ACT_NONE && a <= TFGNN_ACT_GELU; }
+bool valid_agg(int a) { return a >= TFGNN_AGG_SUM && a <= TFGNN_AGG_SQRT_N; }
+
+// Node-level contraction C = epi(A B) with B [K,N] row-major in device memory.
+// tc_scratch: buffer for the tensor-core operand packing (may be null -> SIMT only).
+int node_gemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long M, int N,
+                     int K, const GemmEpilogue& epi, int path, tfgnn_batch* batch, int tc_slot,
+                     cudaStream_t st) {
+  bool want_tc = (path == TFGNN_PATH_AUTO || path == TFGNN_PATH_SORTED_TC || path == TFGNN_PATH_FUSED_TC);
+  if (want_tc && ldb == N && gemm_tc_supported(M, N, K, A, lda, C, ldc)) {
+    void* packed = nullptr;
+    int rc = batch_scratch(batch, tc_slot, gemm_tc_packed_bytes(N, K), &packed);
+    if (rc) return rc;
+    rc = launch_pack_weights_tc(B, ldb, K, N, (float*)packed, st);
+    if (rc) return rc;
+    return launch_gemm_tc(A, lda, (const float*)packed, C, ldc, M, N, K, epi, st);
+  }
+  if (path == TFGNN_PATH_SORTED_TC)
+    return unsupported("TFGNN_PATH_SORTED_TC: shape not supported by the tcgen05 GEMM (need N%16==0, K%32==0)");
+  return launch_gemm_simt(A, lda, B, ldb, C, ldc, M, N, K, epi, st);
+}
+
+int agg_row_norm(int aggregation) {
+  return aggregation == TFGNN_AGG_MEAN ? 1 : aggregation == TFGNN_AGG_SQRT_N ? 2 : 0;
+}
+
+// Edge-MLP family core.  Writes act/agg result to out[V, ldo].
+int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp_weights,
+                         int n_hidden, int H, uint32_t flags, int aggregation, int activation, int path,
+                         float* out, int ldo, cudaStream_t st) {
+  TFGNN_REQUIRE(b != nullptr, "batch is NULL");
+  TFGNN_REQUIRE(D > 0 && H > 0, "D and H must be positive");
+  TFGNN_REQUIRE(n_hidden >= 0, "num_hidden_layers must be >= 0");
+  TFGNN_REQUIRE(valid_act(activation), "unknown activation code");
+  TFGNN_REQUIRE(valid_agg(aggregation), "unknown aggregation code");
+  TFGNN_REQUIRE(path >= TFGNN_PATH_AUTO && path <= TFGNN_PATH_FUSED_TC, "unknown path code");
+  const int V = (int)b->V, L = b->L;
+  if (V == 0) return 0;
+  TFGNN_REQUIRE(h != nullptr && out != nullptr, "h / out is NULL");
+  TFGNN_REQUIRE(L == 0 || mlp_weights != nullptr, "mlp_weights is NULL");
+  const int n_layers = n_hidden + 1;
+  for (int i = 0; i < L * n_layers; ++i) TFGNN_REQUIRE(mlp_weights[i] != nullptr, "a weight pointer is NULL");
+
+  const bool normalize = flags & TFGNN_FLAG_NORMALIZE_BY_NUM_INCOMING;
+  const bool act_before = flags & TFGNN_FLAG_ACT_BEFORE_AGGREGATION;
+  const bool use_target = flags & TFGNN_FLAG_USE_TARGET_STATE;
+  const bool sum_like = aggregation != TFGNN_AGG_MAX;
+  const int row_norm = agg_row_norm(aggregation);
+
+  PtrTable first{}, last{};
+  for (int l = 0; l < L; ++l) {
+    first.p[l] = mlp_weights[l * n_layers];
+    last.p[l] = mlp_weights[l * n_layers + n_hidden];
+  }
+
+  if (L == 0) {
+    // No edges at all: agg identity then activation (message_passing.py:172-177).
+    EdgeReduceParams p;
+    p.X = h; p.ldx = D; p.row_ptr = b->row_ptr; p.src = b->src_sorted;
+    p.out = out; p.ldo = ldo; p.V = V; p.L = 0; p.C = H;
+    p.reduce_max = aggregation == TFGNN_AGG_MAX;
+    p.final_act = act_before ? TFGNN_ACT_NONE : activation;
+    return launch_edge_reduce(p, /*merged=*/true, st);
+  }
+
+  if (n_hidden == 0 && sum_like && !act_before) {
+    // ---- aggregate-then-transform ----
+    const int K = L * D * (use_target ? 2 : 1);
+    void *A = nullptr, *Wcat = nullptr;
+    int rc = batch_scratch(b, 2, (size_t)V * K * sizeof(float), &A);
+    if (rc) return rc;
+    rc = batch_scratch(b, 3, (size_t)K * H * sizeof(float), &Wcat);
+    if (rc) return rc;
+    if (path == TFGNN_PATH_ATOMIC) {
+      TFGNN_CUDA(cudaMemsetAsync(A, 0, (size_t)V * K * sizeof(float), st));
+      rc = launch_edge_scatter_atomic(b, h, D, D, normalize, (float*)A, K, D, st);
+      if (rc) return rc;
+    } else {
+      EdgeReduceParams p;
+      p.X = h; p.ldx = D; p.x_type_stride = 0;
+      p.row_ptr = b->row_ptr; p.src = b->src_sorted;
+      p.out = (float*)A; p.ldo = K; p.out_type_stride = D;
+      p.V = V; p.L = L; p.C = D; p.normalize = normalize;
+      rc = launch_edge_reduce(p, /*merged=*/false, st);
+      if (rc) return rc;
+    }
+    rc = launch_pack_vertical(first, L, 0, D, H, H, (float*)Wcat, H, 0, st);
+    if (rc) return rc;
+    if (use_target) {
+      rc = launch_target_term(h, D, b->row_ptr, V, L, D, normalize, (float*)A, K, L * D, st);
+      if (rc) return rc;
+      rc = launch_pack_vertical(first, L, D, D, H, H, (float*)Wcat, H, L * D, st);
+      if (rc) return rc;
+    }
+    GemmEpilogue epi;
+    epi.act = activation;
+    epi.row_norm = row_norm; epi.row_ptr = b->row_ptr; epi.V = V; epi.L = L;
+    return node_gemm((const float*)A, K, (const float*)Wcat, H, out, ldo, V, H, K, epi, path, b, 6, st);
+  }
+
+  if (path == TFGNN_PATH_ATOMIC)
+    return unsupported("TFGNN_PATH_ATOMIC only implements the linear-message sum/mean/sqrt_n case");
+
+  if (n_hidden == 0) {
+    // ---- transform-then-aggregate (max aggregation and/or activation before aggregation) ----
+    const int LH = L * H;
+    void *P = nullptr, *Tt = nullptr, *Wcat = nullptr;
+    int rc = batch_scratch(b, 2, (size_t)V * LH * sizeof(float), &P);
+    if (rc) return rc;
+    rc = batch_scratch(b, 3, (size_t)D * LH * sizeof(float), &Wcat);
+    if (rc) return rc;
+    rc = launch_pack_horizontal(first, L, 0, D, H, H, (float*)Wcat, LH, st);
+    if (rc) return rc;
+    GemmEpilogue none;
+    rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)P, LH, V, LH, D, none, path, b, 6, st);
+    if (rc) return rc;
+    if (use_target) {
+      rc = batch_scratch(b, 4, (size_t)V * LH * sizeof(float), &Tt);
+      if (rc) return rc;
+      rc = launch_pack_horizontal(first, L, D, D, H, H, (float*)Wcat, LH, st);
+      if (rc) return rc;
+      rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)Tt, LH, V, LH, D, none, path, b, 6, st);
+      if (rc) return rc;
+    }
+    EdgeReduceParams p;
+    p.X = (const float*)P; p.ldx = LH; p.x_type_stride = H;
+    p.T = (const float*)Tt; p.ldt = LH; p.t_type_stride = H;
+    p.row_ptr = b->row_ptr; p.src = b->src_sorted;
+    p.out = out; p.ldo = ldo; p.V = V; p.L = L; p.C = H;
+    p.normalize = normalize;
+    p.edge_act = act_before ? activation : TFGNN_ACT_NONE;
+    p.reduce_max = aggregation == TFGNN_AGG_MAX;
+    p.row_norm = row_norm;
+    p.final_act = act_before ? TFGNN_ACT_NONE : activation;
+    return launch_edge_reduce(p, /*merged=*/true, st);
+  }
+
+  if (n_hidden == 1 && sum_like && !act_before) {
+    // ---- hoisted hidden layer: per-edge relu on pre-projected tables, output layer per (v,l) ----
+    const int LH = L * H;
+    void *Xs = nullptr, *Xt = nullptr, *Wcat = nullptr, *A = nullptr, *W2 = nullptr;
+    int rc = batch_scratch(b, 2, (size_t)V * LH * sizeof(float), &Xs);
+    if (rc) return rc;
+    rc = batch_scratch(b, 3, (size_t)(D > H ? D : H) * LH * sizeof(float), &Wcat);
+    if (rc) return rc;
+    rc = launch_pack_horizontal(first, L, 0, D, H, H, (float*)Wcat, LH, st);
+    if (rc) return rc;
+    GemmEpilogue none;
+    rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)Xs, LH, V, LH, D, none, path, b, 6, st);
+    if (rc) return rc;
+    if (use_target) {
+      rc = batch_scratch(b, 4, (size_t)V * LH * sizeof(float), &Xt);
+      if (rc) return rc;
+      rc = launch_pack_horizontal(first, L, D, D, H, H, (float*)Wcat, LH, st);
+      if (rc) return rc;
+      rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)Xt, LH, V, LH, D, none, path, b, 6, st);
+      if (rc) return rc;
+    }
+    rc = batch_scratch(b, 5, (size_t)V * LH * sizeof(float), &A);
+    if (rc) return rc;
+    EdgeReduceParams p;
+    p.X = (const float*)Xs; p.ldx = LH; p.x_type_stride = H;
+    p.T = (const float*)Xt; p.ldt = LH; p.t_type_stride = H;
+    p.row_ptr = b->row_ptr; p.src = b->src_sorted;
+    p.out = (float*)A; p.ldo = LH; p.out_type_stride = H;
+    p.V = V; p.L = L; p.C = H; p.normalize = normalize; p.hidden_relu = 1;
+    rc = launch_edge_reduce(p, /*merged=*/false, st);
+    if (rc) return rc;
+    rc = batch_scratch(b, 7, (size_t)LH * H * sizeof(float), &W2);
+    if (rc) return rc;
+    rc = launch_pack_vertical(last, L, 0, H, H, H, (float*)W2, H, 0, st);
+    if (rc) return rc;
+    GemmEpilogue epi;
+    epi.act = activation;
+    epi.row_norm = row_norm; epi.row_ptr = b->row_ptr; epi.V = V; epi.L = L;
+    return node_gemm((const float*)A, LH, (const float*)W2, H, out, ldo, V, H, LH, epi, path, b, 6, st);
+  }
+
+  return unsupported(
+      "edge MLP with >=2 hidden layers, or 1 hidden layer combined with max-aggregation / "
+      "activation-before-aggregation, needs the per-edge literal path (not built yet)");
+}
+
+}  // namespace tfgnn
+
+using namespace tfgnn;
+
+extern "C" int tfgnn_b200_abi_version(void) { return TFGNN_B200_ABI_VERSION; }
+extern "C" const char* tfgnn_b200_last_error(void) { return t_last_error.c_str(); }
+extern "C" int64_t tfgnn_b200_launch_count(void) { return g_launch_count.load(); }
+
+extern "C" int tfgnn_b200_edge_mlp_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
+                                       const float* const* mlp_weights, int32_t num_hidden_layers, int32_t H,
+                                       uint32_t flags, int32_t aggregation, int32_t activation, int32_t path,
+                                       float* out, void* stream) {
+  return edge_mlp_core(batch, h, D, mlp_weights, num_hidden_layers, H, flags, aggregation, activation, path, out,
+                       H, (cudaStream_t)stream);
+}
+
+extern "C" int tfgnn_b200_rgcn_fwd(tfgnn_batch_t* batch, const float* h, int32_t D, const float* const* W,
+                                   int32_t H, uint32_t flags, int32_t aggregation, int32_t activation,
+                                   int32_t path, float* out, void* stream) {
+  return edge_mlp_core(batch, h, D, W, 0, H, flags & ~TFGNN_FLAG_USE_TARGET_STATE, aggregation, activation, path,
+                       out, H, (cudaStream_t)stream);
+}
+
+extern "C" int tfgnn_b200_dense_fwd(const float* x, const float* W, float* out, int64_t V, int32_t K, int32_t N,
+                                    int32_t activation, int32_t path, void* stream) {
+  TFGNN_REQUIRE(V >= 0 && K > 0 && N > 0, "bad dense shape");
+  TFGNN_REQUIRE(valid_act(activation), "unknown activation code");
+  if (V == 0) return 0;
+  TFGNN_REQUIRE(x && W && out, "NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmEpilogue epi;
+  epi.act = activation;
+  const bool want_tc = path == TFGNN_PATH_AUTO || path == TFGNN_PATH_SORTED_TC || path == TFGNN_PATH_FUSED_TC;
+  if (want_tc && gemm_tc_supported(V, N, K, x, K, out, N)) {
+    void* packed = nullptr;
+    TFGNN_CUDA(cudaMallocAsync(&packed, gemm_tc_packed_bytes(N, K), st));
+    int rc = launch_pack_weights_tc(W, N, K, N, (float*)packed, st);
+    if (!rc) rc = launch_gemm_tc(x, K, (const float*)packed, out, N, V, N, K, epi, st);
+    cudaFreeAsync(packed, st);
+    return rc;
+  }
+  if (path == TFGNN_PATH_SORTED_TC)
+    return unsupported("dense_fwd: shape not supported by the tcgen05 GEMM (need N%16==0, K%32==0)");
+  return launch_gemm_simt(x, K, W, N, out, N, V, N, K, epi, st);
+}

@@ -1,0 +1,102 @@
+// Shared helpers for the tfgnn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <string>
+
+#include "../../include/tfgnn_b200.h"
+
+namespace tfgnn {
+
+constexpr float kSmallNumber = 1e-7f;       // tf2_gnn/utils/constants.py:2
+constexpr float kLeakyReluAlpha = 0.2f;     // tf.nn.leaky_relu default
+constexpr float kSeluAlpha = 1.6732632423543772f;
+constexpr float kSeluScale = 1.0507009873554805f;
+constexpr float kLowestFloat = -3.402823466e+38f;  // tf.math.unsorted_segment_max identity
+
+extern std::atomic<long long> g_launch_count;
+void set_error(int code, const std::string& msg);
+int last_error_code();
+
+// Returns 0 or sets the thread-local error and returns TFGNN_ERR_CUDA.
+int check_cuda(cudaError_t e, const char* what, const char* file, int line);
+#define TFGNN_CUDA(expr)                                                        \
+  do {                                                                          \
+    int _rc = ::tfgnn::check_cuda((expr), #expr, __FILE__, __LINE__);           \
+    if (_rc) return _rc;                                                        \
+  } while (0)
+#define TFGNN_LAUNCH_CHECK()                                                    \
+  do {                                                                          \
+    ::tfgnn::g_launch_count.fetch_add(1, std::memory_order_relaxed);            \
+    TFGNN_CUDA(cudaGetLastError());                                             \
+  } while (0)
+#define TFGNN_REQUIRE(cond, msg)                                                \
+  do {                                                                          \
+    if (!(cond)) {                                                              \
+      ::tfgnn::set_error(TFGNN_ERR_INVALID_ARGUMENT, std::string(msg));         \
+      return TFGNN_ERR_INVALID_ARGUMENT;                                        \
+    }                                                                           \
+  } while (0)
+
+// Activation table (tf2_gnn/utils/param_helpers.py:22-42).  tanhf/expm1f are the accurate
+// libdevice versions: parity target is 1e-5 relative to the fp32 reference.
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case TFGNN_ACT_RELU: return fmaxf(x, 0.0f);
+    case TFGNN_ACT_TANH: return tanhf(x);
+    case TFGNN_ACT_LEAKY_RELU: return x > 0.0f ? x : kLeakyReluAlpha * x;
+    case TFGNN_ACT_ELU: return x > 0.0f ? x : expm1f(x);
+    case TFGNN_ACT_SELU: return kSeluScale * (x > 0.0f ? x : kSeluAlpha * expm1f(x));
+    case TFGNN_ACT_GELU: {
+      // tf2_gnn/utils/activation.py:7-14 (tanh approximation)
+      const float c = 0.7978845608028654f;  // sqrt(2/pi)
+      float cdf = 0.5f * (1.0f + tanhf(c * (x + 0.044715f * x * x * x)));
+      return x * cdf;
+    }
+    default: return x;
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ float apply_act_t(float x) {
+  return apply_act(x, ACT);
+}
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+struct PtrTable {
+  const void* p[TFGNN_MAX_EDGE_TYPES];
+};
+struct CountTable {
+  long long n[TFGNN_MAX_EDGE_TYPES];
+};
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace tfgnn
+
+// The opaque batch (see include/tfgnn_b200.h).  Keyed CSR: segment s = l*V + v holds the
+// sources of all type-l edges into v, so c[l,v] = row_ptr[s+1]-row_ptr[s].
+struct tfgnn_batch {
+  long long V = 0;
+  int L = 0;
+  long long M_in = 0;     // edges handed in
+  int device = 0;
+  int32_t* row_ptr = nullptr;     // [L*V+1]
+  int32_t* src_sorted = nullptr;  // [M_in] (first row_ptr[L*V] entries valid)
+  int32_t* invalid_count = nullptr;
+  // caller-owned adjacency (kept for the TFGNN_PATH_ATOMIC evidence path only)
+  const int32_t* adj[TFGNN_MAX_EDGE_TYPES] = {};
+  long long E[TFGNN_MAX_EDGE_TYPES] = {};
+  // grow-only scratch owned by the batch
+  void* scratch[16] = {};
+  size_t scratch_bytes[16] = {};
+};
+
+namespace tfgnn {
+// Returns a device scratch buffer of at least `bytes` in slot `slot` of the batch.
+int batch_scratch(tfgnn_batch* b, int slot, size_t bytes, void** out);
+}  // namespace tfgnn

@@ -1,0 +1,36 @@
+#pragma once
+#include "common.cuh"
+
+namespace tfgnn {
+
+// Epilogue of the node-level contractions: out = act( rownorm(v) * (A B)[v,:] + bias ).
+struct GemmEpilogue {
+  int act = TFGNN_ACT_NONE;
+  const float* bias = nullptr;   // [N] or null
+  // per-row normalisation for mean / sqrt_n aggregation (counts over all edge types of the CSR)
+  const int* row_ptr = nullptr;
+  int V = 0, L = 0;
+  int row_norm = 0;  // 0 none, 1 mean (/max(cnt,1)), 2 sqrt_n (/sqrt(max(cnt,1)))
+};
+
+// fp32 SIMT GEMM, any shape / alignment (universal fallback).  C[M,N] = epi(A[M,K] B[K,N]).
+int launch_gemm_simt(const float* A, int lda, const float* B, int ldb, float* C, int ldc, long long M,
+                     int N, int K, const GemmEpilogue& epi, cudaStream_t st);
+
+// 3xTF32 tcgen05 GEMM (sm_100a tensor cores, fp32-level accuracy).  Requirements are checked by
+// gemm_tc_supported(); B is given K-major-packed by pack_weights_tc (see gemm_tc.cu).
+bool gemm_tc_supported(long long M, int N, int K, const float* A, int lda, const float* C, int ldc);
+size_t gemm_tc_packed_bytes(int N, int K);
+int launch_pack_weights_tc(const float* B, int ldb, int K, int N, float* packed, cudaStream_t st);
+int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int ldc, long long M, int N,
+                   int K, const GemmEpilogue& epi, cudaStream_t st);
+
+// Weight packing helpers: gather per-type matrices into one node-level operand.
+//  vertical:   dst[(blk*rows + r), :] = src_blk[row0 + r, :]          (aggregate-then-transform)
+//  horizontal: dst[r, blk*cols + c]  = src_blk[row0 + r, c]           (transform-then-aggregate)
+int launch_pack_vertical(const PtrTable& src, int nblk, int row0, int rows, int cols, int ld_src, float* dst,
+                         int ld_dst, int dst_row0, cudaStream_t st);
+int launch_pack_horizontal(const PtrTable& src, int nblk, int row0, int rows, int cols, int ld_src, float* dst,
+                           int ld_dst, cudaStream_t st);
+
+}  // namespace tfgnn

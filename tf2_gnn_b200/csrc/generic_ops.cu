@@ -1,0 +1,134 @@
+// The three stock ops of the reference's generic MessagePassing.call as stand-alone kernels, for
+// user-defined _message_function plugins and the literal per-edge path:
+//   gather_rows              = tf.nn.embedding_lookup             (message_passing.py:197-206)
+//   unsorted_segment_reduce  = tf.math.unsorted_segment_{sum,mean,max,sqrt_n} (:172-174)
+//   activation               = get_activation_function(name)      (:169-177)
+#include "common.cuh"
+
+namespace tfgnn {
+
+__global__ void gather_rows_kernel(const float* __restrict__ table, long long num_rows, int D,
+                                   const int* __restrict__ ids, long long ids_stride, long long n,
+                                   float* __restrict__ out, int vec) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long num_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long e = warp; e < n; e += num_warps) {
+    const int id = __ldg(ids + e * ids_stride);
+    const bool ok = (unsigned)id < (unsigned long long)num_rows;
+    const float* row = table + (long long)(ok ? id : 0) * D;
+    float* o = out + e * D;
+    if (vec) {
+      for (int c = lane * 4; c < D; c += 128) {
+        float4 v = ok ? ldg_f4(row + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(o + c) = v;
+      }
+    } else {
+      for (int c = lane; c < D; c += 32) o[c] = ok ? __ldg(row + c) : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float val) {
+  // total order trick: positive floats compare like ints, negative floats reversed as uints
+  if (val >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(val));
+  else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(val));
+}
+
+__global__ void fill_kernel(float* __restrict__ out, long long n, float v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = v;
+}
+
+__global__ void segment_scatter_kernel(const float* __restrict__ data, const int* __restrict__ ids,
+                                       long long ids_stride, long long M, int H, long long num_segments,
+                                       int use_max, float* __restrict__ out, int* __restrict__ counts) {
+  const long long total = M * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / H;
+    const int c = (int)(i - m * H);
+    const int seg = __ldg(ids + m * ids_stride);
+    if ((unsigned)seg >= (unsigned long long)num_segments) continue;  // TF drops out-of-range ids on GPU
+    const float v = data[i];
+    if (use_max) atomic_max_float(out + (long long)seg * H + c, v);
+    else atomicAdd(out + (long long)seg * H + c, v);
+    if (counts && c == 0) atomicAdd(counts + seg, 1);
+  }
+}
+
+__global__ void segment_norm_kernel(float* __restrict__ out, const int* __restrict__ counts,
+                                    long long num_segments, int H, int mode) {
+  const long long total = num_segments * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float n = (float)max(counts[i / H], 1);
+    out[i] = out[i] / (mode == 1 ? n : sqrtf(n));
+  }
+}
+
+__global__ void activation_kernel(const float* __restrict__ x, long long n, int act, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = apply_act(x[i], act);
+}
+
+static int grid_for(long long n, int cap = 148 * 32) {
+  int b = ceil_div(n, 256);
+  return b < 1 ? 1 : (b > cap ? cap : b);
+}
+
+}  // namespace tfgnn
+
+using namespace tfgnn;
+
+extern "C" int tfgnn_b200_gather_rows(const float* table, int64_t num_rows, int32_t D, const int32_t* ids,
+                                      int64_t ids_stride, int64_t n, float* out, void* stream) {
+  TFGNN_REQUIRE(D > 0 && n >= 0 && num_rows >= 0 && ids_stride >= 1, "bad gather_rows arguments");
+  if (n == 0) return 0;
+  TFGNN_REQUIRE(table && ids && out, "NULL pointer");
+  const int vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  gather_rows_kernel<<<grid_for(n * 32), 256, 0, (cudaStream_t)stream>>>(table, num_rows, D, ids, ids_stride, n, out, vec);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tfgnn_b200_unsorted_segment_reduce(const float* data, const int32_t* segment_ids, int64_t ids_stride,
+                                                  int64_t M, int32_t H, int64_t num_segments, int32_t aggregation,
+                                                  float* out, void* stream) {
+  TFGNN_REQUIRE(H > 0 && M >= 0 && num_segments >= 0 && ids_stride >= 1, "bad segment_reduce arguments");
+  TFGNN_REQUIRE(aggregation >= TFGNN_AGG_SUM && aggregation <= TFGNN_AGG_SQRT_N, "unknown aggregation code");
+  if (num_segments == 0) return 0;
+  TFGNN_REQUIRE(out != nullptr, "out is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool use_max = aggregation == TFGNN_AGG_MAX;
+  const bool need_counts = aggregation == TFGNN_AGG_MEAN || aggregation == TFGNN_AGG_SQRT_N;
+  fill_kernel<<<grid_for(num_segments * H), 256, 0, st>>>(out, num_segments * H, use_max ? kLowestFloat : 0.f);
+  TFGNN_LAUNCH_CHECK();
+  int* counts = nullptr;
+  if (need_counts) {
+    TFGNN_CUDA(cudaMallocAsync(&counts, (size_t)num_segments * sizeof(int), st));
+    TFGNN_CUDA(cudaMemsetAsync(counts, 0, (size_t)num_segments * sizeof(int), st));
+  }
+  if (M > 0) {
+    TFGNN_REQUIRE(data && segment_ids, "NULL pointer");
+    segment_scatter_kernel<<<grid_for(M * H), 256, 0, st>>>(data, segment_ids, ids_stride, M, H, num_segments,
+                                                          use_max, out, counts);
+    TFGNN_LAUNCH_CHECK();
+  }
+  if (need_counts) {
+    segment_norm_kernel<<<grid_for(num_segments * H), 256, 0, st>>>(out, counts, num_segments, H,
+                                                                   aggregation == TFGNN_AGG_MEAN ? 1 : 2);
+    TFGNN_LAUNCH_CHECK();
+    TFGNN_CUDA(cudaFreeAsync(counts, st));
+  }
+  return 0;
+}
+
+extern "C" int tfgnn_b200_activation(const float* x, int64_t n, int32_t activation, float* out, void* stream) {
+  TFGNN_REQUIRE(n >= 0 && activation >= TFGNN_ACT_NONE && activation <= TFGNN_ACT_GELU, "bad activation arguments");
+  if (n == 0) return 0;
+  TFGNN_REQUIRE(x && out, "NULL pointer");
+  activation_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, n, activation, out);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}

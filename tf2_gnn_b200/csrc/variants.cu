@@ -1,0 +1,177 @@
+// GGNN / RGIN / GNN-FiLM / RGAT entry points: compositions of the edge-level and node-level kernels.
+#include "layers.cuh"
+
+namespace tfgnn {
+
+// Keras GRUCell, reset_after=True (ggnn.py:84-87): gx = agg K + b0, gh = h U + b1 (both [V,3H]),
+// z = sigmoid(gx_z+gh_z), r = sigmoid(gx_r+gh_r), hh = tanh(gx_h + r*gh_h), h' = z*h + (1-z)*hh.
+__global__ void gru_gate_kernel(const float* __restrict__ gx, const float* __restrict__ gh,
+                                const float* __restrict__ h, int ldh, long long V, int H,
+                                float* __restrict__ out) {
+  const long long total = V * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i / H;
+    const int c = (int)(i - v * H);
+    const float* x = gx + v * 3 * H;
+    const float* r_ = gh + v * 3 * H;
+    const float z = 1.0f / (1.0f + expf(-(x[c] + r_[c])));
+    const float r = 1.0f / (1.0f + expf(-(x[H + c] + r_[H + c])));
+    const float hh = tanhf(x[2 * H + c] + r * r_[2 * H + c]);
+    const float hp = h[v * ldh + c];
+    out[i] = z * hp + (1.0f - z) * hh;
+  }
+}
+
+}  // namespace tfgnn
+
+using namespace tfgnn;
+
+extern "C" int tfgnn_b200_ggnn_fwd(tfgnn_batch_t* b, const float* h, int32_t D, const float* const* mlp_weights,
+                                   int32_t num_hidden_layers, int32_t H, uint32_t flags, int32_t aggregation,
+                                   const float* gru_kernel, const float* gru_recurrent_kernel,
+                                   const float* gru_bias, int32_t path, float* out, void* stream) {
+  TFGNN_REQUIRE(b != nullptr, "batch is NULL");
+  TFGNN_REQUIRE(D == H, "GGNN needs node embedding dimension == hidden_dim (ggnn.py:30)");
+  const long long V = b->V;
+  if (V == 0) return 0;
+  TFGNN_REQUIRE(gru_kernel && gru_recurrent_kernel && gru_bias, "GRU weight pointer is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  void *agg = nullptr, *gx = nullptr, *gh = nullptr;
+  int rc = batch_scratch(b, 8, (size_t)V * H * sizeof(float), &agg);
+  if (rc) return rc;
+  rc = batch_scratch(b, 9, (size_t)V * 3 * H * sizeof(float), &gx);
+  if (rc) return rc;
+  rc = batch_scratch(b, 10, (size_t)V * 3 * H * sizeof(float), &gh);
+  if (rc) return rc;
+  // ggnn.py:68-89: aggregation of the messages, no activation (act_before is ignored too).
+  rc = edge_mlp_core(b, h, D, mlp_weights, num_hidden_layers, H, flags & ~TFGNN_FLAG_ACT_BEFORE_AGGREGATION,
+                     aggregation, TFGNN_ACT_NONE, path, (float*)agg, H, st);
+  if (rc) return rc;
+  GemmEpilogue ex, eh;
+  ex.bias = gru_bias;
+  eh.bias = gru_bias + 3 * H;
+  rc = node_gemm((const float*)agg, H, gru_kernel, 3 * H, (float*)gx, 3 * H, V, 3 * H, H, ex, path, b, 6, st);
+  if (rc) return rc;
+  rc = node_gemm(h, D, gru_recurrent_kernel, 3 * H, (float*)gh, 3 * H, V, 3 * H, H, eh, path, b, 6, st);
+  if (rc) return rc;
+  int blocks = ceil_div(V * H, 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  gru_gate_kernel<<<blocks, 256, 0, st>>>((const float*)gx, (const float*)gh, h, D, V, H, out);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tfgnn_b200_rgin_fwd(tfgnn_batch_t* b, const float* h, int32_t D, const float* const* mlp_weights,
+                                   int32_t num_hidden_layers, int32_t H, uint32_t flags, int32_t aggregation,
+                                   int32_t activation, const float* const* aggr_weights, int32_t num_aggr_layers,
+                                   int32_t path, float* out, void* stream) {
+  TFGNN_REQUIRE(b != nullptr, "batch is NULL");
+  TFGNN_REQUIRE(num_aggr_layers >= 0, "num_aggr_layers must be >= 0");
+  TFGNN_REQUIRE(valid_act(activation), "unknown activation code");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long V = b->V;
+  // rgin.py:88-106: aggregate, optional MLP, then the activation (activation-before is ignored).
+  flags &= ~TFGNN_FLAG_ACT_BEFORE_AGGREGATION;
+  if (num_aggr_layers == 0)
+    return edge_mlp_core(b, h, D, mlp_weights, num_hidden_layers, H, flags, aggregation, activation, path, out, H,
+                         st);
+  TFGNN_REQUIRE(aggr_weights != nullptr, "aggr_weights is NULL");
+  if (V == 0) return 0;
+  void *t0 = nullptr, *t1 = nullptr;
+  int rc = batch_scratch(b, 8, (size_t)V * H * sizeof(float), &t0);
+  if (rc) return rc;
+  rc = batch_scratch(b, 9, (size_t)V * H * sizeof(float), &t1);
+  if (rc) return rc;
+  rc = edge_mlp_core(b, h, D, mlp_weights, num_hidden_layers, H, flags, aggregation, TFGNN_ACT_NONE, path,
+                     (float*)t0, H, st);
+  if (rc) return rc;
+  float* cur = (float*)t0;
+  float* nxt = (float*)t1;
+  for (int i = 0; i < num_aggr_layers; ++i) {
+    TFGNN_REQUIRE(aggr_weights[i] != nullptr, "an aggregation MLP weight pointer is NULL");
+    const bool last = i == num_aggr_layers - 1;
+    GemmEpilogue epi;
+    epi.act = last ? activation : TFGNN_ACT_RELU;
+    float* dst = last ? out : nxt;
+    rc = node_gemm(cur, H, aggr_weights[i], H, dst, H, V, H, H, epi, path, b, 6, st);
+    if (rc) return rc;
+    float* t = cur; cur = nxt; nxt = t;
+    if (!last) cur = dst;
+  }
+  return 0;
+}
+
+extern "C" int tfgnn_b200_film_fwd(tfgnn_batch_t* b, const float* h, int32_t D, const float* const* mlp_weights,
+                                   int32_t num_hidden_layers, const float* const* film_weights, int32_t H,
+                                   uint32_t flags, int32_t aggregation, int32_t activation, int32_t path,
+                                   float* out, void* stream) {
+  TFGNN_REQUIRE(b != nullptr, "batch is NULL");
+  TFGNN_REQUIRE(D > 0 && H > 0, "D and H must be positive");
+  TFGNN_REQUIRE(valid_act(activation) && valid_agg(aggregation), "unknown activation / aggregation code");
+  const int V = (int)b->V, L = b->L;
+  if (V == 0) return 0;
+  if (L == 0)
+    return edge_mlp_core(b, h, D, mlp_weights, 0, H, flags, aggregation, activation, path, out, H,
+                         (cudaStream_t)stream);
+  TFGNN_REQUIRE(mlp_weights && film_weights, "weight table is NULL");
+  if (num_hidden_layers != 0)
+    return unsupported("GNN-FiLM with hidden layers in the edge MLP needs the per-edge literal path (not built yet)");
+  if (path == TFGNN_PATH_ATOMIC) return unsupported("TFGNN_PATH_ATOMIC is not available for GNN-FiLM");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool normalize = flags & TFGNN_FLAG_NORMALIZE_BY_NUM_INCOMING;
+  const bool act_before = flags & TFGNN_FLAG_ACT_BEFORE_AGGREGATION;
+  const bool use_target = flags & TFGNN_FLAG_USE_TARGET_STATE;
+  const int LH = L * H;
+  PtrTable first{}, film{};
+  for (int l = 0; l < L; ++l) {
+    TFGNN_REQUIRE(mlp_weights[l] && film_weights[l], "a weight pointer is NULL");
+    first.p[l] = mlp_weights[l];
+    film.p[l] = film_weights[l];
+  }
+  void *P = nullptr, *Tt = nullptr, *Wcat = nullptr, *FB = nullptr, *Fcat = nullptr;
+  int rc = batch_scratch(b, 2, (size_t)V * LH * sizeof(float), &P);
+  if (rc) return rc;
+  rc = batch_scratch(b, 3, (size_t)D * LH * sizeof(float), &Wcat);
+  if (rc) return rc;
+  rc = batch_scratch(b, 11, (size_t)V * 2 * LH * sizeof(float), &FB);
+  if (rc) return rc;
+  rc = batch_scratch(b, 12, (size_t)D * 2 * LH * sizeof(float), &Fcat);
+  if (rc) return rc;
+  GemmEpilogue none;
+  // projected source messages P_l = h W^s_l  (gnn_edge_mlp.py:100 hoisted to node level)
+  rc = launch_pack_horizontal(first, L, 0, D, H, H, (float*)Wcat, LH, st);
+  if (rc) return rc;
+  rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)P, LH, V, LH, D, none, path, b, 6, st);
+  if (rc) return rc;
+  if (use_target) {
+    rc = batch_scratch(b, 4, (size_t)V * LH * sizeof(float), &Tt);
+    if (rc) return rc;
+    rc = launch_pack_horizontal(first, L, D, D, H, H, (float*)Wcat, LH, st);
+    if (rc) return rc;
+    rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)Tt, LH, V, LH, D, none, path, b, 6, st);
+    if (rc) return rc;
+  }
+  // FiLM parameters [gamma_l | beta_l] = h F_l depend on (target, type) only (gnn_film.py:99-103)
+  rc = launch_pack_horizontal(film, L, 0, D, 2 * H, 2 * H, (float*)Fcat, 2 * LH, st);
+  if (rc) return rc;
+  rc = node_gemm(h, D, (const float*)Fcat, 2 * LH, (float*)FB, 2 * LH, V, 2 * LH, D, none, path, b, 6, st);
+  if (rc) return rc;
+  EdgeReduceParams p;
+  p.X = (const float*)P; p.ldx = LH; p.x_type_stride = H;
+  p.T = (const float*)Tt; p.ldt = LH; p.t_type_stride = H;
+  p.G = (const float*)FB; p.ldg = 2 * LH; p.g_type_stride = 2 * H; p.beta_off = H;
+  p.row_ptr = b->row_ptr; p.src = b->src_sorted;
+  p.out = out; p.ldo = H; p.V = V; p.L = L; p.C = H;
+  p.normalize = normalize;
+  p.edge_act = act_before ? activation : TFGNN_ACT_NONE;
+  p.reduce_max = aggregation == TFGNN_AGG_MAX;
+  p.row_norm = agg_row_norm(aggregation);
+  p.final_act = act_before ? TFGNN_ACT_NONE : activation;
+  return launch_edge_reduce(p, /*merged=*/true, st);
+}
+
+extern "C" int tfgnn_b200_rgat_fwd(tfgnn_batch_t*, const float*, int32_t, const float* const*,
+                                   const float* const*, int32_t, int32_t, int32_t, int32_t, float*, void*) {
+  return unsupported("tfgnn_b200_rgat_fwd is not built yet");
+}

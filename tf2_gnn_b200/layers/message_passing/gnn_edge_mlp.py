@@ -1,0 +1,102 @@
+"""GNN_Edge_MLP — mirror of tf2_gnn/layers/message_passing/gnn_edge_mlp.py:12-107 on the B200 path."""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional
+
+import torch
+
+from ... import _ffi
+from ...runtime import PreparedBatch, stream_ptr
+from .message_passing import (MessagePassing, MessagePassingInput, Variable, _last_dim,
+                              register_message_passing_implementation)
+
+
+class EdgeMLP:
+    """Weights of one dpu_utils.tf2utils.MLP(out_size=H, hidden_layers=n, use_biases=False):
+    n hidden Dense(H, relu) + linear Dense(H) (gnn_edge_mlp.py:76-79)."""
+
+    def __init__(self, layer: MessagePassing, scope: str, in_size: int, out_size: int, hidden_layers):
+        sizes = [out_size] * hidden_layers if isinstance(hidden_layers, int) else list(hidden_layers)
+        dims = [in_size] + sizes + [out_size]
+        self.layers: List[Variable] = []
+        for i in range(len(dims) - 1):
+            lname = "dense_out" if i == len(dims) - 2 else f"dense_{i}"
+            self.layers.append(layer.add_weight(f"{scope}/MLP/{lname}/kernel:0", (dims[i], dims[i + 1])))
+
+    @property
+    def num_hidden_layers(self) -> int:
+        return len(self.layers) - 1
+
+
+@register_message_passing_implementation
+class GNN_Edge_MLP(MessagePassing):
+    """h'_v = sum_l sum_{(u,v) in A_l} sigma(1/c_{v,l} * MLP_l(h_u || h_v))  (gnn_edge_mlp.py:13-44)."""
+
+    @classmethod
+    def get_default_hyperparameters(cls):
+        these_hypers = {
+            "use_target_state_as_input": True,
+            "normalize_by_num_incoming": False,
+            "num_edge_MLP_hidden_layers": 1,
+        }
+        mp_hypers = super().get_default_hyperparameters()
+        mp_hypers.update(these_hypers)
+        return mp_hypers
+
+    def __init__(self, params: Dict[str, Any], **kwargs):
+        super().__init__(params, **kwargs)
+        self._use_target_state_as_input = params["use_target_state_as_input"]
+        self._normalize_by_num_incoming = params["normalize_by_num_incoming"]
+        self._num_edge_MLP_hidden_layers = params["num_edge_MLP_hidden_layers"]
+        self._edge_type_mlps: List[EdgeMLP] = []
+
+    def build(self, input_shapes: MessagePassingInput):
+        D = _last_dim(input_shapes.node_embeddings)
+        num_edge_types = len(input_shapes.adjacency_lists)
+        edge_layer_input_size = 2 * D if self._use_target_state_as_input else D
+        for i in range(num_edge_types):
+            self._edge_type_mlps.append(
+                EdgeMLP(self, f"edge_type_{i}", edge_layer_input_size, self._hidden_dim,
+                        self._num_edge_MLP_hidden_layers))
+        super().build(input_shapes)
+
+    # -- C-ABI glue ---------------------------------------------------------------------------
+    def _flags(self) -> int:
+        f = 0
+        if self._normalize_by_num_incoming:
+            f |= _ffi.FLAG_NORMALIZE
+        if self._message_activation_before_aggregation:
+            f |= _ffi.FLAG_ACT_BEFORE_AGG
+        if self._use_target_state_as_input:
+            f |= _ffi.FLAG_USE_TARGET
+        return f
+
+    def _mlp_weight_ptrs(self):
+        tensors = [v.value for mlp in self._edge_type_mlps for v in mlp.layers]
+        return _ffi.ptr_array(tensors), tensors
+
+    def _check_types(self, prepared: PreparedBatch):
+        if prepared.num_edge_types != len(self._edge_type_mlps):
+            raise ValueError(f"layer was built for {len(self._edge_type_mlps)} edge types, "
+                             f"got {prepared.num_edge_types} adjacency lists")
+
+    def call(self, inputs: MessagePassingInput, training: bool = False,
+             prepared: Optional[PreparedBatch] = None):
+        h, prepared = self._device_inputs(inputs, prepared)
+        self._check_types(prepared)
+        out = torch.empty((h.shape[0], self._hidden_dim), dtype=torch.float32, device=h.device)
+        ptrs, _keep = self._mlp_weight_ptrs()
+        _ffi.check(_ffi.lib().tfgnn_b200_edge_mlp_fwd(
+            prepared.handle, h.data_ptr(), int(h.shape[1]), ptrs, int(self._num_edge_MLP_hidden_layers),
+            self._hidden_dim, self._flags(), self._aggregation_fn.code, self._activation_fn.code,
+            _ffi.PATH[self._path], out.data_ptr(), stream_ptr()))
+        return out
+
+    def _message_function(self, edge_source_states, edge_target_states, num_incoming_to_node_per_message,
+                          edge_type_idx: int, training: bool):
+        raise NotImplementedError("built-in layers run fused; _message_function is only a plugin hook")
+
+    def set_weights_from_oracle_dict(self, w: Dict[str, Any]) -> None:
+        for mlp, mats in zip(self._edge_type_mlps, w["edge_mlps"]):
+            for var, m in zip(mlp.layers, mats):
+                var.assign(m)
