@@ -307,6 +307,17 @@ def test_film_parity(use_target, act_before, agg):
     run_case("gnn_film", p, V, D, L, adjs)
 
 
+@pytest.mark.parametrize("V,D,H,K,L,E", [(5, 3, 12, 3, 3, 3), (400, 64, 64, 4, 3, 3000), (300, 32, 36, 3, 2, 2000),
+                                         (1000, 128, 128, 4, 3, 8000)])
+def test_rgat_parity(V, D, H, K, L, E):
+    _need_gpu()
+    rng = np.random.default_rng(V + H)
+    adjs = random_graph(rng, V, L, E, hub=V > 100, dups=True)
+    p = mo.default_hyperparameters("rgat")
+    p.update(hidden_dim=H, num_heads=K, message_activation_function="tanh")
+    run_case("rgat", p, V, D, L, adjs)
+
+
 # ------------------------------------------------------------------------------------------
 # Node-level dense and error behaviour
 # ------------------------------------------------------------------------------------------
@@ -323,6 +334,25 @@ def test_dense_fwd(V, K, N):
     _ffi.check(_ffi.lib().tfgnn_b200_dense_fwd(xt.data_ptr(), wt.data_ptr(), out.data_ptr(), V, K, N,
                                                 _ffi.ACT["tanh"], 0, stream_ptr()))
     assert_states_close(out.cpu().numpy(), np.tanh(x.astype(np.float64) @ w.astype(np.float64)))
+
+
+@pytest.mark.parametrize("V,K,N", [(128, 32, 64), (129, 64, 16), (1000, 320, 320), (300, 1024, 256),
+                                   (5000, 960, 320), (500, 100, 48), (70000, 256, 1024)])
+def test_dense_fwd_tensor_core_3xtf32(V, K, N):
+    """tcgen05 3xTF32 GEMM keeps fp32-level accuracy (plain TF32 would be ~1e-3)."""
+    _need_gpu()
+    from tf2_gnn_b200 import _ffi
+    from tf2_gnn_b200.runtime import stream_ptr
+    rng = np.random.default_rng(V + K)
+    x = rng.uniform(-1, 1, (V, K)).astype(np.float32)
+    w = rng.uniform(-0.3, 0.3, (K, N)).astype(np.float32)
+    xt, wt = torch.from_numpy(x).cuda(), torch.from_numpy(w).cuda()
+    out = torch.full((V, N), float("nan"), dtype=torch.float32, device="cuda")
+    _ffi.check(_ffi.lib().tfgnn_b200_dense_fwd(xt.data_ptr(), wt.data_ptr(), out.data_ptr(), V, K, N,
+                                                _ffi.ACT["relu"], _ffi.PATH["sorted_tc"], stream_ptr()))
+    torch.cuda.synchronize()
+    ref = np.maximum(x.astype(np.float64) @ w.astype(np.float64), 0.0)
+    assert_states_close(out.cpu().numpy(), ref, tol=2e-6)
 
 
 def test_unknown_names_raise_like_the_reference():

@@ -171,7 +171,140 @@ extern "C" int tfgnn_b200_film_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   return launch_edge_reduce(p, /*merged=*/true, st);
 }
 
-extern "C" int tfgnn_b200_rgat_fwd(tfgnn_batch_t*, const float*, int32_t, const float* const*,
-                                   const float* const*, int32_t, int32_t, int32_t, int32_t, float*, void*) {
-  return unsupported("tfgnn_b200_rgat_fwd is not built yet");
+namespace tfgnn {
+
+// Node-level attention score halves (rgat.py:111-121 split by linearity of the einsum):
+//   s_src[v,l,k] = a_l[k,:d] . P_l[v,k,:]      s_tgt[v,l,k] = a_l[k,d:] . P_l[v,k,:]
+// so the per-edge score is leaky_relu(s_src[src] + s_tgt[tgt]).
+__global__ void rgat_scores_kernel(const float* __restrict__ P, long long V, int L, int K, int d, PtrTable att,
+                                   float* __restrict__ s_src, float* __restrict__ s_tgt) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = V * L * K;
+  if (idx >= total) return;
+  const int k = (int)(idx % K);
+  const int l = (int)((idx / K) % L);
+  const long long v = idx / ((long long)K * L);
+  const float* a = reinterpret_cast<const float*>(att.p[l]) + (long long)k * 2 * d;
+  const float* p = P + v * (long long)(L * K * d) + (long long)l * K * d + (long long)k * d;
+  float ss = 0.f, st = 0.f;
+  for (int i = 0; i < d; ++i) {
+    const float x = p[i];
+    ss = fmaf(a[i], x, ss);
+    st = fmaf(a[d + i], x, st);
+  }
+  s_src[idx] = ss;
+  s_tgt[idx] = st;
+}
+
+__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeakyReluAlpha * x; }
+
+// One thread per (target v, output column c): segment softmax over ALL incoming edges of v (all
+// types jointly, rgat.py:135-151) for head k = c/d, then the weighted sum of P_l[src, c].
+// Two passes over the node's CSR segments: running max, then exp-sum and weighted accumulate.
+// VEC: 4 columns per thread (needs d % 4 == 0).
+template <bool VEC>
+__global__ void rgat_aggregate_kernel(const float* __restrict__ P, const float* __restrict__ s_src,
+                                      const float* __restrict__ s_tgt, const int* __restrict__ row_ptr,
+                                      const int* __restrict__ src, long long V, int L, int K, int d, int act,
+                                      float* __restrict__ out) {
+  const int H = K * d;
+  const int cols = VEC ? H / 4 : H;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= V * cols) return;
+  const long long v = idx / cols;
+  const int c = (int)(idx % cols) * (VEC ? 4 : 1);
+  const int k = c / d;
+  const long long LK = (long long)L * K, LH = (long long)L * H;
+  float m = kLowestFloat;
+  for (int l = 0; l < L; ++l) {
+    const long long seg = (long long)l * V + v;
+    const int beg = __ldg(row_ptr + seg), end = __ldg(row_ptr + seg + 1);
+    const float st = __ldg(s_tgt + v * LK + l * K + k);
+    for (int e = beg; e < end; ++e)
+      m = fmaxf(m, leaky(__ldg(s_src + (long long)__ldg(src + e) * LK + l * K + k) + st));
+  }
+  float den = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int l = 0; l < L; ++l) {
+    const long long seg = (long long)l * V + v;
+    const int beg = __ldg(row_ptr + seg), end = __ldg(row_ptr + seg + 1);
+    const float st = __ldg(s_tgt + v * LK + l * K + k);
+    for (int e = beg; e < end; ++e) {
+      const long long u = __ldg(src + e);
+      const float w = expf(leaky(__ldg(s_src + u * LK + l * K + k) + st) - m);
+      den += w;
+      const float* prow = P + u * LH + (long long)l * H + c;
+      if (VEC) {
+        const float4 x = ldg_f4(prow);
+        acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y);
+        acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
+      } else {
+        acc.x = fmaf(w, __ldg(prow), acc.x);
+      }
+    }
+  }
+  const float inv = den > 0.f ? 1.0f / den : 0.f;
+  float* o = out + v * H + c;
+  if (VEC) {
+    *reinterpret_cast<float4*>(o) = make_float4(apply_act(acc.x * inv, act), apply_act(acc.y * inv, act),
+                                                apply_act(acc.z * inv, act), apply_act(acc.w * inv, act));
+  } else {
+    o[0] = apply_act(acc.x * inv, act);
+  }
+}
+
+}  // namespace tfgnn
+
+extern "C" int tfgnn_b200_rgat_fwd(tfgnn_batch_t* b, const float* h, int32_t D, const float* const* W,
+                                   const float* const* attention, int32_t H, int32_t num_heads,
+                                   int32_t activation, int32_t path, float* out, void* stream) {
+  TFGNN_REQUIRE(b != nullptr, "batch is NULL");
+  TFGNN_REQUIRE(D > 0 && H > 0 && num_heads > 0, "D, H and num_heads must be positive");
+  TFGNN_REQUIRE(H % num_heads == 0, "hidden_dim must be divisible by num_heads (rgat.py:72)");
+  TFGNN_REQUIRE(valid_act(activation), "unknown activation code");
+  const long long V = b->V;
+  const int L = b->L, K = num_heads, d = H / num_heads;
+  if (V == 0) return 0;
+  TFGNN_REQUIRE(h && out, "h / out is NULL");
+  if (path == TFGNN_PATH_ATOMIC) return unsupported("TFGNN_PATH_ATOMIC is not available for RGAT");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int LH = L * H;
+  PtrTable wt{}, at{};
+  for (int l = 0; l < L; ++l) {
+    TFGNN_REQUIRE(W && attention && W[l] && attention[l], "a weight pointer is NULL");
+    wt.p[l] = W[l];
+    at.p[l] = attention[l];
+  }
+  void *P = nullptr, *Wcat = nullptr, *ss = nullptr, *stt = nullptr;
+  int rc;
+  if (L > 0) {
+    rc = batch_scratch(b, 2, (size_t)V * LH * sizeof(float), &P);
+    if (rc) return rc;
+    rc = batch_scratch(b, 3, (size_t)D * LH * sizeof(float), &Wcat);
+    if (rc) return rc;
+    rc = batch_scratch(b, 13, (size_t)V * L * K * sizeof(float), &ss);
+    if (rc) return rc;
+    rc = batch_scratch(b, 14, (size_t)V * L * K * sizeof(float), &stt);
+    if (rc) return rc;
+    // P_l = h W_l for every node once (rgat.py:102-109 applies the same Dense to source and target rows)
+    rc = launch_pack_horizontal(wt, L, 0, D, H, H, (float*)Wcat, LH, st);
+    if (rc) return rc;
+    GemmEpilogue none;
+    rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)P, LH, V, LH, D, none, path, b, 6, st);
+    if (rc) return rc;
+    const long long total = V * L * K;
+    rgat_scores_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)P, V, L, K, d, at, (float*)ss,
+                                                            (float*)stt);
+    TFGNN_LAUNCH_CHECK();
+  }
+  const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const long long threads = V * (vec ? H / 4 : H);
+  if (vec)
+    rgat_aggregate_kernel<true><<<ceil_div(threads, 128), 128, 0, st>>>(
+        (const float*)P, (const float*)ss, (const float*)stt, b->row_ptr, b->src_sorted, V, L, K, d, activation, out);
+  else
+    rgat_aggregate_kernel<false><<<ceil_div(threads, 128), 128, 0, st>>>(
+        (const float*)P, (const float*)ss, (const float*)stt, b->row_ptr, b->src_sorted, V, L, K, d, activation, out);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
 }

@@ -53,6 +53,9 @@ def to_device_adj(a, device: Optional[torch.device] = None) -> torch.Tensor:
         t = torch.from_dlpack(a)
     else:
         t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.int32).reshape(-1, 2)))
+    if (isinstance(a, torch.Tensor) and a.dtype == torch.int32 and a.device == device and a.dim() == 2
+            and a.shape[1] == 2 and a.is_contiguous()):
+        return a  # same object: lets prepared_batch_for() recognise the tensor across layers / calls
     if t.dtype != torch.int32:
         t = t.to(torch.int32)
     if t.device != device:
