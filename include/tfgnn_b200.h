@@ -165,6 +165,14 @@ int tfgnn_b200_unsorted_segment_reduce(const float* data, const int32_t* segment
                                        void* stream);
 int tfgnn_b200_activation(const float* x, int64_t n, int32_t activation, float* out, void* stream);
 
+/* Node-level glue of GNN._internal_call around the message-passing layers (gnn.py:291-296,317-321):
+ *   residual_average   out = (x + last) / 2                      gnn.py:294-295
+ *   layer_norm         tf.keras.layers.LayerNormalization(axis=-1, epsilon) over each row  gnn.py:318-321
+ * x, last, out: [V, H] contiguous; gamma, beta: [H]. */
+int tfgnn_b200_residual_average(const float* x, const float* last, float* out, int64_t n, void* stream);
+int tfgnn_b200_layer_norm(const float* x, const float* gamma, const float* beta, int64_t V, int32_t H,
+                          float epsilon, float* out, void* stream);
+
 /* Number of kernels this library has launched in the calling process (all threads). */
 int64_t tfgnn_b200_launch_count(void);
 

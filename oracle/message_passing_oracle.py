@@ -371,3 +371,45 @@ def make_weights(kind: str, params: Dict[str, Any], D: int, L: int, rng: np.rand
         w["film_mlps"] = [[glorot_uniform(rng, (s[i], s[i + 1]), dtype)
                            for i in range(len(s) - 1)] for _ in range(L)]
     return w
+
+
+# --------------------------------------------------------------------------------------
+# GNN stack, inference mode (gnn.py:276-329).  Global exchange layers are not restated
+# (disabled by every PPI config: global_exchange_every_num_layers = 10000).
+# --------------------------------------------------------------------------------------
+def layer_norm(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, epsilon: float = 1e-3) -> np.ndarray:
+    """tf.keras.layers.LayerNormalization() defaults (axis=-1, epsilon=1e-3) [external Keras]."""
+    mean = x.mean(axis=-1, keepdims=True)
+    var = ((x - mean) ** 2).mean(axis=-1, keepdims=True)
+    return (x - mean) / np.sqrt(var + x.dtype.type(epsilon)) * gamma + beta
+
+
+def gnn_forward(params: Dict[str, Any], weights: Dict[str, Any], node_features: np.ndarray,
+                adjacency_lists: Sequence[np.ndarray], dtype=np.float32):
+    """weights: {"initial_projection": [F,H], "mp": [per-layer message-passing weight dicts],
+    "dense": {layer_idx: [H,H]}, "layernorm": [(gamma, beta) per layer]}.
+    Returns (final representations, tuple of all representations) like GNN._internal_call."""
+    kind = params["message_calculation_class"].lower()
+    act_init = get_activation_function(params["initial_node_representation_activation"])
+    act_dense = get_activation_function(params["dense_intermediate_layer_activation"])
+    x = np.asarray(node_features, dtype=dtype) @ np.asarray(weights["initial_projection"], dtype=dtype)
+    cur = act_init(x) if act_init is not None else x                      # gnn.py:279
+    last = cur
+    all_reps = [cur]
+    for i in range(int(params["num_layers"])):
+        if i % int(params["residual_every_num_layers"]) == 0:             # gnn.py:291-296
+            tmp = cur
+            if i > 0:
+                cur = (cur + last) / dtype(2)
+            last = tmp
+        cur = message_passing_forward(kind, params, weights["mp"][i], cur, adjacency_lists, dtype=dtype)
+        all_reps.append(cur)                                              # gnn.py:305
+        if i and i % int(params["global_exchange_every_num_layers"]) == 0:
+            raise NotImplementedError("global exchange is outside the restated path")
+        if params["use_inter_layer_layernorm"]:                           # gnn.py:317-321
+            g, b = weights["layernorm"][i]
+            cur = layer_norm(cur, np.asarray(g, dtype=dtype), np.asarray(b, dtype=dtype)).astype(dtype)
+        if i % int(params["dense_every_num_layers"]) == 0:                # gnn.py:324-327
+            y = cur @ np.asarray(weights["dense"][i], dtype=dtype)
+            cur = act_dense(y) if act_dense is not None else y
+    return cur, tuple(all_reps)

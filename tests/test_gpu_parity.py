@@ -198,6 +198,24 @@ def test_rgcn_parity(V, D, H, L, E, opts, path):
     run_case("rgcn", p, V, D, L, adjs, seed=V, path=path)
 
 
+@pytest.mark.parametrize("chunk_rows,V", [(256, 3000), (128, 1000), (None, 160000)])
+def test_rgcn_pipelined_two_stream(chunk_rows, V, monkeypatch):
+    """gather || tensor-core-GEMM pipeline over node chunks (triple-buffered) == oracle."""
+    _need_gpu()
+    if chunk_rows is not None:
+        monkeypatch.setenv("TFGNN_B200_PIPE_CHUNK_ROWS", str(chunk_rows))
+    rng = np.random.default_rng(V)
+    D = H = 64
+    L = 3
+    adjs = random_graph(rng, V, L, V * 3, hub=True, self_loops=True)
+    p = mo.default_hyperparameters("rgcn")
+    p.update(hidden_dim=H, aggregation_function="mean", message_activation_function="tanh")
+    a = run_case("rgcn", p, V, D, L, adjs, seed=2, path="auto")
+    monkeypatch.setenv("TFGNN_B200_PIPE_CHUNK_ROWS", str(1 << 24))   # disables the pipeline
+    b = run_case("rgcn", p, V, D, L, adjs, seed=2, path="sorted_tc")
+    assert_states_close(a.cpu().numpy(), b.cpu().numpy().astype(np.float64), tol=1e-6)
+
+
 def test_rgcn_atomic_path_matches():
     _need_gpu()
     rng = np.random.default_rng(5)
@@ -316,6 +334,51 @@ def test_rgat_parity(V, D, H, K, L, E):
     p = mo.default_hyperparameters("rgat")
     p.update(hidden_dim=H, num_heads=K, message_activation_function="tanh")
     run_case("rgat", p, V, D, L, adjs)
+
+
+@pytest.mark.parametrize("kind,extra", [
+    ("rgcn", dict(dense_every_num_layers=10000, residual_every_num_layers=10000)),          # PPI_RGCN.json shape
+    ("rgcn", dict(use_inter_layer_layernorm=True, message_activation_function="leaky_relu")),  # QM9_RGCN.json
+    ("gnn_film", dict(dense_every_num_layers=1, residual_every_num_layers=2, use_target_state_as_input=True)),
+    ("ggnn", dict(num_layers=3, normalize_by_num_incoming=False, message_activation_function="tanh")),
+])
+def test_gnn_stack_parity(kind, extra):
+    """GNN._internal_call (gnn.py:276-329): projection, residuals, MP layers, LayerNorm, Dense."""
+    _need_gpu()
+    from tf2_gnn_b200.layers import GNN, GNNInput
+    rng = np.random.default_rng(17)
+    V, F, H, L = 600, 50, 64, 3
+    adjs = random_graph(rng, V, L, 4000, self_loops=True)
+    params = GNN.get_default_hyperparameters(kind)
+    params.update(hidden_dim=H, global_exchange_every_num_layers=10000)
+    params.update(extra)
+    feats = rng.uniform(-1, 1, (V, F)).astype(np.float32)
+    gnn = GNN(params)
+    gnn.build(GNNInput((None, F), tuple((None, 2) for _ in range(L)), (None,), ()))
+    w = {"initial_projection": mo.glorot_uniform(rng, (F, H)), "mp": [], "dense": {}, "layernorm": []}
+    gnn._initial_projection_layer.kernel.assign(w["initial_projection"])
+    for i, mp in enumerate(gnn._mp_layers):
+        wi = mo.make_weights(kind, params, H, L, rng)
+        mp.set_weights_from_oracle_dict(wi)
+        w["mp"].append(wi)
+        if params["use_inter_layer_layernorm"]:
+            g, b = rng.uniform(0.5, 1.5, H).astype(np.float32), rng.uniform(-0.2, 0.2, H).astype(np.float32)
+            gnn._inter_layer_layernorms[i].gamma.assign(g)
+            gnn._inter_layer_layernorms[i].beta.assign(b)
+            w["layernorm"].append((g, b))
+        if str(i) in gnn._dense_layers:
+            w["dense"][i] = mo.glorot_uniform(rng, (H, H))
+            gnn._dense_layers[str(i)].kernel.assign(w["dense"][i])
+    inp = GNNInput(torch.from_numpy(feats).cuda(), tuple(torch.from_numpy(a).cuda() for a in adjs),
+                   torch.zeros(V, dtype=torch.int32).cuda(), 1)
+    out, all_reps = gnn(inp, training=False, return_all_representations=True)
+    ref, ref_all = mo.gnn_forward(params, w, feats, adjs, dtype=np.float64)
+    assert len(all_reps) == len(ref_all) == params["num_layers"] + 1
+    assert_states_close(out.cpu().numpy(), ref)
+    for a, b in zip(all_reps, ref_all):
+        assert_states_close(a.cpu().numpy(), b)
+    out2 = gnn(inp)
+    assert np.array_equal(out2.cpu().numpy(), out.cpu().numpy())
 
 
 # ------------------------------------------------------------------------------------------

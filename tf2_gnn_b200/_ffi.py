@@ -28,7 +28,8 @@ EXPORTED_SYMBOLS = (
     "tfgnn_b200_batch_info", "tfgnn_b200_batch_export_csr", "tfgnn_b200_in_degree", "tfgnn_b200_edge_mlp_fwd", "tfgnn_b200_rgcn_fwd",
     "tfgnn_b200_ggnn_fwd", "tfgnn_b200_rgin_fwd", "tfgnn_b200_film_fwd", "tfgnn_b200_rgat_fwd",
     "tfgnn_b200_dense_fwd", "tfgnn_b200_gather_rows", "tfgnn_b200_unsorted_segment_reduce",
-    "tfgnn_b200_activation", "tfgnn_b200_launch_count",
+    "tfgnn_b200_activation", "tfgnn_b200_residual_average", "tfgnn_b200_layer_norm",
+    "tfgnn_b200_launch_count",
 )
 
 _PP = POINTER(c_void_p)
@@ -75,6 +76,8 @@ def lib() -> ctypes.CDLL:
     L.tfgnn_b200_unsorted_segment_reduce.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int64,
                                                      c_int32, c_void_p, c_void_p]
     L.tfgnn_b200_activation.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    L.tfgnn_b200_residual_average.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+    L.tfgnn_b200_layer_norm.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is ctypes.c_int and name not in ("tfgnn_b200_abi_version",):

@@ -9,6 +9,7 @@
 //   transform-then-aggregate  P = h [W_0|..|W_{L-1}];  out[v] = agg_{l,e} f(P_l[src_e], v, l)
 //     for max-aggregation / activation-before-aggregation (per-edge non-linearity).
 //   hoisted hidden layer      A_l[v] = scale * sum_e relu(U^s_l h_u + U^t_l h_v); out = act(A W2cat)
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -62,6 +63,84 @@ int node_gemm(const float* A, int lda, const float* B, int ldb, float* C, int ld
   return launch_gemm_simt(A, lda, B, ldb, C, ldc, M, N, K, epi, st);
 }
 
+static int pipeline_init(tfgnn_batch* b) {
+  if (b->pipe_ready) return 0;
+  int lo = 0, hi = 0;
+  TFGNN_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  TFGNN_CUDA(cudaStreamCreateWithPriority(&b->pipe_gather, cudaStreamNonBlocking, lo));
+  TFGNN_CUDA(cudaStreamCreateWithPriority(&b->pipe_gemm, cudaStreamNonBlocking, hi));
+  TFGNN_CUDA(cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming));
+  TFGNN_CUDA(cudaEventCreateWithFlags(&b->ev_join_g, cudaEventDisableTiming));
+  TFGNN_CUDA(cudaEventCreateWithFlags(&b->ev_join_m, cudaEventDisableTiming));
+  for (int i = 0; i < tfgnn_batch::kPipeBufs; ++i) {
+    TFGNN_CUDA(cudaEventCreateWithFlags(&b->ev_g[i], cudaEventDisableTiming));
+    TFGNN_CUDA(cudaEventCreateWithFlags(&b->ev_m[i], cudaEventDisableTiming));
+  }
+  b->pipe_ready = true;
+  return 0;
+}
+
+// RGCN-style layer as a two-stream pipeline over node chunks: the HBM-bound gather/reduce of chunk
+// i+1 (stream G) overlaps the tensor-core contraction of chunk i (stream M); the per-chunk
+// intermediate A[chunk, L*D] is triple-buffered.  Fork/join on the caller's stream with events, so
+// the call stays stream-ordered (and graph-capturable).
+static int pipe_chunk_rows() {
+  // default: two 128-row tiles per SM; TFGNN_B200_PIPE_CHUNK_ROWS overrides (tests / tuning)
+  int rows = 2 * 148 * 128;
+  if (const char* e = getenv("TFGNN_B200_PIPE_CHUNK_ROWS")) {
+    const int v = atoi(e);
+    if (v >= 128) rows = (v > (1 << 24) ? (1 << 24) : v) / 128 * 128;
+  }
+  return rows;
+}
+static int rgcn_pipelined(tfgnn_batch* b, const float* h, int D, const float* Wcat, int H, bool normalize,
+                          const GemmEpilogue& epi_in, float* out, int ldo, cudaStream_t st) {
+  const int V = (int)b->V, L = b->L, K = L * D;
+  const int kPipeChunkRows = pipe_chunk_rows();
+  int rc = pipeline_init(b);
+  if (rc) return rc;
+  void *A = nullptr, *packed = nullptr;
+  const size_t a_chunk_elems = (size_t)kPipeChunkRows * K;
+  rc = batch_scratch(b, 2, a_chunk_elems * tfgnn_batch::kPipeBufs * sizeof(float), &A);
+  if (rc) return rc;
+  rc = batch_scratch(b, 6, gemm_tc_packed_bytes(H, K), &packed);
+  if (rc) return rc;
+  rc = launch_pack_weights_tc(Wcat, H, K, H, (float*)packed, st);
+  if (rc) return rc;
+  cudaStream_t sg = b->pipe_gather, sm = b->pipe_gemm;
+  TFGNN_CUDA(cudaEventRecord(b->ev_fork, st));
+  TFGNN_CUDA(cudaStreamWaitEvent(sg, b->ev_fork, 0));
+  TFGNN_CUDA(cudaStreamWaitEvent(sm, b->ev_fork, 0));
+  const int nchunks = (V + kPipeChunkRows - 1) / kPipeChunkRows;
+  for (int i = 0; i < nchunks; ++i) {
+    const int buf = i % tfgnn_batch::kPipeBufs;
+    const int v0 = i * kPipeChunkRows;
+    const int vc = (V - v0 < kPipeChunkRows) ? V - v0 : kPipeChunkRows;
+    float* Abuf = (float*)A + (size_t)buf * a_chunk_elems;
+    if (i >= tfgnn_batch::kPipeBufs) TFGNN_CUDA(cudaStreamWaitEvent(sg, b->ev_m[buf], 0));
+    EdgeReduceParams p;
+    p.X = h; p.ldx = D; p.x_type_stride = 0;
+    p.row_ptr = b->row_ptr; p.src = b->src_sorted;
+    p.out = Abuf; p.ldo = K; p.out_type_stride = D;
+    p.V = V; p.L = L; p.C = D; p.normalize = normalize;
+    p.v_begin = v0; p.v_count = vc;
+    rc = launch_edge_reduce(p, /*merged=*/false, sg, /*max_blocks=*/148 * 6);
+    if (rc) return rc;
+    TFGNN_CUDA(cudaEventRecord(b->ev_g[buf], sg));
+    TFGNN_CUDA(cudaStreamWaitEvent(sm, b->ev_g[buf], 0));
+    GemmEpilogue epi = epi_in;
+    epi.row0 = v0;
+    rc = launch_gemm_tc(Abuf, K, (const float*)packed, out + (size_t)v0 * ldo, ldo, vc, H, K, epi, sm);
+    if (rc) return rc;
+    TFGNN_CUDA(cudaEventRecord(b->ev_m[buf], sm));
+  }
+  TFGNN_CUDA(cudaEventRecord(b->ev_join_g, sg));
+  TFGNN_CUDA(cudaEventRecord(b->ev_join_m, sm));
+  TFGNN_CUDA(cudaStreamWaitEvent(st, b->ev_join_g, 0));
+  TFGNN_CUDA(cudaStreamWaitEvent(st, b->ev_join_m, 0));
+  return 0;
+}
+
 int agg_row_norm(int aggregation) {
   return aggregation == TFGNN_AGG_MEAN ? 1 : aggregation == TFGNN_AGG_SQRT_N ? 2 : 0;
 }
@@ -109,9 +188,21 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
     // ---- aggregate-then-transform ----
     const int K = L * D * (use_target ? 2 : 1);
     void *A = nullptr, *Wcat = nullptr;
-    int rc = batch_scratch(b, 2, (size_t)V * K * sizeof(float), &A);
+    int rc = batch_scratch(b, 3, (size_t)K * H * sizeof(float), &Wcat);
     if (rc) return rc;
-    rc = batch_scratch(b, 3, (size_t)K * H * sizeof(float), &Wcat);
+    const bool pipelined = (path == TFGNN_PATH_AUTO || path == TFGNN_PATH_FUSED_TC) && !use_target &&
+                           V >= 2 * pipe_chunk_rows() && D % 4 == 0 &&
+                           gemm_tc_supported(V, H, K, h, K, out, ldo) &&
+                           (reinterpret_cast<uintptr_t>(h) & 15) == 0;
+    if (pipelined) {
+      rc = launch_pack_vertical(first, L, 0, D, H, H, (float*)Wcat, H, 0, st);
+      if (rc) return rc;
+      GemmEpilogue epi;
+      epi.act = activation;
+      epi.row_norm = row_norm; epi.row_ptr = b->row_ptr; epi.V = V; epi.L = L;
+      return rgcn_pipelined(b, h, D, (const float*)Wcat, H, normalize, epi, out, ldo, st);
+    }
+    rc = batch_scratch(b, 2, (size_t)V * K * sizeof(float), &A);
     if (rc) return rc;
     if (path == TFGNN_PATH_ATOMIC) {
       TFGNN_CUDA(cudaMemsetAsync(A, 0, (size_t)V * K * sizeof(float), st));

@@ -94,6 +94,12 @@ struct tfgnn_batch {
   // grow-only scratch owned by the batch
   void* scratch[16] = {};
   size_t scratch_bytes[16] = {};
+  // internal fork/join streams of the gather || node-GEMM pipeline (created lazily)
+  static constexpr int kPipeBufs = 3;
+  bool pipe_ready = false;
+  cudaStream_t pipe_gather = nullptr, pipe_gemm = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join_g = nullptr, ev_join_m = nullptr;
+  cudaEvent_t ev_g[kPipeBufs] = {}, ev_m[kPipeBufs] = {};
 };
 
 namespace tfgnn {

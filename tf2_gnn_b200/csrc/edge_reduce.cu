@@ -50,25 +50,28 @@ struct EdgeFn {
 template <int NV, bool MERGED, bool PLAIN>
 __global__ void __launch_bounds__(256) edge_reduce_kernel(const EdgeReduceParams p) {
   const int lane = threadIdx.x & 31;
-  const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long num_items = MERGED ? (long long)p.V : (long long)p.L * p.V;
-  if (item >= num_items) return;
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long warp_stride = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int vcount = p.v_count;
+  const long long num_items = MERGED ? (long long)vcount : (long long)p.L * vcount;
   const int C4 = p.C >> 2;
+  const bool use_max = (!PLAIN) && p.reduce_max;
+  for (long long item = warp_global; item < num_items; item += warp_stride) {
   int l_first, l_last, v;
   if (MERGED) {
-    v = (int)item;
+    v = p.v_begin + (int)item;
     l_first = 0;
     l_last = p.L;
   } else {
-    l_first = (int)(item / p.V);
+    l_first = (int)(item / vcount);
     l_last = l_first + 1;
-    v = (int)(item - (long long)l_first * p.V);
+    v = p.v_begin + (int)(item - (long long)l_first * vcount);
   }
-  const bool use_max = (!PLAIN) && p.reduce_max;
   float4 acc[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) acc[j] = f4_fill(use_max ? kLowestFloat : 0.f);
   int total_cnt = 0;
+
 
   for (int l = l_first; l < l_last; ++l) {
     const long long seg = (long long)l * p.V + v;
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(256) edge_reduce_kernel(const EdgeReduceParams
     if (p.row_norm == 1) { rn = (float)max(total_cnt, 1); divide = true; }
     else if (p.row_norm == 2) { rn = sqrtf((float)max(total_cnt, 1)); divide = true; }
   }
-  float* orow = p.out + (long long)v * p.ldo + (MERGED ? 0 : (long long)l_first * p.out_type_stride);
+  float* orow = p.out + (long long)(v - p.v_begin) * p.ldo + (MERGED ? 0 : (long long)l_first * p.out_type_stride);
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int c4 = lane + 32 * j;
@@ -177,6 +180,7 @@ __global__ void __launch_bounds__(256) edge_reduce_kernel(const EdgeReduceParams
       *reinterpret_cast<float4*>(orow + 4 * c4) = y;
     }
   }
+  }  // item loop
 }
 
 // Scalar fallback for column counts / leading dimensions that are not multiples of 4 (doctest
@@ -184,13 +188,13 @@ __global__ void __launch_bounds__(256) edge_reduce_kernel(const EdgeReduceParams
 template <bool MERGED>
 __global__ void edge_reduce_scalar_kernel(const EdgeReduceParams p) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long num_items = MERGED ? (long long)p.V : (long long)p.L * p.V;
+  const long long num_items = MERGED ? (long long)p.v_count : (long long)p.L * p.v_count;
   if (idx >= num_items * p.C) return;
   const long long item = idx / p.C;
   const int c = (int)(idx - item * p.C);
   int l_first, l_last, v;
-  if (MERGED) { v = (int)item; l_first = 0; l_last = p.L; }
-  else { l_first = (int)(item / p.V); l_last = l_first + 1; v = (int)(item - (long long)l_first * p.V); }
+  if (MERGED) { v = p.v_begin + (int)item; l_first = 0; l_last = p.L; }
+  else { l_first = (int)(item / p.v_count); l_last = l_first + 1; v = p.v_begin + (int)(item - (long long)l_first * p.v_count); }
   const bool use_max = p.reduce_max;
   float acc = use_max ? kLowestFloat : 0.f;
   int total_cnt = 0;
@@ -229,7 +233,7 @@ __global__ void edge_reduce_scalar_kernel(const EdgeReduceParams p) {
     else if (p.row_norm == 2) acc = acc / sqrtf((float)max(total_cnt, 1));
   }
   acc = apply_act(acc, p.final_act);
-  p.out[(long long)v * p.ldo + (MERGED ? 0 : (long long)l_first * p.out_type_stride) + c] = acc;
+  p.out[(long long)(v - p.v_begin) * p.ldo + (MERGED ? 0 : (long long)l_first * p.out_type_stride) + c] = acc;
 }
 
 // Target-state term of a 0-hidden-layer edge MLP with use_target_state_as_input
@@ -277,8 +281,13 @@ __global__ void edge_scatter_atomic_kernel(const int2* __restrict__ edges, long 
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-int launch_edge_reduce(const EdgeReduceParams& p, bool merged, cudaStream_t st) {
-  const long long items = merged ? (long long)p.V : (long long)p.L * p.V;
+int launch_edge_reduce(const EdgeReduceParams& p_in, bool merged, cudaStream_t st, int max_blocks) {
+  EdgeReduceParams p = p_in;
+  if (p.v_count <= 0) {  // full range
+    p.v_begin = 0;
+    p.v_count = p.V;
+  }
+  const long long items = merged ? (long long)p.v_count : (long long)p.L * p.v_count;
   if (items == 0 || p.C == 0) return 0;
   const bool plain = !merged && !p.T && !p.G && !p.hidden_relu && p.edge_act == TFGNN_ACT_NONE &&
                      !p.reduce_max && p.final_act == TFGNN_ACT_NONE;
@@ -295,7 +304,8 @@ int launch_edge_reduce(const EdgeReduceParams& p, bool merged, cudaStream_t st) 
     return 0;
   }
   const int nv = (p.C + 127) / 128;
-  const int blocks = ceil_div(items * 32, 256);
+  int blocks = ceil_div(items * 32, 256);
+  if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
 #define TFGNN_ER_LAUNCH(NV)                                                              \
   do {                                                                                   \
     if (merged) edge_reduce_kernel<NV, true, false><<<blocks, 256, 0, st>>>(p);          \

@@ -21,6 +21,8 @@ struct EdgeReduceParams {
   int ldo = 0;
   int out_type_stride = 0;
   int V = 0, L = 0, C = 0;
+  int v_begin = 0, v_count = 0;  // target-node range handled by this launch (v_count 0 = all V);
+                                 // output rows are relative to v_begin
   int normalize = 0;    // multiply by 1/(c_{v,l}+1e-7)                        gnn_edge_mlp.py:102-106
   int hidden_relu = 0;  // per-edge ReLU of the (pre-projected) hidden layer   dpu_utils MLP
   int edge_act = 0;     // activation before aggregation                      message_passing.py:169-170
@@ -29,7 +31,8 @@ struct EdgeReduceParams {
   int final_act = 0;    // MERGED only: activation after aggregation          message_passing.py:176-177
 };
 
-int launch_edge_reduce(const EdgeReduceParams& p, bool merged, cudaStream_t st);
+// max_blocks > 0 caps the grid (grid-stride over segments) so another kernel can co-reside on the SMs.
+int launch_edge_reduce(const EdgeReduceParams& p, bool merged, cudaStream_t st, int max_blocks = 0);
 int launch_target_term(const float* h, int ldh, const int* row_ptr, int V, int L, int D, int normalize,
                        float* out, int ldo, int col0, cudaStream_t st);
 int launch_edge_scatter_atomic(const tfgnn_batch* b, const float* X, int ldx, int C, int normalize,

@@ -10,6 +10,7 @@ struct GemmEpilogue {
   // per-row normalisation for mean / sqrt_n aggregation (counts over all edge types of the CSR)
   const int* row_ptr = nullptr;
   int V = 0, L = 0;
+  long long row0 = 0;  // global node id of output row 0 (chunked launches)
   int row_norm = 0;  // 0 none, 1 mean (/max(cnt,1)), 2 sqrt_n (/sqrt(max(cnt,1)))
 };
 

@@ -12,7 +12,7 @@ __device__ __forceinline__ float row_norm_factor(const GemmEpilogue& e, long lon
   if (e.row_norm == 0) return 1.0f;
   int cnt = 0;
   for (int l = 0; l < e.L; ++l) {
-    const long long s = (long long)l * e.V + row;
+    const long long s = (long long)l * e.V + e.row0 + row;
     cnt += e.row_ptr[s + 1] - e.row_ptr[s];
   }
   const float c = (float)max(cnt, 1);

@@ -1,8 +1,13 @@
 // Node-level GEMM on the 5th-generation tensor cores with fp32-level accuracy ("3xTF32"):
 //     C[M,N] = epi( A[M,K] * B[K,N] ),   x = x_hi + x_lo (tf32 split),
-//     A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi     (dropped term ~2^-22 relative)
+//     A*B ~= A_hi*B_hi + (A_lo*B_hi + A_hi*B_lo)     (dropped term ~2^-22 relative)
 // so the 1e-5 parity bar of the fp32 reference holds (plain TF32 would miss it by 100x) while the
 // contraction runs at tensor-core rate instead of the ~70 TFLOP/s FFMA ceiling.
+// Measured on B200: the tensor core adds each K=8 product into the fp32 accumulator with
+// truncation, a bias that grows with the number of accumulate steps (9e-6 relative at K=1024 with
+// one accumulator).  The two small correction products therefore go to their OWN TMEM accumulator
+// (their truncation error is 2^-11 smaller) and are added to the main one in the epilogue with
+// round-to-nearest: 3x fewer biased steps on the large-magnitude sum.
 //
 // Persistent warp-specialised kernel, one CTA per SM, 128 x BLOCK_N output tiles, K in 32-float
 // (128 B = one swizzle row) blocks through an mbarrier ring:
@@ -24,7 +29,7 @@ constexpr int kTcBK = 32;                       // floats per K block = 128 byte
 constexpr int kTcATileBytes = kTcBM * 128;      // 16 KiB
 constexpr int kTcThreads = 320;
 constexpr int kTcTmemCols = 512;
-constexpr int kTcAccStride = 256;               // TMEM columns per accumulator stage
+constexpr int kTcAccStride = 256;               // TMEM columns per accumulator stage (main + correction)
 constexpr int kTcSmemLimit = 227 * 1024;
 
 struct TcParams {
@@ -42,7 +47,7 @@ __device__ __forceinline__ float tc_row_norm(const GemmEpilogue& e, long long ro
   if (e.row_norm == 0) return 1.0f;
   int cnt = 0;
   for (int l = 0; l < e.L; ++l) {
-    const long long s = (long long)l * e.V + row;
+    const long long s = (long long)l * e.V + e.row0 + row;
     cnt += __ldg(e.row_ptr + s + 1) - __ldg(e.row_ptr + s);
   }
   const float c = (float)max(cnt, 1);
@@ -113,11 +118,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ================= MMA issuer =================
     const uint32_t idesc = ptx::umma_idesc_tf32_m128((uint32_t)p.block_n);
     uint32_t it = 0, tile_count = 0;
+    const uint32_t n_acc = p.block_n <= 128 ? 2 : 1;       // accumulator stages that fit 512 TMEM columns
+    const uint32_t corr_off = p.block_n <= 128 ? 128 : 256;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_count) {
-      const uint32_t acc = tile_count & 1, acc_ph = (tile_count >> 1) & 1;
+      const uint32_t acc = tile_count % n_acc, acc_ph = (tile_count / n_acc) & 1;
       ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
       ptx::tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * kTcAccStride;
+      const uint32_t c_tmem = d_tmem + corr_off;
       for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
@@ -133,9 +141,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < kTcBK / 8; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 8 tf32 = 32 B along K inside the swizzle row
-            ptx::mma_tf32_ss(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-            ptx::mma_tf32_ss(d_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-            ptx::mma_tf32_ss(d_tmem, a_hi + adv, b_hi + adv, idesc, 1);
+            ptx::mma_tf32_ss(c_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+            ptx::mma_tf32_ss(c_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+            ptx::mma_tf32_ss(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
           }
           ptx::mma_commit(&empty[s]);
           if (kb == p.num_k_blocks - 1) ptx::mma_commit(&tmem_full[acc]);
@@ -173,10 +181,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ================= epilogue (warps 6..9 -> TMEM lane quarters 2,3,0,1) =================
     const int q = warp & 3;
     uint32_t tile_count = 0;
+    const uint32_t n_acc = p.block_n <= 128 ? 2 : 1;
+    const uint32_t corr_off = p.block_n <= 128 ? 128 : 256;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_count) {
       const long long m0 = (tile / p.n_tiles) * kTcBM;
       const int n0 = (int)(tile % p.n_tiles) * p.block_n;
-      const uint32_t acc = tile_count & 1, acc_ph = (tile_count >> 1) & 1;
+      const uint32_t acc = tile_count % n_acc, acc_ph = (tile_count / n_acc) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_ph);
       ptx::tc_fence_after_sync();
       const long long row = m0 + q * 32 + lane;
@@ -185,12 +195,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       float* crow = p.C + row * p.ldc + n0;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTcAccStride;
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        float v[16];
+        float v[16], w[16];
         ptx::tmem_ld_x16(taddr + c0, v);
+        ptx::tmem_ld_x16(taddr + corr_off + c0, w);
         if (row_ok) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float x = v[j];
+            float x = v[j] + w[j];
             if (p.epi.row_norm) x = x / rn;
             if (p.epi.bias) x += __ldg(p.epi.bias + n0 + c0 + j);
             v[j] = apply_act(x, p.epi.act);

@@ -72,6 +72,37 @@ __global__ void activation_kernel(const float* __restrict__ x, long long n, int 
     out[i] = apply_act(x[i], act);
 }
 
+__global__ void residual_average_kernel(const float* __restrict__ x, const float* __restrict__ last, long long n,
+                                        float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (x[i] + last[i]) / 2.0f;
+}
+
+// One warp per row; two-pass mean / variance in registers (Keras LayerNormalization: biased variance,
+// y = (x - mean) * rsqrt(var + eps) * gamma + beta).
+__global__ void layer_norm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, long long V, int H, float eps,
+                                  float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= V) return;
+  const float* xr = x + row * H;
+  float s = 0.f;
+  for (int c = lane; c < H; c += 32) s += xr[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)H;
+  float q = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    const float d = xr[c] - mean;
+    q += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float inv = rsqrtf(q / (float)H + eps);
+  for (int c = lane; c < H; c += 32) out[row * H + c] = (xr[c] - mean) * inv * gamma[c] + beta[c];
+}
+
 static int grid_for(long long n, int cap = 148 * 32) {
   int b = ceil_div(n, 256);
   return b < 1 ? 1 : (b > cap ? cap : b);
@@ -129,6 +160,25 @@ extern "C" int tfgnn_b200_activation(const float* x, int64_t n, int32_t activati
   if (n == 0) return 0;
   TFGNN_REQUIRE(x && out, "NULL pointer");
   activation_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, n, activation, out);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tfgnn_b200_residual_average(const float* x, const float* last, float* out, int64_t n, void* stream) {
+  TFGNN_REQUIRE(n >= 0, "negative size");
+  if (n == 0) return 0;
+  TFGNN_REQUIRE(x && last && out, "NULL pointer");
+  residual_average_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, last, n, out);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tfgnn_b200_layer_norm(const float* x, const float* gamma, const float* beta, int64_t V, int32_t H,
+                                     float epsilon, float* out, void* stream) {
+  TFGNN_REQUIRE(V >= 0 && H > 0, "bad layer_norm shape");
+  if (V == 0) return 0;
+  TFGNN_REQUIRE(x && gamma && beta && out, "NULL pointer");
+  layer_norm_kernel<<<ceil_div(V * 32, 256), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, V, H, epsilon, out);
   TFGNN_LAUNCH_CHECK();
   return 0;
 }

@@ -307,6 +307,17 @@ extern "C" int tfgnn_b200_free_batch(tfgnn_batch_t* b) {
   cudaFree(b->src_sorted);
   cudaFree(b->invalid_count);
   for (int i = 0; i < 16; ++i) cudaFree(b->scratch[i]);
+  if (b->pipe_ready) {
+    cudaStreamDestroy(b->pipe_gather);
+    cudaStreamDestroy(b->pipe_gemm);
+    cudaEventDestroy(b->ev_fork);
+    cudaEventDestroy(b->ev_join_g);
+    cudaEventDestroy(b->ev_join_m);
+    for (int i = 0; i < tfgnn_batch::kPipeBufs; ++i) {
+      cudaEventDestroy(b->ev_g[i]);
+      cudaEventDestroy(b->ev_m[i]);
+    }
+  }
   delete b;
   return 0;
 }

@@ -1,0 +1,204 @@
+"""GNN encoder — B200-backed mirror of tf2_gnn.layers.gnn (/root/reference/tf2_gnn/layers/gnn.py:21-329).
+
+Same GNNInput namedtuple, hyper-parameter dict, layer loop and return convention.  The adjacency
+lists are prepared ONCE per call (CSR sorted by type,target) and shared by all message-passing layers;
+the reference rebuilds the in-degree table in every layer (message_passing.py:190).
+
+Node-level glue implemented on the library's kernels: initial projection / inter-layer Dense
+(tfgnn_b200_dense_fwd), residual average, LayerNormalization.  Not built yet (raise, never fall
+back): training-time dropout with rate > 0 and the graph global exchange layers.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, NamedTuple, Optional, Tuple
+
+import torch
+
+from .. import _ffi
+from ..runtime import PreparedBatch, prepared_batch_for, stream_ptr, to_device_adj, to_device_f32
+from ..utils.param_helpers import get_activation_function
+from .message_passing import MessagePassing, MessagePassingInput, get_message_passing_class
+from .message_passing.message_passing import Variable, glorot_uniform
+
+
+class GNNInput(NamedTuple):
+    """Input named tuple for the GNN (gnn.py:21-27)."""
+
+    node_features: Any
+    adjacency_lists: Tuple[Any, ...]
+    node_to_graph_map: Any
+    num_graphs: Any
+
+
+class _Dense:
+    """tf.keras.layers.Dense(units, use_bias=False, activation=...) on tfgnn_b200_dense_fwd."""
+
+    def __init__(self, name: str, in_dim: int, units: int, activation):
+        self.kernel = Variable(f"{name}/kernel:0", glorot_uniform((in_dim, units)))
+        self.activation = activation
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        V, K = int(x.shape[0]), int(x.shape[1])
+        N = int(self.kernel.value.shape[1])
+        out = torch.empty((V, N), dtype=torch.float32, device=x.device)
+        _ffi.check(_ffi.lib().tfgnn_b200_dense_fwd(
+            x.data_ptr(), self.kernel.value.data_ptr(), out.data_ptr(), V, K, N,
+            self.activation.code if self.activation is not None else 0, 0, stream_ptr()))
+        return out
+
+
+class _LayerNorm:
+    """tf.keras.layers.LayerNormalization() defaults: axis=-1, epsilon=1e-3, gamma=1, beta=0."""
+
+    def __init__(self, name: str, dim: int, epsilon: float = 1e-3):
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        self.gamma = Variable(f"{name}/gamma:0", torch.ones(dim, dtype=torch.float32, device=dev))
+        self.beta = Variable(f"{name}/beta:0", torch.zeros(dim, dtype=torch.float32, device=dev))
+        self.epsilon = epsilon
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        out = torch.empty_like(x)
+        _ffi.check(_ffi.lib().tfgnn_b200_layer_norm(
+            x.data_ptr(), self.gamma.value.data_ptr(), self.beta.value.data_ptr(), int(x.shape[0]),
+            int(x.shape[1]), self.epsilon, out.data_ptr(), stream_ptr()))
+        return out
+
+
+class GNN:
+    """Encode graph states using a combination of graph message passing layers and dense layers
+    (gnn.py:30-329)."""
+
+    @classmethod
+    def get_default_hyperparameters(cls, mp_style: Optional[str] = None) -> Dict[str, Any]:
+        """gnn.py:53-79: the GNN-level keys override the message-passing defaults."""
+        these_hypers = {
+            "message_calculation_class": "rgcn",
+            "initial_node_representation_activation": "tanh",
+            "dense_intermediate_layer_activation": "tanh",
+            "num_layers": 4,
+            "dense_every_num_layers": 2,
+            "residual_every_num_layers": 2,
+            "use_inter_layer_layernorm": False,
+            "hidden_dim": 16,
+            "layer_input_dropout_rate": 0.0,
+            "global_exchange_mode": "gru",  # One of "mean", "mlp", "gru"
+            "global_exchange_every_num_layers": 2,
+            "global_exchange_weighting_fun": "softmax",  # One of "softmax", "sigmoid"
+            "global_exchange_num_heads": 4,
+            "global_exchange_dropout_rate": 0.2,
+        }  # type: Dict[str, Any]
+        if mp_style is not None:
+            these_hypers["message_calculation_class"] = mp_style
+        message_passing_class = get_message_passing_class(these_hypers["message_calculation_class"])
+        message_passing_hypers = message_passing_class.get_default_hyperparameters()
+        message_passing_hypers.update(these_hypers)
+        return message_passing_hypers
+
+    def __init__(self, params: Dict[str, Any]):
+        self._params = params
+        self._hidden_dim = params["hidden_dim"]
+        self._num_layers = params["num_layers"]
+        self._dense_every_num_layers = params["dense_every_num_layers"]
+        self._residual_every_num_layers = params["residual_every_num_layers"]
+        self._use_inter_layer_layernorm = params["use_inter_layer_layernorm"]
+        self._initial_node_representation_activation_fn = get_activation_function(
+            params["initial_node_representation_activation"])
+        self._dense_intermediate_layer_activation_fn = get_activation_function(
+            params["dense_intermediate_layer_activation"])
+        self._message_passing_class = get_message_passing_class(params["message_calculation_class"])
+        if not params["global_exchange_mode"].lower() in {"mean", "mlp", "gru"}:
+            raise ValueError(
+                f"Unknown global_exchange_mode mode {params['global_exchange_mode']} - has to be one of 'mean', 'mlp', 'gru'!")
+        self._global_exchange_mode = params["global_exchange_mode"]
+        self._global_exchange_every_num_layers = params["global_exchange_every_num_layers"]
+        self._initial_projection_layer: Optional[_Dense] = None
+        self._mp_layers: List[MessagePassing] = []
+        self._inter_layer_layernorms: List[_LayerNorm] = []
+        self._dense_layers: Dict[str, _Dense] = {}
+        self.built = False
+
+    def _exchange_layers(self) -> List[int]:
+        return [i for i in range(self._num_layers) if i and i % self._global_exchange_every_num_layers == 0]
+
+    def build(self, tensor_shapes: GNNInput):
+        """gnn.py:117-232 (same name scopes, so reference checkpoints map by name)."""
+        in_dim = int(tuple(tensor_shapes.node_features)[-1])
+        adjacency_list_shapes = tuple(tensor_shapes.adjacency_lists)
+        scope = f"{self._message_passing_class.__name__}_GNN"
+        self._initial_projection_layer = _Dense(f"{scope}/gnn_initial_node_projection/dense", in_dim,
+                                                self._hidden_dim, self._initial_node_representation_activation_fn)
+        for layer_idx in range(self._num_layers):
+            mp = self._message_passing_class(self._params)
+            mp.build(MessagePassingInput((None, self._hidden_dim), adjacency_list_shapes))
+            for v in mp.variables:
+                v.name = f"{scope}/Layer_{layer_idx}/MessagePassing/{v.name}"
+            self._mp_layers.append(mp)
+            if self._use_inter_layer_layernorm:
+                self._inter_layer_layernorms.append(
+                    _LayerNorm(f"{scope}/Layer_{layer_idx}/LayerNorm/layer_normalization", self._hidden_dim))
+            if layer_idx % self._dense_every_num_layers == 0:
+                self._dense_layers[str(layer_idx)] = _Dense(
+                    f"{scope}/Layer_{layer_idx}/Dense/dense", self._hidden_dim, self._hidden_dim,
+                    self._dense_intermediate_layer_activation_fn)
+        self.built = True
+
+    @property
+    def variables(self) -> List[Variable]:
+        out = [self._initial_projection_layer.kernel] if self._initial_projection_layer else []
+        for i, mp in enumerate(self._mp_layers):
+            out.extend(mp.variables)
+            if self._use_inter_layer_layernorm:
+                out.extend([self._inter_layer_layernorms[i].gamma, self._inter_layer_layernorms[i].beta])
+            if str(i) in self._dense_layers:
+                out.append(self._dense_layers[str(i)].kernel)
+        return out
+
+    trainable_variables = variables
+    weights = variables
+
+    def __call__(self, inputs: GNNInput, training: bool = False, return_all_representations: bool = False):
+        if not self.built:
+            self.build(GNNInput(tuple(inputs.node_features.shape),
+                                tuple(tuple(a.shape) for a in inputs.adjacency_lists), None, None))
+        return self.call(inputs, training=training, return_all_representations=return_all_representations)
+
+    def call(self, inputs: GNNInput, training: bool = False, return_all_representations: bool = False):
+        """gnn.py:234-274."""
+        cur, all_reps = self._internal_call(inputs, training)
+        if return_all_representations:
+            return cur, all_reps
+        return cur
+
+    def _internal_call(self, inputs: GNNInput, training: bool = False):
+        """gnn.py:276-329."""
+        if self._exchange_layers():
+            raise NotImplementedError(
+                "graph global exchange layers are not built yet (set global_exchange_every_num_layers > "
+                "num_layers, as every PPI config of the reference does)")
+        if training and float(self._params.get("layer_input_dropout_rate", 0.0)) > 0.0:
+            raise NotImplementedError("training-time dropout is not built yet (forward/inference path only)")
+        feats = to_device_f32(inputs.node_features)
+        adjs = tuple(to_device_adj(a, feats.device) for a in inputs.adjacency_lists)
+        if all(a is b for a, b in zip(adjs, inputs.adjacency_lists)):
+            prepared = prepared_batch_for(adjs, int(feats.shape[0]))
+        else:
+            prepared = PreparedBatch(adjs, int(feats.shape[0]))
+        cur = self._initial_projection_layer(feats)
+        last = cur
+        all_reps = [cur]
+        for layer_idx, mp_layer in enumerate(self._mp_layers):
+            if layer_idx % self._residual_every_num_layers == 0:
+                tmp = cur
+                if layer_idx > 0:
+                    avg = torch.empty_like(cur)
+                    _ffi.check(_ffi.lib().tfgnn_b200_residual_average(cur.data_ptr(), last.data_ptr(),
+                                                                      avg.data_ptr(), cur.numel(), stream_ptr()))
+                    cur = avg
+                last = tmp
+            cur = mp_layer(MessagePassingInput(cur, adjs), training=training, prepared=prepared)
+            all_reps.append(cur)
+            if self._use_inter_layer_layernorm:
+                cur = self._inter_layer_layernorms[layer_idx](cur)
+            if layer_idx % self._dense_every_num_layers == 0:
+                cur = self._dense_layers[str(layer_idx)](cur)
+        return cur, tuple(all_reps)

@@ -1,0 +1,60 @@
+"""Summarise ncu outputs into small tracked text files under profiles/.
+
+  python tools/ncu_summary.py launches gpurun_out/launches.csv profiles/launches_rNN.md
+  python tools/ncu_summary.py full gpurun_out/prof.ncu-rep profiles/ncu_full_rNN_<kernel>.md
+"""
+import collections
+import csv
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum.per_second",
+    "dram__bytes_write.sum.per_second", "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tensor.sum", "launch__registers_per_thread", "launch__grid_size",
+    "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "smsp__cycles_active.avg",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+    "smsp__average_warp_latency_issue_stalled_long_scoreboard.pct",
+    "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+]
+
+
+def launches(src, dst):
+    lines = [l for l in open(src) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        name = row["Kernel Name"].split("(")[0][:80]
+        agg.setdefault(name, []).append(float(row["Metric Value"].replace(",", "")))
+    total = sum(sum(v) for v in agg.values())
+    with open(dst, "w") as f:
+        f.write(f"# ncu launch list ({src}); gpu__time_duration.sum, --clock-control none\n\n")
+        f.write("Per-launch times under ncu are cold-cache and serialised: compare SHARES, not absolutes.\n\n")
+        f.write("| kernel | launches | avg us | total ms | share |\n|---|---:|---:|---:|---:|\n")
+        for k, v in agg.items():
+            f.write(f"| `{k}` | {len(v)} | {sum(v) / len(v) / 1e3:.1f} | {sum(v) / 1e6:.3f} | {sum(v) / total:.1%} |\n")
+    print(open(dst).read())
+
+
+def full(src, dst):
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full summary ({src})\n\n")
+        for r in rows[2:]:
+            name = r[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+            f.write(f"## {name[:100]}\n\n| metric | value | unit |\n|---|---:|---|\n")
+            for k in KEYS:
+                if k in hdr:
+                    i = hdr.index(k)
+                    f.write(f"| {k} | {r[i]} | {units[i]} |\n")
+            f.write("\n")
+    print(open(dst).read())
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
