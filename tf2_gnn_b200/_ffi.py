@@ -24,7 +24,7 @@ PREPARE_VALIDATE = 1
 MAX_EDGE_TYPES = 32
 
 EXPORTED_SYMBOLS = (
-    "tfgnn_b200_abi_version", "tfgnn_b200_last_error", "tfgnn_b200_prepare", "tfgnn_b200_free_batch",
+    "tfgnn_b200_abi_version", "tfgnn_b200_last_error", "tfgnn_b200_prepare", "tfgnn_b200_prepare_sharded", "tfgnn_b200_free_batch",
     "tfgnn_b200_batch_info", "tfgnn_b200_batch_export_csr", "tfgnn_b200_in_degree", "tfgnn_b200_edge_mlp_fwd", "tfgnn_b200_rgcn_fwd",
     "tfgnn_b200_ggnn_fwd", "tfgnn_b200_rgin_fwd", "tfgnn_b200_film_fwd", "tfgnn_b200_rgat_fwd",
     "tfgnn_b200_dense_fwd", "tfgnn_b200_gather_rows", "tfgnn_b200_unsorted_segment_reduce",
@@ -53,6 +53,8 @@ def lib() -> ctypes.CDLL:
     L.tfgnn_b200_last_error.restype = c_char_p
     L.tfgnn_b200_launch_count.restype = c_int64
     L.tfgnn_b200_prepare.argtypes = [_PP, POINTER(c_int64), c_int32, c_int64, c_uint32, POINTER(c_void_p), c_void_p]
+    L.tfgnn_b200_prepare_sharded.argtypes = [_PP, POINTER(c_int64), c_int32, c_int64, c_int64, c_int64, c_uint32,
+                                             POINTER(c_void_p), c_void_p]
     L.tfgnn_b200_free_batch.argtypes = [c_void_p]
     L.tfgnn_b200_batch_info.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int32), POINTER(c_int64),
                                         POINTER(c_void_p), POINTER(c_void_p)]

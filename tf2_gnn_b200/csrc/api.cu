@@ -156,9 +156,12 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
   TFGNN_REQUIRE(valid_agg(aggregation), "unknown aggregation code");
   TFGNN_REQUIRE(path >= TFGNN_PATH_AUTO && path <= TFGNN_PATH_FUSED_TC, "unknown path code");
   const int V = (int)b->V, L = b->L;
+  const int Vs = (int)b->V_src;                           // rows of the source table h
   if (V == 0) return 0;
   TFGNN_REQUIRE(h != nullptr && out != nullptr, "h / out is NULL");
   TFGNN_REQUIRE(L == 0 || mlp_weights != nullptr, "mlp_weights is NULL");
+  const float* h_tgt = h + (size_t)b->tgt_off * D;        // rows of the targets owned by this batch
+  const bool sharded = (b->tgt_off != 0 || b->V_src != b->V);
   const int n_layers = n_hidden + 1;
   for (int i = 0; i < L * n_layers; ++i) TFGNN_REQUIRE(mlp_weights[i] != nullptr, "a weight pointer is NULL");
 
@@ -205,6 +208,7 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
     rc = batch_scratch(b, 2, (size_t)V * K * sizeof(float), &A);
     if (rc) return rc;
     if (path == TFGNN_PATH_ATOMIC) {
+      if (sharded) return unsupported("TFGNN_PATH_ATOMIC is not available on a target-range shard");
       TFGNN_CUDA(cudaMemsetAsync(A, 0, (size_t)V * K * sizeof(float), st));
       rc = launch_edge_scatter_atomic(b, h, D, D, normalize, (float*)A, K, D, st);
       if (rc) return rc;
@@ -220,7 +224,7 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
     rc = launch_pack_vertical(first, L, 0, D, H, H, (float*)Wcat, H, 0, st);
     if (rc) return rc;
     if (use_target) {
-      rc = launch_target_term(h, D, b->row_ptr, V, L, D, normalize, (float*)A, K, L * D, st);
+      rc = launch_target_term(h_tgt, D, b->row_ptr, V, L, D, normalize, (float*)A, K, L * D, st);
       if (rc) return rc;
       rc = launch_pack_vertical(first, L, D, D, H, H, (float*)Wcat, H, L * D, st);
       if (rc) return rc;
@@ -238,21 +242,21 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
     // ---- transform-then-aggregate (max aggregation and/or activation before aggregation) ----
     const int LH = L * H;
     void *P = nullptr, *Tt = nullptr, *Wcat = nullptr;
-    int rc = batch_scratch(b, 2, (size_t)V * LH * sizeof(float), &P);
+    int rc = batch_scratch(b, 2, (size_t)Vs * LH * sizeof(float), &P);
     if (rc) return rc;
     rc = batch_scratch(b, 3, (size_t)D * LH * sizeof(float), &Wcat);
     if (rc) return rc;
     rc = launch_pack_horizontal(first, L, 0, D, H, H, (float*)Wcat, LH, st);
     if (rc) return rc;
     GemmEpilogue none;
-    rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)P, LH, V, LH, D, none, path, b, 6, st);
+    rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)P, LH, Vs, LH, D, none, path, b, 6, st);
     if (rc) return rc;
     if (use_target) {
       rc = batch_scratch(b, 4, (size_t)V * LH * sizeof(float), &Tt);
       if (rc) return rc;
       rc = launch_pack_horizontal(first, L, D, D, H, H, (float*)Wcat, LH, st);
       if (rc) return rc;
-      rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)Tt, LH, V, LH, D, none, path, b, 6, st);
+      rc = node_gemm(h_tgt, D, (const float*)Wcat, LH, (float*)Tt, LH, V, LH, D, none, path, b, 6, st);
       if (rc) return rc;
     }
     EdgeReduceParams p;
@@ -272,21 +276,21 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
     // ---- hoisted hidden layer: per-edge relu on pre-projected tables, output layer per (v,l) ----
     const int LH = L * H;
     void *Xs = nullptr, *Xt = nullptr, *Wcat = nullptr, *A = nullptr, *W2 = nullptr;
-    int rc = batch_scratch(b, 2, (size_t)V * LH * sizeof(float), &Xs);
+    int rc = batch_scratch(b, 2, (size_t)Vs * LH * sizeof(float), &Xs);
     if (rc) return rc;
     rc = batch_scratch(b, 3, (size_t)(D > H ? D : H) * LH * sizeof(float), &Wcat);
     if (rc) return rc;
     rc = launch_pack_horizontal(first, L, 0, D, H, H, (float*)Wcat, LH, st);
     if (rc) return rc;
     GemmEpilogue none;
-    rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)Xs, LH, V, LH, D, none, path, b, 6, st);
+    rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)Xs, LH, Vs, LH, D, none, path, b, 6, st);
     if (rc) return rc;
     if (use_target) {
       rc = batch_scratch(b, 4, (size_t)V * LH * sizeof(float), &Xt);
       if (rc) return rc;
       rc = launch_pack_horizontal(first, L, D, D, H, H, (float*)Wcat, LH, st);
       if (rc) return rc;
-      rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)Xt, LH, V, LH, D, none, path, b, 6, st);
+      rc = node_gemm(h_tgt, D, (const float*)Wcat, LH, (float*)Xt, LH, V, LH, D, none, path, b, 6, st);
       if (rc) return rc;
     }
     rc = batch_scratch(b, 5, (size_t)V * LH * sizeof(float), &A);

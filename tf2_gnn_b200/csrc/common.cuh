@@ -81,7 +81,9 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 // The opaque batch (see include/tfgnn_b200.h).  Keyed CSR: segment s = l*V + v holds the
 // sources of all type-l edges into v, so c[l,v] = row_ptr[s+1]-row_ptr[s].
 struct tfgnn_batch {
-  long long V = 0;
+  long long V = 0;        // number of TARGET nodes owned by this batch (= rows of every layer output)
+  long long V_src = 0;    // number of rows of the source node table (== V unless target-range sharded)
+  long long tgt_off = 0;  // global id of local target 0 (target-range sharding)
   int L = 0;
   long long M_in = 0;     // edges handed in
   int device = 0;

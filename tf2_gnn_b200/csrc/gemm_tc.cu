@@ -31,6 +31,8 @@ constexpr int kTcThreads = 320;
 constexpr int kTcTmemCols = 512;
 constexpr int kTcAccStride = 256;               // TMEM columns per accumulator stage (main + correction)
 constexpr int kTcSmemLimit = 227 * 1024;
+constexpr int kTcEpiPitch = 36;                 // floats per staged row (32 + 4 pad, keeps 16 B alignment)
+constexpr int kTcEpiBytes = 4 * 32 * kTcEpiPitch * 4;  // 4 epilogue warps x 32 rows
 
 struct TcParams {
   long long M;
@@ -69,6 +71,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_full = bars + 3 * S;    // accumulator complete
   uint64_t* tmem_empty = bars + 3 * S + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
+  float* epi_stage = reinterpret_cast<float*>(bars + ((3 * S + 7) & ~1));  // 16 B aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -192,24 +195,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const long long row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
       const float rn = row_ok ? tc_row_norm(p.epi, row) : 1.0f;
-      float* crow = p.C + row * p.ldc + n0;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTcAccStride;
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        float v[16], w[16];
-        ptx::tmem_ld_x16(taddr + c0, v);
-        ptx::tmem_ld_x16(taddr + corr_off + c0, w);
-        if (row_ok) {
+      float* stage = epi_stage + (size_t)(warp - 6) * 32 * kTcEpiPitch;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        const int ncols = min(32, p.block_n - c0);     // 32 or 16
+        // TMEM -> registers (row = lane), epilogue math, -> smem staging tile [32 rows][ncols]
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x = v[j] + w[j];
-            if (p.epi.row_norm) x = x / rn;
-            if (p.epi.bias) x += __ldg(p.epi.bias + n0 + c0 + j);
-            v[j] = apply_act(x, p.epi.act);
+        for (int half = 0; half < 2; ++half) {
+          if (half * 16 < ncols) {
+            float v[16], w[16];
+            ptx::tmem_ld_x16(taddr + c0 + half * 16, v);
+            ptx::tmem_ld_x16(taddr + corr_off + c0 + half * 16, w);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = v[j] + w[j];
+              if (p.epi.row_norm) x = x / rn;
+              if (p.epi.bias) x += __ldg(p.epi.bias + n0 + c0 + half * 16 + j);
+              v[j] = apply_act(x, p.epi.act);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(stage + lane * kTcEpiPitch + half * 16 + j) =
+                  make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(crow + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
+        __syncwarp();
+        // coalesced stores: 8 lanes cover one row's 128 B, 4 rows per instruction
+        const int f4_per_row = ncols / 4;                 // 8 or 4
+        const int rows_per_it = 32 / f4_per_row;          // 4 or 8
+        const int rr = lane / f4_per_row, cc = (lane % f4_per_row) * 4;
+        for (int r0 = 0; r0 < 32; r0 += rows_per_it) {
+          const int r = r0 + rr;
+          const long long grow = m0 + q * 32 + r;
+          if (grow < p.M) {
+            const float4 val = *reinterpret_cast<const float4*>(stage + r * kTcEpiPitch + cc);
+            *reinterpret_cast<float4*>(p.C + grow * p.ldc + n0 + c0 + cc) = val;
+          }
+        }
+        __syncwarp();
       }
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&tmem_empty[acc]);
@@ -258,8 +281,13 @@ static EncodeTiledFn get_encode_fn() {
 
 static int pick_block_n(int N) {
   if (N % 16 != 0 || N < 16) return 0;
+  if (N <= 128) return N;
+  // <=128 columns: main + correction accumulators fit twice in the 512 TMEM columns, so the epilogue of
+  // one tile overlaps the MMAs of the next; the A tile is then read once per N tile (L2 hit).
+  for (int bn = 128; bn >= 64; bn -= 16)
+    if (N % bn == 0) return bn;
   if (N <= 256) return N;
-  for (int bn = 256; bn >= 64; bn -= 16)
+  for (int bn = 256; bn > 128; bn -= 16)
     if (N % bn == 0) return bn;
   return 0;
 }
@@ -311,7 +339,7 @@ int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int 
   p.total_tiles = p.m_tiles * p.n_tiles;
   p.num_k_blocks = Kp / kTcBK;
   const int stage_bytes = 2 * kTcATileBytes + 2 * p.block_n * 128;
-  int stages = (kTcSmemLimit - 2048) / stage_bytes;
+  int stages = (kTcSmemLimit - 2048 - kTcEpiBytes) / stage_bytes;
   if (stages > 4) stages = 4;
   TFGNN_REQUIRE(stages >= 2, "tcgen05 GEMM: tile does not fit shared memory");
   p.num_stages = stages;
@@ -344,7 +372,7 @@ int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int 
       return TFGNN_ERR_CUDA;
     }
   }
-  const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 8) * sizeof(uint64_t) + kTcEpiBytes + 1024;
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {

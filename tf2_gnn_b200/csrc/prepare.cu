@@ -9,8 +9,8 @@
 namespace tfgnn {
 
 // ---- 1. histogram of targets per (type, node) -------------------------------------------
-__global__ void count_targets_kernel(PtrTable adj, CountTable E, int V, int* __restrict__ counts,
-                                     int* __restrict__ invalid) {
+__global__ void count_targets_kernel(PtrTable adj, CountTable E, int V, int V_src, int off,
+                                     int* __restrict__ counts, int* __restrict__ invalid) {
   const int l = blockIdx.y;
   const long long n = E.n[l];
   const int2* __restrict__ edges = reinterpret_cast<const int2*>(adj.p[l]);
@@ -18,8 +18,9 @@ __global__ void count_targets_kernel(PtrTable adj, CountTable E, int V, int* __r
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
     int2 st = __ldg(edges + e);
-    if ((unsigned)st.x < (unsigned)V && (unsigned)st.y < (unsigned)V) {
-      atomicAdd(counts + (long long)l * V + st.y, 1);
+    if ((unsigned)st.x < (unsigned)V_src && (unsigned)st.y < (unsigned)V_src) {
+      const unsigned t = (unsigned)(st.y - off);
+      if (t < (unsigned)V) atomicAdd(counts + (long long)l * V + t, 1);   // else: another shard's target
     } else {
       ++bad;
     }
@@ -106,17 +107,20 @@ __global__ void scan_apply_kernel(int* __restrict__ data, long long n, const int
 }
 
 // ---- 3. fill: sources into their (type,target) segment -------------------------------------
-__global__ void fill_sources_kernel(PtrTable adj, CountTable E, int V, int* __restrict__ cursor,
-                                    int* __restrict__ src_sorted) {
+__global__ void fill_sources_kernel(PtrTable adj, CountTable E, int V, int V_src, int off,
+                                    int* __restrict__ cursor, int* __restrict__ src_sorted) {
   const int l = blockIdx.y;
   const long long n = E.n[l];
   const int2* __restrict__ edges = reinterpret_cast<const int2*>(adj.p[l]);
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
     int2 st = __ldg(edges + e);
-    if ((unsigned)st.x < (unsigned)V && (unsigned)st.y < (unsigned)V) {
-      int pos = atomicAdd(cursor + (long long)l * V + st.y, 1);
-      src_sorted[pos] = st.x;
+    if ((unsigned)st.x < (unsigned)V_src && (unsigned)st.y < (unsigned)V_src) {
+      const unsigned t = (unsigned)(st.y - off);
+      if (t < (unsigned)V) {
+        int pos = atomicAdd(cursor + (long long)l * V + t, 1);
+        src_sorted[pos] = st.x;
+      }
     }
   }
 }
@@ -201,13 +205,14 @@ int exclusive_scan_inplace(int* data, long long n, int* block_sums_scratch, cuda
 
 using namespace tfgnn;
 
-extern "C" int tfgnn_b200_prepare(const int32_t* const* adj, const int64_t* num_edges,
-                                  int32_t L, int64_t V, uint32_t prepare_flags,
-                                  tfgnn_batch_t** out_batch, void* stream) {
+static int prepare_impl(const int32_t* const* adj, const int64_t* num_edges, int32_t L, int64_t V_total,
+                        int64_t tgt_begin, int64_t V, uint32_t prepare_flags, tfgnn_batch_t** out_batch,
+                        void* stream) {
   TFGNN_REQUIRE(out_batch != nullptr, "out_batch is NULL");
   *out_batch = nullptr;
   TFGNN_REQUIRE(L >= 0 && L <= TFGNN_MAX_EDGE_TYPES, "num_edge_types must be in [0, 32]");
-  TFGNN_REQUIRE(V >= 0 && V < (1ll << 31), "num_nodes must be in [0, 2^31)");
+  TFGNN_REQUIRE(V_total >= 0 && V_total < (1ll << 31), "num_nodes must be in [0, 2^31)");
+  TFGNN_REQUIRE(tgt_begin >= 0 && V >= 0 && tgt_begin + V <= V_total, "target range must lie inside [0, num_nodes]");
   TFGNN_REQUIRE(L == 0 || (adj != nullptr && num_edges != nullptr), "adj / num_edges is NULL");
   long long M = 0, maxE = 0;
   for (int l = 0; l < L; ++l) {
@@ -223,6 +228,8 @@ extern "C" int tfgnn_b200_prepare(const int32_t* const* adj, const int64_t* num_
 
   tfgnn_batch* b = new tfgnn_batch();
   b->V = V;
+  b->V_src = V_total;
+  b->tgt_off = tgt_begin;
   b->L = L;
   b->M_in = M;
   int rc = 0;
@@ -257,7 +264,8 @@ extern "C" int tfgnn_b200_prepare(const int32_t* const* adj, const int64_t* num_
     if (bx > 148 * 16) bx = 148 * 16;
     if (bx < 1) bx = 1;
     dim3 grid(bx, L);
-    count_targets_kernel<<<grid, 256, 0, st>>>(pt, ct, (int)V, b->row_ptr, b->invalid_count);
+    count_targets_kernel<<<grid, 256, 0, st>>>(pt, ct, (int)V, (int)V_total, (int)tgt_begin, b->row_ptr,
+                                               b->invalid_count);
     g_launch_count.fetch_add(1);
     TRY_CUDA(cudaGetLastError());
   }
@@ -275,7 +283,8 @@ extern "C" int tfgnn_b200_prepare(const int32_t* const* adj, const int64_t* num_
     int bx = ceil_div(maxE, 256);
     if (bx > 148 * 16) bx = 148 * 16;
     dim3 grid(bx, L);
-    fill_sources_kernel<<<grid, 256, 0, st>>>(pt, ct, (int)V, (int*)cursor, b->src_sorted);
+    fill_sources_kernel<<<grid, 256, 0, st>>>(pt, ct, (int)V, (int)V_total, (int)tgt_begin, (int*)cursor,
+                                              b->src_sorted);
     g_launch_count.fetch_add(1);
     TRY_CUDA(cudaGetLastError());
     long long warps_needed = S;
@@ -291,7 +300,7 @@ extern "C" int tfgnn_b200_prepare(const int32_t* const* adj, const int64_t* num_
     TRY_CUDA(cudaStreamSynchronize(st));
     if (bad) {
       set_error(TFGNN_ERR_INDEX_OUT_OF_RANGE,
-                std::to_string(bad) + " edge(s) reference a node outside [0, " + std::to_string(V) + ")");
+                std::to_string(bad) + " edge(s) reference a node outside [0, " + std::to_string(V_total) + ")");
       return fail(TFGNN_ERR_INDEX_OUT_OF_RANGE);
     }
   }
@@ -299,6 +308,18 @@ extern "C" int tfgnn_b200_prepare(const int32_t* const* adj, const int64_t* num_
 #undef TRY_CUDA
   *out_batch = b;
   return 0;
+}
+
+extern "C" int tfgnn_b200_prepare(const int32_t* const* adj, const int64_t* num_edges, int32_t L, int64_t V,
+                                  uint32_t prepare_flags, tfgnn_batch_t** out_batch, void* stream) {
+  return prepare_impl(adj, num_edges, L, V, 0, V, prepare_flags, out_batch, stream);
+}
+
+extern "C" int tfgnn_b200_prepare_sharded(const int32_t* const* adj, const int64_t* num_edges, int32_t L,
+                                          int64_t num_nodes_total, int64_t target_begin, int64_t target_count,
+                                          uint32_t prepare_flags, tfgnn_batch_t** out_batch, void* stream) {
+  return prepare_impl(adj, num_edges, L, num_nodes_total, target_begin, target_count, prepare_flags, out_batch,
+                      stream);
 }
 
 extern "C" int tfgnn_b200_free_batch(tfgnn_batch_t* b) {

@@ -53,11 +53,12 @@ extern "C" int tfgnn_b200_ggnn_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   eh.bias = gru_bias + 3 * H;
   rc = node_gemm((const float*)agg, H, gru_kernel, 3 * H, (float*)gx, 3 * H, V, 3 * H, H, ex, path, b, 6, st);
   if (rc) return rc;
-  rc = node_gemm(h, D, gru_recurrent_kernel, 3 * H, (float*)gh, 3 * H, V, 3 * H, H, eh, path, b, 6, st);
+  const float* h_tgt = h + (size_t)b->tgt_off * D;
+  rc = node_gemm(h_tgt, D, gru_recurrent_kernel, 3 * H, (float*)gh, 3 * H, V, 3 * H, H, eh, path, b, 6, st);
   if (rc) return rc;
   int blocks = ceil_div(V * H, 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  gru_gate_kernel<<<blocks, 256, 0, st>>>((const float*)gx, (const float*)gh, h, D, V, H, out);
+  gru_gate_kernel<<<blocks, 256, 0, st>>>((const float*)gx, (const float*)gh, h_tgt, D, V, H, out);
   TFGNN_LAUNCH_CHECK();
   return 0;
 }
@@ -129,8 +130,10 @@ extern "C" int tfgnn_b200_film_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
     first.p[l] = mlp_weights[l];
     film.p[l] = film_weights[l];
   }
+  const int Vs = (int)b->V_src;
+  const float* h_tgt = h + (size_t)b->tgt_off * D;
   void *P = nullptr, *Tt = nullptr, *Wcat = nullptr, *FB = nullptr, *Fcat = nullptr;
-  int rc = batch_scratch(b, 2, (size_t)V * LH * sizeof(float), &P);
+  int rc = batch_scratch(b, 2, (size_t)Vs * LH * sizeof(float), &P);
   if (rc) return rc;
   rc = batch_scratch(b, 3, (size_t)D * LH * sizeof(float), &Wcat);
   if (rc) return rc;
@@ -142,20 +145,20 @@ extern "C" int tfgnn_b200_film_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   // projected source messages P_l = h W^s_l  (gnn_edge_mlp.py:100 hoisted to node level)
   rc = launch_pack_horizontal(first, L, 0, D, H, H, (float*)Wcat, LH, st);
   if (rc) return rc;
-  rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)P, LH, V, LH, D, none, path, b, 6, st);
+  rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)P, LH, Vs, LH, D, none, path, b, 6, st);
   if (rc) return rc;
   if (use_target) {
     rc = batch_scratch(b, 4, (size_t)V * LH * sizeof(float), &Tt);
     if (rc) return rc;
     rc = launch_pack_horizontal(first, L, D, D, H, H, (float*)Wcat, LH, st);
     if (rc) return rc;
-    rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)Tt, LH, V, LH, D, none, path, b, 6, st);
+    rc = node_gemm(h_tgt, D, (const float*)Wcat, LH, (float*)Tt, LH, V, LH, D, none, path, b, 6, st);
     if (rc) return rc;
   }
   // FiLM parameters [gamma_l | beta_l] = h F_l depend on (target, type) only (gnn_film.py:99-103)
   rc = launch_pack_horizontal(film, L, 0, D, 2 * H, 2 * H, (float*)Fcat, 2 * LH, st);
   if (rc) return rc;
-  rc = node_gemm(h, D, (const float*)Fcat, 2 * LH, (float*)FB, 2 * LH, V, 2 * LH, D, none, path, b, 6, st);
+  rc = node_gemm(h_tgt, D, (const float*)Fcat, 2 * LH, (float*)FB, 2 * LH, V, 2 * LH, D, none, path, b, 6, st);
   if (rc) return rc;
   EdgeReduceParams p;
   p.X = (const float*)P; p.ldx = LH; p.x_type_stride = H;
@@ -205,8 +208,8 @@ __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : kLeakyRel
 template <bool VEC>
 __global__ void rgat_aggregate_kernel(const float* __restrict__ P, const float* __restrict__ s_src,
                                       const float* __restrict__ s_tgt, const int* __restrict__ row_ptr,
-                                      const int* __restrict__ src, long long V, int L, int K, int d, int act,
-                                      float* __restrict__ out) {
+                                      const int* __restrict__ src, long long V, long long tgt_off, int L, int K,
+                                      int d, int act, float* __restrict__ out) {
   const int H = K * d;
   const int cols = VEC ? H / 4 : H;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -219,7 +222,7 @@ __global__ void rgat_aggregate_kernel(const float* __restrict__ P, const float* 
   for (int l = 0; l < L; ++l) {
     const long long seg = (long long)l * V + v;
     const int beg = __ldg(row_ptr + seg), end = __ldg(row_ptr + seg + 1);
-    const float st = __ldg(s_tgt + v * LK + l * K + k);
+    const float st = __ldg(s_tgt + (v + tgt_off) * LK + l * K + k);
     for (int e = beg; e < end; ++e)
       m = fmaxf(m, leaky(__ldg(s_src + (long long)__ldg(src + e) * LK + l * K + k) + st));
   }
@@ -228,7 +231,7 @@ __global__ void rgat_aggregate_kernel(const float* __restrict__ P, const float* 
   for (int l = 0; l < L; ++l) {
     const long long seg = (long long)l * V + v;
     const int beg = __ldg(row_ptr + seg), end = __ldg(row_ptr + seg + 1);
-    const float st = __ldg(s_tgt + v * LK + l * K + k);
+    const float st = __ldg(s_tgt + (v + tgt_off) * LK + l * K + k);
     for (int e = beg; e < end; ++e) {
       const long long u = __ldg(src + e);
       const float w = expf(leaky(__ldg(s_src + u * LK + l * K + k) + st) - m);
@@ -262,7 +265,7 @@ extern "C" int tfgnn_b200_rgat_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   TFGNN_REQUIRE(D > 0 && H > 0 && num_heads > 0, "D, H and num_heads must be positive");
   TFGNN_REQUIRE(H % num_heads == 0, "hidden_dim must be divisible by num_heads (rgat.py:72)");
   TFGNN_REQUIRE(valid_act(activation), "unknown activation code");
-  const long long V = b->V;
+  const long long V = b->V, Vs = b->V_src;
   const int L = b->L, K = num_heads, d = H / num_heads;
   if (V == 0) return 0;
   TFGNN_REQUIRE(h && out, "h / out is NULL");
@@ -278,22 +281,22 @@ extern "C" int tfgnn_b200_rgat_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   void *P = nullptr, *Wcat = nullptr, *ss = nullptr, *stt = nullptr;
   int rc;
   if (L > 0) {
-    rc = batch_scratch(b, 2, (size_t)V * LH * sizeof(float), &P);
+    rc = batch_scratch(b, 2, (size_t)Vs * LH * sizeof(float), &P);
     if (rc) return rc;
     rc = batch_scratch(b, 3, (size_t)D * LH * sizeof(float), &Wcat);
     if (rc) return rc;
-    rc = batch_scratch(b, 13, (size_t)V * L * K * sizeof(float), &ss);
+    rc = batch_scratch(b, 13, (size_t)Vs * L * K * sizeof(float), &ss);
     if (rc) return rc;
-    rc = batch_scratch(b, 14, (size_t)V * L * K * sizeof(float), &stt);
+    rc = batch_scratch(b, 14, (size_t)Vs * L * K * sizeof(float), &stt);
     if (rc) return rc;
     // P_l = h W_l for every node once (rgat.py:102-109 applies the same Dense to source and target rows)
     rc = launch_pack_horizontal(wt, L, 0, D, H, H, (float*)Wcat, LH, st);
     if (rc) return rc;
     GemmEpilogue none;
-    rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)P, LH, V, LH, D, none, path, b, 6, st);
+    rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)P, LH, Vs, LH, D, none, path, b, 6, st);
     if (rc) return rc;
-    const long long total = V * L * K;
-    rgat_scores_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)P, V, L, K, d, at, (float*)ss,
+    const long long total = Vs * L * K;
+    rgat_scores_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)P, Vs, L, K, d, at, (float*)ss,
                                                             (float*)stt);
     TFGNN_LAUNCH_CHECK();
   }
@@ -301,10 +304,12 @@ extern "C" int tfgnn_b200_rgat_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   const long long threads = V * (vec ? H / 4 : H);
   if (vec)
     rgat_aggregate_kernel<true><<<ceil_div(threads, 128), 128, 0, st>>>(
-        (const float*)P, (const float*)ss, (const float*)stt, b->row_ptr, b->src_sorted, V, L, K, d, activation, out);
+        (const float*)P, (const float*)ss, (const float*)stt, b->row_ptr, b->src_sorted, V, b->tgt_off, L, K, d,
+        activation, out);
   else
     rgat_aggregate_kernel<false><<<ceil_div(threads, 128), 128, 0, st>>>(
-        (const float*)P, (const float*)ss, (const float*)stt, b->row_ptr, b->src_sorted, V, L, K, d, activation, out);
+        (const float*)P, (const float*)ss, (const float*)stt, b->row_ptr, b->src_sorted, V, b->tgt_off, L, K, d,
+        activation, out);
   TFGNN_LAUNCH_CHECK();
   return 0;
 }

@@ -50,7 +50,7 @@ class GGNN(GNN_Edge_MLP):
         self._check_types(prepared)
         if int(h.shape[1]) != self._hidden_dim:
             raise ValueError("GGNN: the node embedding dimension must equal hidden_dim")
-        out = torch.empty((h.shape[0], self._hidden_dim), dtype=torch.float32, device=h.device)
+        out = torch.empty((prepared.num_nodes, self._hidden_dim), dtype=torch.float32, device=h.device)
         ptrs, _keep = self._mlp_weight_ptrs()
         _ffi.check(_ffi.lib().tfgnn_b200_ggnn_fwd(
             prepared.handle, h.data_ptr(), int(h.shape[1]), ptrs, int(self._num_edge_MLP_hidden_layers),

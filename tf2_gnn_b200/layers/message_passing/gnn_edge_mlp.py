@@ -84,7 +84,7 @@ class GNN_Edge_MLP(MessagePassing):
              prepared: Optional[PreparedBatch] = None):
         h, prepared = self._device_inputs(inputs, prepared)
         self._check_types(prepared)
-        out = torch.empty((h.shape[0], self._hidden_dim), dtype=torch.float32, device=h.device)
+        out = torch.empty((prepared.num_nodes, self._hidden_dim), dtype=torch.float32, device=h.device)
         ptrs, _keep = self._mlp_weight_ptrs()
         _ffi.check(_ffi.lib().tfgnn_b200_edge_mlp_fwd(
             prepared.handle, h.data_ptr(), int(h.shape[1]), ptrs, int(self._num_edge_MLP_hidden_layers),

@@ -47,7 +47,7 @@ class GNN_FiLM(GNN_Edge_MLP):
         self._check_types(prepared)
         if any(m.num_hidden_layers for m in self._edge_type_film_layer_computations):
             raise NotImplementedError("film_parameter_MLP_hidden_layers != [] is not built yet")
-        out = torch.empty((h.shape[0], self._hidden_dim), dtype=torch.float32, device=h.device)
+        out = torch.empty((prepared.num_nodes, self._hidden_dim), dtype=torch.float32, device=h.device)
         ptrs, _keep = self._mlp_weight_ptrs()
         film = [m.layers[0].value for m in self._edge_type_film_layer_computations]
         _ffi.check(_ffi.lib().tfgnn_b200_film_fwd(

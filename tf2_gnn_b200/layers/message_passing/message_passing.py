@@ -161,7 +161,7 @@ class MessagePassing:
                 prepared = prepared_batch_for(adjs, h.shape[0])
             else:
                 prepared = PreparedBatch(adjs, h.shape[0])
-        elif prepared.num_nodes != h.shape[0]:
+        elif prepared.num_source_nodes != h.shape[0]:
             raise ValueError("prepared batch was built for a different number of nodes")
         return h, prepared
 

@@ -48,7 +48,7 @@ class RGAT(MessagePassing):
             raise ValueError("number of adjacency lists differs from the number the layer was built for")
         if self._hidden_dim % self._num_heads:
             raise ValueError("hidden_dim must be divisible by num_heads (rgat.py:72)")
-        out = torch.empty((h.shape[0], self._hidden_dim), dtype=torch.float32, device=h.device)
+        out = torch.empty((prepared.num_nodes, self._hidden_dim), dtype=torch.float32, device=h.device)
         kernels = [v.value for v in self._edge_type_to_message_computation_layer]
         att = [v.value for v in self._edge_type_to_attention_parameters]
         _ffi.check(_ffi.lib().tfgnn_b200_rgat_fwd(

@@ -45,7 +45,7 @@ class RGIN(GNN_Edge_MLP):
              prepared: Optional[PreparedBatch] = None):
         h, prepared = self._device_inputs(inputs, prepared)
         self._check_types(prepared)
-        out = torch.empty((h.shape[0], self._hidden_dim), dtype=torch.float32, device=h.device)
+        out = torch.empty((prepared.num_nodes, self._hidden_dim), dtype=torch.float32, device=h.device)
         ptrs, _keep = self._mlp_weight_ptrs()
         aggr = [v.value for v in (self._aggregation_mlp or [])]
         _ffi.check(_ffi.lib().tfgnn_b200_rgin_fwd(

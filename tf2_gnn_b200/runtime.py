@@ -68,9 +68,15 @@ class PreparedBatch:
     """Owner of a tfgnn_batch_t: the per-batch CSR (sorted by type,target) + in-degree, built once
     and shared by all layers (the adjacency is layer-invariant, gnn.py:278,301)."""
 
-    def __init__(self, adjacency_lists: Sequence[torch.Tensor], num_nodes: int, validate: bool = False):
+    def __init__(self, adjacency_lists: Sequence[torch.Tensor], num_nodes: int, validate: bool = False,
+                 target_range: Optional[Tuple[int, int]] = None):
+        """target_range=(lo, hi): this batch is one rank's target-range shard of a graph with `num_nodes`
+        nodes (sharding.py case 2); layer outputs then have hi-lo rows and `node_embeddings` passed to the
+        layers must be the full [num_nodes, D] table."""
         self.adjacency_lists = tuple(adjacency_lists)  # keep caller memory alive (atomic path reads it)
-        self.num_nodes = int(num_nodes)
+        self.num_source_nodes = int(num_nodes)
+        self.target_range = (0, int(num_nodes)) if target_range is None else (int(target_range[0]), int(target_range[1]))
+        self.num_nodes = self.target_range[1] - self.target_range[0]
         self.num_edge_types = len(self.adjacency_lists)
         if self.num_edge_types > _ffi.MAX_EDGE_TYPES:
             raise ValueError(f"at most {_ffi.MAX_EDGE_TYPES} edge types are supported")
@@ -78,8 +84,8 @@ class PreparedBatch:
         self._handle = c_void_p()
         ptrs = _ffi.ptr_array(self.adjacency_lists)
         counts = (c_int64 * max(self.num_edge_types, 1))(*self.num_edges)
-        _ffi.check(_ffi.lib().tfgnn_b200_prepare(
-            ptrs, counts, self.num_edge_types, self.num_nodes,
+        _ffi.check(_ffi.lib().tfgnn_b200_prepare_sharded(
+            ptrs, counts, self.num_edge_types, self.num_source_nodes, self.target_range[0], self.num_nodes,
             _ffi.PREPARE_VALIDATE if validate else 0, byref(self._handle), stream_ptr()))
         self._finalizer = weakref.finalize(self, PreparedBatch._free, self._handle.value)
 
