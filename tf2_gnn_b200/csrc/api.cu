@@ -124,7 +124,11 @@ static int rgcn_pipelined(tfgnn_batch* b, const float* h, int D, const float* Wc
     p.out = Abuf; p.ldo = K; p.out_type_stride = D;
     p.V = V; p.L = L; p.C = D; p.normalize = normalize;
     p.v_begin = v0; p.v_count = vc;
-    rc = launch_edge_reduce(p, /*merged=*/false, sg, /*max_blocks=*/148 * 6);
+    static const int gather_cap = [] {
+      const char* e = getenv("TFGNN_B200_PIPE_GATHER_BLOCKS");
+      return e && atoi(e) > 0 ? atoi(e) : 148 * 3;   // 3 lean CTAs/SM leave registers for the GEMM CTA
+    }();
+    rc = launch_edge_reduce(p, /*merged=*/false, sg, gather_cap);
     if (rc) return rc;
     TFGNN_CUDA(cudaEventRecord(b->ev_g[buf], sg));
     TFGNN_CUDA(cudaStreamWaitEvent(sm, b->ev_g[buf], 0));
@@ -197,6 +201,26 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
                            V >= 2 * pipe_chunk_rows() && D % 4 == 0 &&
                            gemm_tc_supported(V, H, K, h, K, out, ldo) &&
                            (reinterpret_cast<uintptr_t>(h) & 15) == 0;
+    const bool fused_ok = !use_target && fused_rgcn_supported(V, L, D, H, h, out, ldo);
+    if (path == TFGNN_PATH_FUSED_TC && !fused_ok)
+      return unsupported("TFGNN_PATH_FUSED_TC needs D % 32 == 0, 16 <= H <= 256, H % 16 == 0, no target-state input");
+    static const bool fused_auto = [] { const char* e = getenv("TFGNN_B200_FUSED"); return !e || atoi(e) != 0; }();
+    if (fused_ok && (path == TFGNN_PATH_FUSED_TC || (path == TFGNN_PATH_AUTO && fused_auto))) {
+      void *packed = nullptr, *ring = nullptr;
+      rc = launch_pack_vertical(first, L, 0, D, H, H, (float*)Wcat, H, 0, st);
+      if (rc) return rc;
+      rc = batch_scratch(b, 6, gemm_tc_packed_bytes(H, K), &packed);
+      if (rc) return rc;
+      rc = batch_scratch(b, 15, fused_rgcn_ring_bytes(D), &ring);
+      if (rc) return rc;
+      rc = launch_pack_weights_tc((const float*)Wcat, H, K, H, (float*)packed, st);
+      if (rc) return rc;
+      GemmEpilogue epi;
+      epi.act = activation;
+      epi.row_norm = row_norm; epi.row_ptr = b->row_ptr; epi.V = V; epi.L = L;
+      return launch_fused_rgcn(h, D, b->row_ptr, b->src_sorted, V, L, normalize, (const float*)packed, H,
+                               (float*)ring, out, ldo, epi, st);
+    }
     if (pipelined) {
       rc = launch_pack_vertical(first, L, 0, D, H, H, (float*)Wcat, H, 0, st);
       if (rc) return rc;

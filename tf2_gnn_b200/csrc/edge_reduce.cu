@@ -7,6 +7,8 @@
 // One warp owns one segment (PER_TYPE mode: segment (l,v) -> out[v, l*stride + :]) or one
 // target node (MERGED mode: all L segments of v reduced into out[v, :]), so the reduction is a
 // register accumulation in CSR order: no atomics, run-to-run deterministic.
+#include <cstdlib>
+
 #include "edge_reduce.cuh"
 
 namespace tfgnn {
@@ -47,8 +49,11 @@ struct EdgeFn {
 };
 
 // NV = float4 column groups per lane (C <= 128*NV).  PLAIN: identity message + sum, scale at end.
-template <int NV, bool MERGED, bool PLAIN>
-__global__ void __launch_bounds__(256) edge_reduce_kernel(const EdgeReduceParams p) {
+// U = edges loaded per round (loads in flight per lane = U*NV).  The lean PLAIN variant trades unroll
+// depth for occupancy (<= 40 registers -> 6 CTAs/SM): the gather is bound by the number of independent
+// row_ptr -> index -> row dependency chains in flight, i.e. by resident warps, not by loads per warp.
+template <int NV, bool MERGED, bool PLAIN, int U = 4, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB) edge_reduce_kernel(const EdgeReduceParams p) {
   const int lane = threadIdx.x & 31;
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long warp_stride = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -110,10 +115,10 @@ __global__ void __launch_bounds__(256) edge_reduce_kernel(const EdgeReduceParams
       const int n = min(32, end - base);
       const int my_src = lane < n ? __ldg(p.src + base + lane) : 0;
       int e = 0;
-      for (; e + 4 <= n; e += 4) {
-        float4 r[4][NV];
+      for (; e + U <= n; e += U) {
+        float4 r[U][NV];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
           const int s = __shfl_sync(0xffffffffu, my_src, e + u);
           const float* row = xbase + (long long)s * p.ldx;
 #pragma unroll
@@ -123,7 +128,7 @@ __global__ void __launch_bounds__(256) edge_reduce_kernel(const EdgeReduceParams
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < U; ++u)
 #pragma unroll
           for (int j = 0; j < NV; ++j) {
             if (PLAIN) {
@@ -304,11 +309,13 @@ int launch_edge_reduce(const EdgeReduceParams& p_in, bool merged, cudaStream_t s
     return 0;
   }
   const int nv = (p.C + 127) / 128;
+  static const bool lean = [] { const char* e = getenv("TFGNN_B200_GATHER_LEAN"); return !e || atoi(e) != 0; }();
   int blocks = ceil_div(items * 32, 256);
   if (max_blocks > 0 && blocks > max_blocks) blocks = max_blocks;
 #define TFGNN_ER_LAUNCH(NV)                                                              \
   do {                                                                                   \
     if (merged) edge_reduce_kernel<NV, true, false><<<blocks, 256, 0, st>>>(p);          \
+    else if (plain && lean) edge_reduce_kernel<NV, false, true, 2, (NV == 1 ? 6 : 5)><<<blocks, 256, 0, st>>>(p); \
     else if (plain) edge_reduce_kernel<NV, false, true><<<blocks, 256, 0, st>>>(p);      \
     else edge_reduce_kernel<NV, false, false><<<blocks, 256, 0, st>>>(p);                \
   } while (0)

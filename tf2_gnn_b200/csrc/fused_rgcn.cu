@@ -1,0 +1,454 @@
+// The fused RGCN-style layer: ONE persistent kernel does gather(h[src]) -> segment-sum -> 1/(c+eps)
+// -> 3xTF32 tcgen05 contraction with [W_0;..;W_{L-1}] -> row-norm / activation -> out.
+//
+//   out[v] = act( rn(v) * sum_l ( 1/(c_{v,l}+eps) * sum_{(u,v) in A_l} h_u ) W_l )       (rgcn.py:13-48)
+//
+// One CTA per SM owns 128-target tiles.  Inside the CTA, 16 GATHER warps produce, per edge type l, the
+// normalised row sums A_l[128, D] (full 4*D-byte row reads from HBM, register accumulation, no atomics)
+// into a small per-CTA ring in global memory that stays L2-resident (3 slots x 128 x D x 4 B per CTA,
+// 57 MB chip-wide at D=256: the fp32-accurate operand does not fit the 227 KB of shared memory).  The
+// TMA producer pulls each slot back in 128 B K-slices next to the pre-split weight tiles; splitter warps
+// cut A into tf32 hi/lo; one thread issues the tcgen05 MMAs into TMEM (main + correction accumulators,
+// double-buffered); epilogue warps drain TMEM through a staging tile to coalesced stores.  The gather
+// of slot i+1..i+3 overlaps the MMAs of slot i, so the kernel runs at the HBM rate of the gather and the
+// [V, L*D] intermediate never touches HBM.
+//
+// Warp roles (832 threads): 0 TMA | 1 MMA | 2-5 split | 6-9 epilogue | 10-25 gather.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "gemm.cuh"
+#include "sm100_ptx.cuh"
+
+namespace tfgnn {
+
+constexpr int kFuBM = 128;
+constexpr int kFuBK = 32;
+constexpr int kFuATileBytes = kFuBM * 128;
+constexpr int kFuGatherWarps = 16;
+constexpr int kFuThreads = 32 * (10 + kFuGatherWarps);
+constexpr int kFuSlots = 3;
+constexpr int kFuTmemCols = 512;
+constexpr int kFuAccStride = 256;
+constexpr int kFuSmemLimit = 227 * 1024;
+constexpr int kFuEpiPitch = 36;
+constexpr int kFuEpiBytes = 4 * 32 * kFuEpiPitch * 4;
+
+struct FusedParams {
+  // graph
+  const float* h;
+  int ldh;
+  const int* row_ptr;
+  const int* src;
+  int V, L, D;
+  int normalize;
+  // ring
+  float* ring;  // [grid * kFuSlots * 128, D]
+  // GEMM
+  int N, block_n, n_tiles;
+  long long m_tiles;
+  int kb_per_type, num_stages;
+  float* C;
+  int ldc;
+  GemmEpilogue epi;
+};
+
+__device__ __forceinline__ float fu_row_norm(const GemmEpilogue& e, long long row) {
+  if (e.row_norm == 0) return 1.0f;
+  int cnt = 0;
+  for (int l = 0; l < e.L; ++l) {
+    const long long s = (long long)l * e.V + e.row0 + row;
+    cnt += __ldg(e.row_ptr + s + 1) - __ldg(e.row_ptr + s);
+  }
+  const float c = (float)max(cnt, 1);
+  return e.row_norm == 1 ? c : sqrtf(c);
+}
+
+template <int NV>
+__device__ __forceinline__ void gather_segment_rows(const FusedParams& p, int l, int v, int lane, float* dst) {
+  const int C4 = p.D >> 2;
+  const long long seg = (long long)l * p.V + v;
+  const int beg = __ldg(p.row_ptr + seg), end = __ldg(p.row_ptr + seg + 1);
+  const float scale = p.normalize ? 1.0f / ((float)(end - beg) + kSmallNumber) : 1.0f;
+  float4 acc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int base = beg; base < end; base += 32) {
+    const int n = min(32, end - base);
+    const int my_src = lane < n ? __ldg(p.src + base + lane) : 0;
+    int e = 0;
+    for (; e + 2 <= n; e += 2) {
+      float4 r[2][NV];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int s = __shfl_sync(0xffffffffu, my_src, e + u);
+        const float* row = p.h + (long long)s * p.ldh;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          const int c4 = lane + 32 * j;
+          r[u][j] = c4 < C4 ? ldg_f4(row + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          acc[j].x += r[u][j].x; acc[j].y += r[u][j].y; acc[j].z += r[u][j].z; acc[j].w += r[u][j].w;
+        }
+    }
+    if (e < n) {
+      const int s = __shfl_sync(0xffffffffu, my_src, e);
+      const float* row = p.h + (long long)s * p.ldh;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c4 = lane + 32 * j;
+        if (c4 < C4) {
+          const float4 x = ldg_f4(row + 4 * c4);
+          acc[j].x += x.x; acc[j].y += x.y; acc[j].z += x.z; acc[j].w += x.w;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c4 = lane + 32 * j;
+    if (c4 < C4)
+      *reinterpret_cast<float4*>(dst + 4 * c4) =
+          make_float4(acc[j].x * scale, acc[j].y * scale, acc[j].z * scale, acc[j].w * scale);
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(kFuThreads, 1)
+fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                  const FusedParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.num_stages;
+  const int b_tile_bytes = p.block_n * 128;
+  const int stage_bytes = 2 * kFuATileBytes + 2 * b_tile_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* split = bars + S;
+  uint64_t* empty = bars + 2 * S;
+  uint64_t* tmem_full = bars + 3 * S;
+  uint64_t* tmem_empty = bars + 3 * S + 2;
+  uint64_t* slot_ready = bars + 3 * S + 4;
+  uint64_t* slot_free = bars + 3 * S + 4 + kFuSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4 + 2 * kFuSlots);
+  float* epi_stage = reinterpret_cast<float*>(bars + ((3 * S + 4 + 2 * kFuSlots + 2 + 1) & ~1));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long total_tiles = p.m_tiles * p.n_tiles;
+  const int kb_per_tile = p.L * p.kb_per_type;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&map_a);
+    ptx::prefetch_tensormap(&map_b);
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&split[s], 128);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 128);
+    }
+    for (int r = 0; r < kFuSlots; ++r) {
+      ptx::mbar_init(&slot_ready[r], kFuGatherWarps);
+      ptx::mbar_init(&slot_free[r], 128);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, kFuTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t n_acc = p.block_n <= 128 ? 2 : 1;
+  const uint32_t corr_off = p.block_n <= 128 ? 128 : 256;
+  const int ring_row0 = blockIdx.x * kFuSlots * kFuBM;  // first ring row of this CTA
+
+  // NOTE on tiles: with n_tiles > 1 the same 128 targets would be gathered once per N tile; the host
+  // only launches this kernel with n_tiles == 1 ... or accepts the re-gather (see launch_fused_rgcn).
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t it = 0, slot_it = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n0 = (int)(tile % p.n_tiles) * p.block_n;
+        for (int l = 0; l < p.L; ++l, ++slot_it) {
+          const int slot = slot_it % kFuSlots;
+          ptx::mbar_wait(&slot_ready[slot], (slot_it / kFuSlots) & 1);
+          for (int kb = 0; kb < p.kb_per_type; ++kb, ++it) {
+            const int s = it % S;
+            const uint32_t ph = (it / S) & 1;
+            ptx::mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* st = smem + (size_t)s * stage_bytes;
+            ptx::mbar_arrive_expect_tx(&full[s], kFuATileBytes + 2 * b_tile_bytes);
+            ptx::tma_load_2d(st, &map_a, &full[s], kb * kFuBK, ring_row0 + slot * kFuBM);
+            const int kcol = (l * p.kb_per_type + kb) * kFuBK;
+            ptx::tma_load_2d(st + 2 * kFuATileBytes, &map_b, &full[s], kcol, n0);
+            ptx::tma_load_2d(st + 2 * kFuATileBytes + b_tile_bytes, &map_b, &full[s], kcol, p.N + n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t idesc = ptx::umma_idesc_tf32_m128((uint32_t)p.block_n);
+    uint32_t it = 0, tile_count = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_count) {
+      const uint32_t acc = tile_count % n_acc, acc_ph = (tile_count / n_acc) & 1;
+      ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+      ptx::tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + acc * kFuAccStride;
+      const uint32_t c_tmem = d_tmem + corr_off;
+      for (int kb = 0; kb < kb_per_tile; ++kb, ++it) {
+        const int s = it % S;
+        const uint32_t ph = (it / S) & 1;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::mbar_wait(&split[s], ph);
+        ptx::tc_fence_after_sync();
+        if (lane == 0) {
+          const uint32_t st = ptx::smem_u32(smem + (size_t)s * stage_bytes);
+          const uint64_t a_hi = ptx::umma_desc_k_sw128(st);
+          const uint64_t a_lo = ptx::umma_desc_k_sw128(st + kFuATileBytes);
+          const uint64_t b_hi = ptx::umma_desc_k_sw128(st + 2 * kFuATileBytes);
+          const uint64_t b_lo = ptx::umma_desc_k_sw128(st + 2 * kFuATileBytes + b_tile_bytes);
+#pragma unroll
+          for (int k = 0; k < kFuBK / 8; ++k) {
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);
+            ptx::mma_tf32_ss(c_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+            ptx::mma_tf32_ss(c_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+            ptx::mma_tf32_ss(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+          }
+          ptx::mma_commit(&empty[s]);
+          if (kb == kb_per_tile - 1) ptx::mma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    // ================= A splitters =================
+    const int tid = threadIdx.x - 64;
+    uint32_t it = 0, slot_it = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int l = 0; l < p.L; ++l, ++slot_it) {
+        for (int kb = 0; kb < p.kb_per_type; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (it / S) & 1;
+          ptx::mbar_wait(&full[s], ph);
+          if (kb == p.kb_per_type - 1) ptx::mbar_arrive(&slot_free[slot_it % kFuSlots]);  // all TMA reads of the slot landed
+          float4* a = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
+          float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + kFuATileBytes);
+#pragma unroll
+          for (int i = 0; i < kFuATileBytes / 16 / 128; ++i) {
+            const int idx = tid + i * 128;
+            const float4 x = a[idx];
+            float4 hh, ll;
+            hh.x = ptx::tf32_hi(x.x); hh.y = ptx::tf32_hi(x.y); hh.z = ptx::tf32_hi(x.z); hh.w = ptx::tf32_hi(x.w);
+            ll.x = ptx::tf32_hi(x.x - hh.x); ll.y = ptx::tf32_hi(x.y - hh.y);
+            ll.z = ptx::tf32_hi(x.z - hh.z); ll.w = ptx::tf32_hi(x.w - hh.w);
+            a[idx] = hh;
+            lo[idx] = ll;
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&split[s]);
+        }
+      }
+    }
+  } else if (warp < 10) {
+    // ================= epilogue =================
+    const int q = warp & 3;
+    uint32_t tile_count = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_count) {
+      const long long m0 = (tile / p.n_tiles) * kFuBM;
+      const int n0 = (int)(tile % p.n_tiles) * p.block_n;
+      const uint32_t acc = tile_count % n_acc, acc_ph = (tile_count / n_acc) & 1;
+      ptx::mbar_wait(&tmem_full[acc], acc_ph);
+      ptx::tc_fence_after_sync();
+      const long long row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.V;
+      const float rn = row_ok ? fu_row_norm(p.epi, row) : 1.0f;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kFuAccStride;
+      float* stage = epi_stage + (size_t)(warp - 6) * 32 * kFuEpiPitch;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        const int ncols = min(32, p.block_n - c0);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half * 16 < ncols) {
+            float v[16], w[16];
+            ptx::tmem_ld_x16(taddr + c0 + half * 16, v);
+            ptx::tmem_ld_x16(taddr + corr_off + c0 + half * 16, w);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = v[j] + w[j];
+              if (p.epi.row_norm) x = x / rn;
+              if (p.epi.bias) x += __ldg(p.epi.bias + n0 + c0 + half * 16 + j);
+              v[j] = apply_act(x, p.epi.act);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(stage + lane * kFuEpiPitch + half * 16 + j) =
+                  make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          }
+        }
+        __syncwarp();
+        const int f4_per_row = ncols / 4;
+        const int rows_per_it = 32 / f4_per_row;
+        const int rr = lane / f4_per_row, cc = (lane % f4_per_row) * 4;
+        for (int r0 = 0; r0 < 32; r0 += rows_per_it) {
+          const int r = r0 + rr;
+          const long long grow = m0 + q * 32 + r;
+          if (grow < p.V) {
+            const float4 val = *reinterpret_cast<const float4*>(stage + r * kFuEpiPitch + cc);
+            *reinterpret_cast<float4*>(p.C + grow * p.ldc + n0 + c0 + cc) = val;
+          }
+        }
+        __syncwarp();
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  } else {
+    // ================= gather warps =================
+    const int gw = warp - 10;
+    uint32_t slot_it = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (int)((tile / p.n_tiles) * kFuBM);
+      for (int l = 0; l < p.L; ++l, ++slot_it) {
+        const int slot = slot_it % kFuSlots;
+        ptx::mbar_wait(&slot_free[slot], ((slot_it / kFuSlots) & 1) ^ 1);
+        float* slot_base = p.ring + ((size_t)ring_row0 + (size_t)slot * kFuBM) * p.D;
+        for (int r = gw; r < kFuBM; r += kFuGatherWarps) {
+          const int v = m0 + r;
+          if (v < p.V) gather_segment_rows<NV>(p, l, v, lane, slot_base + (size_t)r * p.D);
+        }
+        // generic-proxy global writes -> visible to the TMA (async proxy) reads of this CTA
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&slot_ready[slot]);
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_base, kFuTmemCols);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn fu_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+bool fused_rgcn_supported(long long V, int L, int D, int H, const float* h, const float* out, int ldo) {
+  if (V < 1 || L < 1 || D % kFuBK != 0 || D > 512 || H % 16 != 0 || H < 16 || H > 256) return false;
+  if ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(out)) & 15) return false;
+  if (ldo % 4 != 0) return false;
+  // one N tile per 128 targets so that every source row is gathered exactly once: the whole H must fit one
+  // accumulator pair in TMEM (main + correction): H <= 256.
+  return gemm_tc_supported(V, H, L * D, h, D, out, ldo) && fu_encode_fn() != nullptr;
+}
+
+constexpr int kFuMaxGrid = 160;
+size_t fused_rgcn_ring_bytes(int D) { return (size_t)kFuMaxGrid * kFuSlots * kFuBM * D * sizeof(float); }
+
+int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src, int V, int L, int normalize,
+                      const float* packedB, int H, float* ring, float* out, int ldo, const GemmEpilogue& epi,
+                      cudaStream_t st) {
+  EncodeTiledFn encode = fu_encode_fn();
+  if (!encode) {
+    set_error(TFGNN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    return TFGNN_ERR_CUDA;
+  }
+  int dev = 0, sms = 148;
+  TFGNN_CUDA(cudaGetDevice(&dev));
+  TFGNN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  FusedParams p{};
+  p.h = h; p.ldh = D; p.row_ptr = row_ptr; p.src = src; p.V = V; p.L = L; p.D = D; p.normalize = normalize;
+  p.ring = ring;
+  p.N = H; p.block_n = H; p.n_tiles = 1;
+  p.m_tiles = ((long long)V + kFuBM - 1) / kFuBM;
+  p.kb_per_type = D / kFuBK;
+  const int stage_bytes = 2 * kFuATileBytes + 2 * p.block_n * 128;
+  int stages = (kFuSmemLimit - 2048 - kFuEpiBytes) / stage_bytes;
+  if (stages > 4) stages = 4;
+  TFGNN_REQUIRE(stages >= 2, "fused RGCN: tile does not fit shared memory");
+  p.num_stages = stages;
+  p.C = out; p.ldc = ldo; p.epi = epi;
+  if (sms > kFuMaxGrid) sms = kFuMaxGrid;
+  const int grid = (int)(p.m_tiles < sms ? p.m_tiles : sms);
+
+  const int Kp = L * D;
+  CUtensorMap map_a, map_b;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)grid * kFuSlots * kFuBM};
+    cuuint64_t strides[1] = {(cuuint64_t)D * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)kFuBK, (cuuint32_t)kFuBM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ring, dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error(TFGNN_ERR_CUDA, "cuTensorMapEncodeTiled(ring) failed with code " + std::to_string((int)r));
+      return TFGNN_ERR_CUDA;
+    }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)(2 * H)};
+    cuuint64_t strides[1] = {(cuuint64_t)Kp * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)kFuBK, (cuuint32_t)p.block_n};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(packedB), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error(TFGNN_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed with code " + std::to_string((int)r));
+      return TFGNN_ERR_CUDA;
+    }
+  }
+  const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4 + 2 * kFuSlots + 4) * sizeof(uint64_t) +
+                            kFuEpiBytes + 1024;
+  const int nv = (D + 127) / 128;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    cudaError_t e1 = cudaFuncSetAttribute(fused_rgcn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit);
+    cudaError_t e2 = cudaFuncSetAttribute(fused_rgcn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit);
+    cudaError_t e3 = cudaFuncSetAttribute(fused_rgcn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit);
+    cudaError_t e4 = cudaFuncSetAttribute(fused_rgcn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit);
+    attr_err = e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3 != cudaSuccess ? e3 : e4;
+  });
+  TFGNN_CUDA(attr_err);
+  switch (nv) {
+    case 1: fused_rgcn_kernel<1><<<grid, kFuThreads, smem_bytes, st>>>(map_a, map_b, p); break;
+    case 2: fused_rgcn_kernel<2><<<grid, kFuThreads, smem_bytes, st>>>(map_a, map_b, p); break;
+    case 3: fused_rgcn_kernel<3><<<grid, kFuThreads, smem_bytes, st>>>(map_a, map_b, p); break;
+    default: fused_rgcn_kernel<4><<<grid, kFuThreads, smem_bytes, st>>>(map_a, map_b, p); break;
+  }
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace tfgnn

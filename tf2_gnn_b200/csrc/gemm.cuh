@@ -26,6 +26,13 @@ int launch_pack_weights_tc(const float* B, int ldb, int K, int N, float* packed,
 int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int ldc, long long M, int N,
                    int K, const GemmEpilogue& epi, cudaStream_t st);
 
+// Fused RGCN-style layer (fused_rgcn.cu): gather -> segment-sum -> 3xTF32 tcgen05 -> epilogue in one kernel.
+bool fused_rgcn_supported(long long V, int L, int D, int H, const float* h, const float* out, int ldo);
+size_t fused_rgcn_ring_bytes(int D);
+int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src, int V, int L, int normalize,
+                      const float* packedB, int H, float* ring, float* out, int ldo, const GemmEpilogue& epi,
+                      cudaStream_t st);
+
 // Weight packing helpers: gather per-type matrices into one node-level operand.
 //  vertical:   dst[(blk*rows + r), :] = src_blk[row0 + r, :]          (aggregate-then-transform)
 //  horizontal: dst[r, blk*cols + c]  = src_blk[row0 + r, c]           (transform-then-aggregate)

@@ -128,10 +128,11 @@ __global__ void fill_sources_kernel(PtrTable adj, CountTable E, int V, int V_src
 // Canonical order inside every segment (ascending source id): the fill above lands edges in
 // atomic-arrival order, which would make float sums differ from one prepare() to the next.
 // Duplicate edges carry equal ids, so ascending order is a unique arrangement.
-// One warp per segment; short segments (<=32) use a shuffle bitonic network, longer ones an
-// in-place odd-even transposition over global memory by the warp (rare: hubs).
+// One warp per segment; short segments (<=32) use a shuffle bitonic network, medium ones (<=256) an
+// in-place odd-even transposition by the warp, hubs are queued for sort_long_segments_kernel.
 __global__ void sort_segments_kernel(const int* __restrict__ row_ptr, long long num_segments,
-                                     int* __restrict__ src_sorted) {
+                                     int* __restrict__ src_sorted, long long* __restrict__ long_list,
+                                     int* __restrict__ long_count) {
   const int lane = threadIdx.x & 31;
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long num_warps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -166,8 +167,54 @@ __global__ void sort_segments_kernel(const int* __restrict__ row_ptr, long long 
         __syncwarp();
       }
     }
-    // len > 256 (hubs): left in arrival order — the order is fixed for the lifetime of the
-    // batch handle, so every layer call on this batch is reproducible (DESIGN.md "Determinism").
+    else {
+      // hubs: queued for the block-level sorter below
+      if (lane == 0) {
+        const int slot = atomicAdd(long_count, 1);
+        long_list[slot] = s;
+      }
+    }
+  }
+}
+
+// Hub segments (> 256 edges): in-place bitonic sort (all-ascending "flip + disperse" network, so the
+// virtual +inf padding beyond the segment end never moves) by one CTA per segment over global memory
+// (L2 resident).  Makes the summation order of every segment a function of the graph alone.
+__global__ void __launch_bounds__(512) sort_long_segments_kernel(const int* __restrict__ row_ptr,
+                                                                 const long long* __restrict__ long_list,
+                                                                 const int* __restrict__ long_count,
+                                                                 int* __restrict__ src_sorted) {
+  const int count = *long_count;
+  for (int li = blockIdx.x; li < count; li += gridDim.x) {
+    const long long s = long_list[li];
+    const int beg = row_ptr[s], n = row_ptr[s + 1] - beg;
+    int* a = src_sorted + beg;
+    int P = 1;
+    while (P < n) P <<= 1;
+    const int half = P >> 1;
+    for (int k = 2; k <= P; k <<= 1) {
+      const int hk = k >> 1;
+      for (int i = threadIdx.x; i < half; i += blockDim.x) {  // flip: i-th pair mirrors inside its k-block
+        const int blk = i / hk, off = i - blk * hk;
+        const int lo = blk * k + off, hi = blk * k + k - 1 - off;
+        if (hi < n) {
+          const int x = a[lo], y = a[hi];
+          if (x > y) { a[lo] = y; a[hi] = x; }
+        }
+      }
+      __syncthreads();
+      for (int j = k >> 2; j > 0; j >>= 1) {                   // disperse
+        for (int i = threadIdx.x; i < half; i += blockDim.x) {
+          const int blk = i / j, off = i - blk * j;
+          const int lo = blk * 2 * j + off, hi = lo + j;
+          if (hi < n) {
+            const int x = a[lo], y = a[hi];
+            if (x > y) { a[lo] = y; a[hi] = x; }
+          }
+        }
+        __syncthreads();
+      }
+    }
   }
 }
 
@@ -290,7 +337,17 @@ static int prepare_impl(const int32_t* const* adj, const int64_t* num_edges, int
     long long warps_needed = S;
     int blocks = ceil_div(warps_needed * 32, 256);
     if (blocks > 148 * 32) blocks = 148 * 32;
-    sort_segments_kernel<<<blocks, 256, 0, st>>>(b->row_ptr, S, b->src_sorted);
+    // a segment longer than 256 edges is a "hub"; there are at most M/257 of them
+    const long long max_long = M / 257 + 1;
+    void* long_buf = nullptr;
+    TRY(batch_scratch(b, 7, (size_t)max_long * sizeof(long long) + 16, &long_buf));
+    int* long_count = reinterpret_cast<int*>(long_buf);
+    long long* long_list = reinterpret_cast<long long*>(reinterpret_cast<char*>(long_buf) + 16);
+    TRY_CUDA(cudaMemsetAsync(long_count, 0, sizeof(int), st));
+    sort_segments_kernel<<<blocks, 256, 0, st>>>(b->row_ptr, S, b->src_sorted, long_list, long_count);
+    g_launch_count.fetch_add(1);
+    TRY_CUDA(cudaGetLastError());
+    sort_long_segments_kernel<<<148 * 2, 512, 0, st>>>(b->row_ptr, long_list, long_count, b->src_sorted);
     g_launch_count.fetch_add(1);
     TRY_CUDA(cudaGetLastError());
   }
