@@ -33,21 +33,39 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (V, edges per type list, H, kind, description)
-    "cfg2": dict(V=1_000_000, E=[5_000_000] * 4, H=256, kind="rgcn",
+    # BASELINE.json configs; the default (N=1) bench line is cfg2, the others are recorded with --workload.
+    "cfg2": dict(V=1_000_000, E=[5_000_000] * 4, H=256, kind="rgcn", graph="er",
                  desc="RGCN synthetic Erdos-Renyi 1M nodes / 20M edges / 4 edge types, hidden_dim=256 "
                       "(BASELINE.json configs[1])"),
-    "cfg1": dict(V=8000, E=[8000, 115_200, 115_200], H=320, kind="rgcn",
+    "cfg1": dict(V=8000, E=[8000, 115_200, 115_200], H=320, kind="rgcn", graph="ppi",
                  desc="RGCN PPI-shaped hidden_dim=320, 3 edge types, 8000 nodes (BASELINE.json configs[0])"),
-    "tiny": dict(V=20_000, E=[100_000] * 4, H=256, kind="rgcn", desc="smoke-sized cfg2"),
+    "cfg3": dict(V=2_000_000, E=[20_000_000] * 3, H=128, kind="rgat", graph="powerlaw", params=dict(num_heads=4),
+                 desc="RGAT 4-head synthetic power-law 2M nodes / 60M edges / 3 edge types, hidden_dim=128 "
+                      "(BASELINE.json configs[2])"),
+    "cfg4": dict(V=500_000, E=[500_000, 600_000, 250_000, 50_000, 100_000], H=128, kind="ggnn", graph="er",
+                 desc="GGNN QM9-shaped 500k nodes / 1.5M edges / 5 edge types, hidden_dim=128 (BASELINE.json configs[3])"),
+    "cfg5_shard": dict(V=2_000_000, E=[5_333_333] * 6, H=320, kind="gnn_film", graph="er",
+                       desc="GNN-FiLM 1/8 shard of BASELINE.json configs[4]: 2M nodes / 32M edges / 6 edge types, hidden_dim=320"),
+    "tiny": dict(V=20_000, E=[100_000] * 4, H=256, kind="rgcn", graph="er", desc="smoke-sized cfg2"),
 }
 METRIC = "edges/sec (fused gather-msg-scatter)"
 
 
-def algorithmic_bytes(V, E_list, D, H, normalize=True):
-    """sum_l E_l*(8+4D) + 4VH + 4*sum(weights) + 4LV."""
-    L = len(E_list)
-    return sum(E_list) * (8 + 4 * D) + 4 * V * H + 4 * L * D * H + (4 * L * V if normalize else 0)
+def algorithmic_bytes(kind, V, E_list, D, H, params):
+    """sum_l E_l*(8+4*D_g) + 4VH + 4*sum(weights) [+4LV normalise] [+4VD target input]
+    [+8VH GGNN GRU reads]; D_g = D (H + K source scores for RGAT)."""
+    L, M = len(E_list), sum(E_list)
+    if kind == "rgat":
+        K = params["num_heads"]
+        return M * (8 + 4 * (H + K)) + 4 * V * H + 4 * L * (D * H + 2 * H) + 4 * V * D
+    b = M * (8 + 4 * D) + 4 * V * H + 4 * L * D * H
+    if params.get("normalize_by_num_incoming"):
+        b += 4 * L * V
+    if kind == "gnn_film":
+        b += 4 * L * D * 2 * H + 4 * V * D
+    if kind == "ggnn":
+        b += 8 * V * H + 4 * (2 * H * 3 * H + 6 * H)
+    return b
 
 
 def make_inputs(wl, seed):
@@ -55,9 +73,15 @@ def make_inputs(wl, seed):
     V, H = wl["V"], wl["H"]
     adjs = []
     for l, E in enumerate(wl["E"]):
-        if wl is WORKLOADS["cfg1"] and l == 0:
+        if wl["graph"] == "ppi" and l == 0:
             ids = np.arange(V, dtype=np.int32)
             adjs.append(np.stack([ids, ids], axis=1))
+        elif wl["graph"] == "powerlaw":
+            # target in-degrees ~ Zipf(2.1) capped at 1e5, sources uniform
+            deg = np.minimum(rng.zipf(2.1, size=V), 100_000).astype(np.float64)
+            tgt = rng.choice(V, size=E, p=deg / deg.sum()).astype(np.int32)
+            src = rng.integers(0, V, size=E, dtype=np.int32)
+            adjs.append(np.stack([src, tgt], axis=1))
         else:
             adjs.append(rng.integers(0, V, size=(E, 2), dtype=np.int32))
     h = rng.random((V, H), dtype=np.float32) * 2.0 - 1.0           # U(-1,1): post-tanh range
@@ -187,6 +211,9 @@ def reference_arm(args, wl, rank, world):
     """--impl reference: the reference's CPU path (restated port; TF is not installable here)."""
     if rank != 0:
         return
+    if wl["kind"] != "rgcn":
+        print(json.dumps({"impl": "reference", "unavailable": "timed CPU port exists for the RGCN workloads only"}))
+        return
     threads = os.cpu_count() or 1
     h, adjs, weights = make_inputs(wl, seed=0)
     M = sum(a.shape[0] for a in adjs)
@@ -236,7 +263,7 @@ def main():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback exists)")
     from tf2_gnn_b200 import _ffi
     from tf2_gnn_b200.build import build_library
-    from tf2_gnn_b200.layers import MessagePassingInput, RGCN
+    from tf2_gnn_b200.layers import MessagePassingInput, get_message_passing_class
     from tf2_gnn_b200.runtime import PreparedBatch
     build_library()
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -249,11 +276,16 @@ def main():
     adj_host = [torch.from_numpy(a).pin_memory() for a in adjs_np]
     out_host = torch.empty((V, H), dtype=torch.float32).pin_memory()
 
-    params = RGCN.get_default_hyperparameters()
+    kind = wl["kind"]
+    layer_cls = get_message_passing_class(kind)
+    params = layer_cls.get_default_hyperparameters()
+    params.update(wl.get("params", {}))
     params.update(hidden_dim=H, b200_path=args.path)
-    layer = RGCN(params)
-    layer.build(MessagePassingInput((None, H), tuple((None, 2) for _ in range(L))))
-    layer.set_weights_from_oracle_dict({"edge_mlps": [[w] for w in w_np]})
+    layer = layer_cls(params)
+    torch.manual_seed(1234 + rank)
+    layer.build(MessagePassingInput((None, H), tuple((None, 2) for _ in range(L))))  # Glorot-uniform weights
+    if kind == "rgcn":
+        layer.set_weights_from_oracle_dict({"edge_mlps": [[w] for w in w_np]})
 
     # ---- device-resident leg -------------------------------------------------------------
     h_dev = h_host.to(dev)
@@ -313,13 +345,13 @@ def main():
         return
     # ---- roofline: algorithmic bytes of the layer over its device time ---------------------
     peak, peak_src = load_peaks()
-    alg = algorithmic_bytes(V, wl["E"], H, H)
+    alg = algorithmic_bytes(kind, V, wl["E"], H, H, params)
     achieved = alg / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
-                "kernel": "whole layer (edge_reduce_kernel + node-level GEMM + weight pack); see profiles/"}
+                "kernel": "whole layer call (for RGCN at H<=256: fused_rgcn_kernel + 2 weight-pack kernels); see profiles/"}
     cpu = None
-    if not args.skip_cpu_baseline:
+    if not args.skip_cpu_baseline and kind == "rgcn":
         threads = os.cpu_count() or 1
         eps, m_sample, t_step = run_cpu_port(wl, h_np, adjs_np, w_np, min(M, 2_000_000), 2, 1, threads)
         cpu = {"value": eps, "unit": "edges/s", "cores": threads, "kind": "port",

@@ -394,10 +394,20 @@ def test_gnn_stack_parity(kind, extra):
                    torch.zeros(V, dtype=torch.int32).cuda(), 1)
     out, all_reps = gnn(inp, training=False, return_all_representations=True)
     ref, ref_all = mo.gnn_forward(params, w, feats, adjs, dtype=np.float64)
+    ref32, ref32_all = mo.gnn_forward(params, w, feats, adjs, dtype=np.float32)
     assert len(all_reps) == len(ref_all) == params["num_layers"] + 1
-    assert_states_close(out.cpu().numpy(), ref)
-    for a, b in zip(all_reps, ref_all):
-        assert_states_close(a.cpu().numpy(), b)
+
+    def close_as_fp32(got, r64, r32):
+        # Through a deep stack the fp32 reference itself drifts from the exact result (FiLM: 1e-4 after 4
+        # layers); the bar is 1e-5 relative OR within 3x of the fp32 restatement's own error.
+        fp32_err = np.abs(r32.astype(np.float64) - r64).max()
+        scale = max(np.abs(r64).max(), 1e-30)
+        err = np.abs(got.astype(np.float64) - r64).max()
+        assert err <= max(1e-5 * scale, 3.0 * fp32_err), f"err {err:.3e}, fp32 oracle err {fp32_err:.3e}, scale {scale:.3e}"
+
+    close_as_fp32(out.cpu().numpy(), ref, ref32)
+    for a, b, c in zip(all_reps, ref_all, ref32_all):
+        close_as_fp32(a.cpu().numpy(), b, c)
     out2 = gnn(inp)
     assert np.array_equal(out2.cpu().numpy(), out.cpu().numpy())
 

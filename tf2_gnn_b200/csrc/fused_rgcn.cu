@@ -65,57 +65,75 @@ __device__ __forceinline__ float fu_row_norm(const GemmEpilogue& e, long long ro
   return e.row_norm == 1 ? c : sqrtf(c);
 }
 
-template <int NV>
-__device__ __forceinline__ void gather_segment_rows(const FusedParams& p, int l, int v, int lane, float* dst) {
+// One warp reduces `nrows` CONSECUTIVE targets of edge type l: their CSR segments are contiguous, so the
+// warp loads the source ids of all of them with coalesced loads and walks the edges in one flat loop with U
+// row loads in flight per lane (the dependent row_ptr -> index chain is paid once per 8 rows, not per row).
+// h rows are read with L2 evict_first (each row is used once per incoming edge, no reuse window); the ring
+// rows are written with L2 evict_last so that they are still resident when the TMA reads them back.
+template <int NV, int U>
+__device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, int v0, int nrows, int lane,
+                                                  float* dst, uint64_t pol_stream, uint64_t pol_keep) {
   const int C4 = p.D >> 2;
-  const long long seg = (long long)l * p.V + v;
-  const int beg = __ldg(p.row_ptr + seg), end = __ldg(p.row_ptr + seg + 1);
-  const float scale = p.normalize ? 1.0f / ((float)(end - beg) + kSmallNumber) : 1.0f;
+  const int rp = lane <= nrows ? __ldg(p.row_ptr + (long long)l * p.V + v0 + lane) : 0;
+  const int e_begin = __shfl_sync(0xffffffffu, rp, 0);
+  const int e_end = __shfl_sync(0xffffffffu, rp, nrows);
+  int row = 0;
+  int seg_end = __shfl_sync(0xffffffffu, rp, 1);
   float4 acc[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int base = beg; base < end; base += 32) {
-    const int n = min(32, end - base);
-    const int my_src = lane < n ? __ldg(p.src + base + lane) : 0;
-    int e = 0;
-    for (; e + 2 <= n; e += 2) {
-      float4 r[2][NV];
+
+  auto flush = [&](int r) {
+    const int cnt = __shfl_sync(0xffffffffu, rp, r + 1) - __shfl_sync(0xffffffffu, rp, r);
+    const float scale = p.normalize ? 1.0f / ((float)cnt + kSmallNumber) : 1.0f;
+    float* d = dst + (size_t)r * p.D;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int s = __shfl_sync(0xffffffffu, my_src, e + u);
-        const float* row = p.h + (long long)s * p.ldh;
+    for (int j = 0; j < NV; ++j) {
+      const int c4 = lane + 32 * j;
+      if (c4 < C4)
+        ptx::st_f4_hint(d + 4 * c4,
+                        make_float4(acc[j].x * scale, acc[j].y * scale, acc[j].z * scale, acc[j].w * scale),
+                        pol_keep);
+      acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
+  for (int base = e_begin; base < e_end; base += 32) {
+    const int n = min(32, e_end - base);
+    const int my_src = lane < n ? __ldg(p.src + base + lane) : 0;
+    for (int j0 = 0; j0 < n; j0 += U) {
+      float4 r[U][NV];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int s = __shfl_sync(0xffffffffu, my_src, (j0 + u) & 31);
+        const float* rowp = p.h + (long long)s * p.ldh;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
           const int c4 = lane + 32 * j;
-          r[u][j] = c4 < C4 ? ldg_f4(row + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          r[u][j] = (j0 + u < n && c4 < C4) ? ptx::ld_nc_f4_hint(rowp + 4 * c4, pol_stream)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < U; ++u) {
+        if (j0 + u < n) {
+          const int e = base + j0 + u;
+          while (e >= seg_end) {   // warp-uniform: close finished (possibly empty) segments
+            flush(row);
+            ++row;
+            seg_end = __shfl_sync(0xffffffffu, rp, row + 1);
+          }
 #pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          acc[j].x += r[u][j].x; acc[j].y += r[u][j].y; acc[j].z += r[u][j].z; acc[j].w += r[u][j].w;
-        }
-    }
-    if (e < n) {
-      const int s = __shfl_sync(0xffffffffu, my_src, e);
-      const float* row = p.h + (long long)s * p.ldh;
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int c4 = lane + 32 * j;
-        if (c4 < C4) {
-          const float4 x = ldg_f4(row + 4 * c4);
-          acc[j].x += x.x; acc[j].y += x.y; acc[j].z += x.z; acc[j].w += x.w;
+          for (int j = 0; j < NV; ++j) {
+            acc[j].x += r[u][j].x; acc[j].y += r[u][j].y; acc[j].z += r[u][j].z; acc[j].w += r[u][j].w;
+          }
         }
       }
     }
   }
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int c4 = lane + 32 * j;
-    if (c4 < C4)
-      *reinterpret_cast<float4*>(dst + 4 * c4) =
-          make_float4(acc[j].x * scale, acc[j].y * scale, acc[j].z * scale, acc[j].w * scale);
+  while (row < nrows) {
+    flush(row);
+    ++row;
   }
 }
 
@@ -179,6 +197,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t it = 0, slot_it = 0;
+      const uint64_t pol_keep = ptx::policy_evict_last();   // ring slots and the 2 MB of weights stay in L2
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n0 = (int)(tile % p.n_tiles) * p.block_n;
         for (int l = 0; l < p.L; ++l, ++slot_it) {
@@ -190,10 +209,10 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             ptx::mbar_wait(&empty[s], ph ^ 1);
             uint8_t* st = smem + (size_t)s * stage_bytes;
             ptx::mbar_arrive_expect_tx(&full[s], kFuATileBytes + 2 * b_tile_bytes);
-            ptx::tma_load_2d(st, &map_a, &full[s], kb * kFuBK, ring_row0 + slot * kFuBM);
+            ptx::tma_load_2d_hint(st, &map_a, &full[s], kb * kFuBK, ring_row0 + slot * kFuBM, pol_keep);
             const int kcol = (l * p.kb_per_type + kb) * kFuBK;
-            ptx::tma_load_2d(st + 2 * kFuATileBytes, &map_b, &full[s], kcol, n0);
-            ptx::tma_load_2d(st + 2 * kFuATileBytes + b_tile_bytes, &map_b, &full[s], kcol, p.N + n0);
+            ptx::tma_load_2d_hint(st + 2 * kFuATileBytes, &map_b, &full[s], kcol, n0, pol_keep);
+            ptx::tma_load_2d_hint(st + 2 * kFuATileBytes + b_tile_bytes, &map_b, &full[s], kcol, p.N + n0, pol_keep);
           }
         }
       }
@@ -266,6 +285,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // ================= epilogue =================
     const int q = warp & 3;
     uint32_t tile_count = 0;
+    const uint64_t pol_stream = ptx::policy_evict_first();
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_count) {
       const long long m0 = (tile / p.n_tiles) * kFuBM;
       const int n0 = (int)(tile % p.n_tiles) * p.block_n;
@@ -307,7 +327,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const long long grow = m0 + q * 32 + r;
           if (grow < p.V) {
             const float4 val = *reinterpret_cast<const float4*>(stage + r * kFuEpiPitch + cc);
-            *reinterpret_cast<float4*>(p.C + grow * p.ldc + n0 + c0 + cc) = val;
+            ptx::st_f4_hint(p.C + grow * p.ldc + n0 + c0 + cc, val, pol_stream);
           }
         }
         __syncwarp();
@@ -318,17 +338,22 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else {
     // ================= gather warps =================
     const int gw = warp - 10;
+    constexpr int kRowsPerWarp = kFuBM / kFuGatherWarps;
+    constexpr int U = NV <= 1 ? 8 : (NV == 2 ? 4 : 2);
+    const uint64_t pol_stream = ptx::policy_evict_first();
+    const uint64_t pol_keep = ptx::policy_evict_last();
     uint32_t slot_it = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m0 = (int)((tile / p.n_tiles) * kFuBM);
+      const int v0 = m0 + gw * kRowsPerWarp;
+      const int nrows = min(kRowsPerWarp, p.V - v0);   // <= 0 for warps past the last node
       for (int l = 0; l < p.L; ++l, ++slot_it) {
         const int slot = slot_it % kFuSlots;
         ptx::mbar_wait(&slot_free[slot], ((slot_it / kFuSlots) & 1) ^ 1);
         float* slot_base = p.ring + ((size_t)ring_row0 + (size_t)slot * kFuBM) * p.D;
-        for (int r = gw; r < kFuBM; r += kFuGatherWarps) {
-          const int v = m0 + r;
-          if (v < p.V) gather_segment_rows<NV>(p, l, v, lane, slot_base + (size_t)r * p.D);
-        }
+        if (nrows > 0)
+          gather_rows_batch<NV, U>(p, l, v0, nrows, lane, slot_base + (size_t)(gw * kRowsPerWarp) * p.D, pol_stream,
+                                   pol_keep);
         // generic-proxy global writes -> visible to the TMA (async proxy) reads of this CTA
         asm volatile("fence.proxy.async.global;" ::: "memory");
         __syncwarp();
