@@ -290,12 +290,29 @@ def test_edge_mlp_grid(agg, act_before, use_target, normalize, n_hidden):
     p.update(hidden_dim=H, aggregation_function=agg, message_activation_before_aggregation=act_before,
              use_target_state_as_input=use_target, normalize_by_num_incoming=normalize,
              num_edge_MLP_hidden_layers=n_hidden, message_activation_function="tanh")
-    literal_only = n_hidden >= 1 and (agg == "max" or act_before)
-    if literal_only:
-        with pytest.raises(NotImplementedError):   # loud, never a silent fallback
-            run_case("gnn_edge_mlp", p, V, D, L, adjs)
-    else:
-        run_case("gnn_edge_mlp", p, V, D, L, adjs)
+    # n_hidden >= 1 with max / act-before runs the literal per-edge path (literal.cu)
+    run_case("gnn_edge_mlp", p, V, D, L, adjs)
+
+
+@pytest.mark.parametrize("kind,extra", [
+    ("gnn_edge_mlp", dict(num_edge_MLP_hidden_layers=2)),
+    ("gnn_edge_mlp", dict(num_edge_MLP_hidden_layers=3, aggregation_function="max", use_target_state_as_input=False)),
+    ("rgin", dict(num_edge_MLP_hidden_layers=2, num_aggr_MLP_hidden_layers=1)),
+    ("gnn_film", dict(num_edge_MLP_hidden_layers=1, normalize_by_num_incoming=True)),
+    ("gnn_film", dict(num_edge_MLP_hidden_layers=2, message_activation_before_aggregation=True,
+                      use_target_state_as_input=True, aggregation_function="mean")),
+    ("ggnn", dict(num_edge_MLP_hidden_layers=2)),
+])
+def test_literal_per_edge_path(kind, extra):
+    """Hyper-parameter combinations whose per-edge non-linearity cannot be hoisted to node level."""
+    _need_gpu()
+    rng = np.random.default_rng(31)
+    V, D, H, L = 250, 48, 48, 3
+    adjs = random_graph(rng, V, L, 1800, hub=True, dups=True, empty_type=1)
+    p = mo.default_hyperparameters(kind)
+    p.update(hidden_dim=H, message_activation_function="tanh")
+    p.update(extra)
+    run_case(kind, p, V, D, L, adjs)
 
 
 @pytest.mark.parametrize("act", ["relu", "tanh", "leaky_relu", "elu", "selu", "gelu"])

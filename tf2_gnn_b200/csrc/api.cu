@@ -13,9 +13,7 @@
 #include <mutex>
 #include <string>
 
-#include "common.cuh"
-#include "edge_reduce.cuh"
-#include "gemm.cuh"
+#include "layers.cuh"
 
 namespace tfgnn {
 
@@ -337,9 +335,10 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
     return node_gemm((const float*)A, LH, (const float*)W2, H, out, ldo, V, H, LH, epi, path, b, 6, st);
   }
 
-  return unsupported(
-      "edge MLP with >=2 hidden layers, or 1 hidden layer combined with max-aggregation / "
-      "activation-before-aggregation, needs the per-edge literal path (not built yet)");
+  // edge MLP with >= 2 hidden layers, or hidden layers combined with max-aggregation /
+  // activation-before-aggregation: the per-edge non-linearity cannot be hoisted -> literal path.
+  return edge_mlp_literal(b, h, D, mlp_weights, n_hidden, H, flags, aggregation, activation, nullptr, 0, path, out,
+                          ldo, st);
 }
 
 }  // namespace tfgnn

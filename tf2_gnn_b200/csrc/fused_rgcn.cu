@@ -13,7 +13,11 @@
 // of slot i+1..i+3 overlaps the MMAs of slot i, so the kernel runs at the HBM rate of the gather and the
 // [V, L*D] intermediate never touches HBM.
 //
-// Warp roles (832 threads): 0 TMA | 1 MMA | 2-5 split | 6-9 epilogue | 10-25 gather.
+// Warp roles (896 threads, by warpgroup so that setmaxnreg can move registers to the gather warps):
+//   WG0: 0 TMA, 1 MMA, 2-3 idle | WG1 (4-7): A splitters | WG2 (8-11): epilogue | WG3-6 (12-27): gather.
+// The gather is latency-bound on register-held loads (72 registers/thread cap at 896 threads), so each
+// gather warp also runs a rolling L2 prefetch window ahead of its loads: DRAM requests in flight are then
+// bounded by the memory system, not by registers.
 #include <cuda.h>
 
 #include <mutex>
@@ -27,7 +31,9 @@ constexpr int kFuBM = 128;
 constexpr int kFuBK = 32;
 constexpr int kFuATileBytes = kFuBM * 128;
 constexpr int kFuGatherWarps = 16;
-constexpr int kFuThreads = 32 * (10 + kFuGatherWarps);
+constexpr int kFuFirstGatherWarp = 12;
+constexpr int kFuThreads = 32 * (kFuFirstGatherWarp + kFuGatherWarps);
+constexpr int kFuPrefetchWindow = 16;  // edges whose rows are L2-prefetched ahead of the register loads
 constexpr int kFuSlots = 3;
 constexpr int kFuTmemCols = 512;
 constexpr int kFuAccStride = 256;
@@ -101,7 +107,29 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, i
   for (int base = e_begin; base < e_end; base += 32) {
     const int n = min(32, e_end - base);
     const int my_src = lane < n ? __ldg(p.src + base + lane) : 0;
+    const int lines = (p.D * 4 + 127) >> 7;                 // 128 B lines per source row
+    // prime the window: rows of the first kFuPrefetchWindow edges
+    {
+      const int we = min(n, kFuPrefetchWindow);
+      for (int t0 = 0; t0 < we * lines; t0 += 32) {
+        const int t = t0 + lane;
+        const int ed = t / lines;
+        const int s = __shfl_sync(0xffffffffu, my_src, ed & 31);
+        if (t < we * lines) ptx::prefetch_l2(p.h + (long long)s * p.ldh + (t - ed * lines) * 32);
+      }
+    }
     for (int j0 = 0; j0 < n; j0 += U) {
+      {
+        // roll the window: prefetch the rows of edges [j0 + W, j0 + W + U)
+        const int w0 = j0 + kFuPrefetchWindow;
+        const int we = min(n, w0 + U) - w0;
+        for (int t0 = 0; t0 < we * lines; t0 += 32) {
+          const int t = t0 + lane;
+          const int ed = w0 + t / lines;
+          const int s = __shfl_sync(0xffffffffu, my_src, ed & 31);
+          if (t < we * lines) ptx::prefetch_l2(p.h + (long long)s * p.ldh + (t % lines) * 32);
+        }
+      }
       float4 r[U][NV];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -252,9 +280,9 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         __syncwarp();
       }
     }
-  } else if (warp < 6) {
+  } else if (warp >= 4 && warp < 8) {
     // ================= A splitters =================
-    const int tid = threadIdx.x - 64;
+    const int tid = threadIdx.x - 128;
     uint32_t it = 0, slot_it = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int l = 0; l < p.L; ++l, ++slot_it) {
@@ -265,7 +293,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (kb == p.kb_per_type - 1) ptx::mbar_arrive(&slot_free[slot_it % kFuSlots]);  // all TMA reads of the slot landed
           float4* a = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
           float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + kFuATileBytes);
-#pragma unroll
+#pragma unroll 2
           for (int i = 0; i < kFuATileBytes / 16 / 128; ++i) {
             const int idx = tid + i * 128;
             const float4 x = a[idx];
@@ -281,8 +309,8 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
       }
     }
-  } else if (warp < 10) {
-    // ================= epilogue =================
+  } else if (warp >= 8 && warp < kFuFirstGatherWarp) {
+    // ================= epilogue (warps 8..11 -> TMEM lane quarters 0..3) =================
     const int q = warp & 3;
     uint32_t tile_count = 0;
     const uint64_t pol_stream = ptx::policy_evict_first();
@@ -296,7 +324,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const bool row_ok = row < p.V;
       const float rn = row_ok ? fu_row_norm(p.epi, row) : 1.0f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kFuAccStride;
-      float* stage = epi_stage + (size_t)(warp - 6) * 32 * kFuEpiPitch;
+      float* stage = epi_stage + (size_t)(warp - 8) * 32 * kFuEpiPitch;
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
         const int ncols = min(32, p.block_n - c0);
 #pragma unroll
@@ -335,9 +363,9 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&tmem_empty[acc]);
     }
-  } else {
+  } else if (warp >= kFuFirstGatherWarp) {
     // ================= gather warps =================
-    const int gw = warp - 10;
+    const int gw = warp - kFuFirstGatherWarp;
     constexpr int kRowsPerWarp = kFuBM / kFuGatherWarps;
     constexpr int U = NV <= 1 ? 8 : (NV == 2 ? 4 : 2);
     const uint64_t pol_stream = ptx::policy_evict_first();

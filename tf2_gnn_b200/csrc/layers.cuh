@@ -12,4 +12,8 @@ int node_gemm(const float* A, int lda, const float* B, int ldb, float* C, int ld
               const GemmEpilogue& epi, int path, tfgnn_batch* batch, int tc_slot, cudaStream_t st);
 int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp_weights, int n_hidden, int H,
                   uint32_t flags, int aggregation, int activation, int path, float* out, int ldo, cudaStream_t st);
+// literal per-edge path (literal.cu); FB = optional FiLM table [V, L*2H] (gamma | beta per type)
+int edge_mlp_literal(tfgnn_batch* b, const float* h, int D, const float* const* mlp_weights, int n_hidden, int H,
+                     uint32_t flags, int aggregation, int activation, const float* FB, int ldf, int path, float* out,
+                     int ldo, cudaStream_t st);
 }  // namespace tfgnn

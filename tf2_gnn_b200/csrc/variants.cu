@@ -116,8 +116,7 @@ extern "C" int tfgnn_b200_film_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
     return edge_mlp_core(b, h, D, mlp_weights, 0, H, flags, aggregation, activation, path, out, H,
                          (cudaStream_t)stream);
   TFGNN_REQUIRE(mlp_weights && film_weights, "weight table is NULL");
-  if (num_hidden_layers != 0)
-    return unsupported("GNN-FiLM with hidden layers in the edge MLP needs the per-edge literal path (not built yet)");
+  TFGNN_REQUIRE(num_hidden_layers >= 0, "num_hidden_layers must be >= 0");
   if (path == TFGNN_PATH_ATOMIC) return unsupported("TFGNN_PATH_ATOMIC is not available for GNN-FiLM");
   cudaStream_t st = (cudaStream_t)stream;
   const bool normalize = flags & TFGNN_FLAG_NORMALIZE_BY_NUM_INCOMING;
@@ -126,8 +125,8 @@ extern "C" int tfgnn_b200_film_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   const int LH = L * H;
   PtrTable first{}, film{};
   for (int l = 0; l < L; ++l) {
-    TFGNN_REQUIRE(mlp_weights[l] && film_weights[l], "a weight pointer is NULL");
-    first.p[l] = mlp_weights[l];
+    TFGNN_REQUIRE(mlp_weights[l * (num_hidden_layers + 1)] && film_weights[l], "a weight pointer is NULL");
+    first.p[l] = mlp_weights[l * (num_hidden_layers + 1)];
     film.p[l] = film_weights[l];
   }
   const int Vs = (int)b->V_src;
@@ -142,6 +141,15 @@ extern "C" int tfgnn_b200_film_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   rc = batch_scratch(b, 12, (size_t)D * 2 * LH * sizeof(float), &Fcat);
   if (rc) return rc;
   GemmEpilogue none;
+  if (num_hidden_layers > 0) {
+    // hidden layers in the edge MLP: FiLM parameters at node level, messages on the literal per-edge path
+    rc = launch_pack_horizontal(film, L, 0, D, 2 * H, 2 * H, (float*)Fcat, 2 * LH, st);
+    if (rc) return rc;
+    rc = node_gemm(h_tgt, D, (const float*)Fcat, 2 * LH, (float*)FB, 2 * LH, V, 2 * LH, D, none, path, b, 6, st);
+    if (rc) return rc;
+    return edge_mlp_literal(b, h, D, mlp_weights, num_hidden_layers, H, flags, aggregation, activation,
+                            (const float*)FB, 2 * LH, path, out, H, st);
+  }
   // projected source messages P_l = h W^s_l  (gnn_edge_mlp.py:100 hoisted to node level)
   rc = launch_pack_horizontal(first, L, 0, D, H, H, (float*)Wcat, LH, st);
   if (rc) return rc;
