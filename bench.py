@@ -207,6 +207,20 @@ def run_cpu_port(wl, h, adjs, weights, sample_edges, steps, warmup, threads):
     return m_sample * len(times) / total, m_sample, total / len(times)
 
 
+def best_cpu_threads(wl, h, adjs, weights):
+    """torch-CPU scaling of the gather / index_add ops is poor on many-core hosts (NUMA): calibrate a few
+    thread counts on a small sample and use the fastest, as a user of the reference would."""
+    total = os.cpu_count() or 1
+    cands = sorted({c for c in (total, 64, 32, 16, 8) if c <= total}, reverse=True)
+    M = sum(a.shape[0] for a in adjs)
+    best, best_rate = total, 0.0
+    for c in cands:
+        rate, _, _ = run_cpu_port(wl, h, adjs, weights, min(M, 200_000), 1, 1, c)
+        if rate > best_rate:
+            best, best_rate = c, rate
+    return best, best_rate, total
+
+
 def reference_arm(args, wl, rank, world):
     """--impl reference: the reference's CPU path (restated port; TF is not installable here)."""
     if rank != 0:
@@ -214,16 +228,16 @@ def reference_arm(args, wl, rank, world):
     if wl["kind"] != "rgcn":
         print(json.dumps({"impl": "reference", "unavailable": "timed CPU port exists for the RGCN workloads only"}))
         return
-    threads = os.cpu_count() or 1
     h, adjs, weights = make_inputs(wl, seed=0)
     M = sum(a.shape[0] for a in adjs)
-    # calibrate on a small sample, then size the per-step sample so the run ends within ~2 minutes
-    rate, _, _ = run_cpu_port(wl, h, adjs, weights, min(M, 200_000), 1, 1, threads)
+    # calibrate threads and rate on a small sample, then size the per-step sample so the run ends within ~2 minutes
+    threads, rate, host_cores = best_cpu_threads(wl, h, adjs, weights)
     budget_s = 120.0
     sample = int(min(M, max(50_000, rate * budget_s / max(1, args.steps + args.warmup))))
     eps, m_sample, t_step = run_cpu_port(wl, h, adjs, weights, sample, args.steps, args.warmup, threads)
     sample_desc = (f"first {m_sample} of {M} edges (same V={wl['V']}, H={wl['H']}, L={len(wl['E'])}), 1 layer/step, "
-                   f"torch-CPU restatement of the reference op order (TensorFlow absent)")
+                   f"torch-CPU restatement of the reference op order (TensorFlow absent); fastest of "
+                   f"{{all,64,32,16,8}} threads on a {host_cores}-core host")
     line = {
         "impl": "reference", "metric": METRIC, "value": eps, "unit": "edges/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True,
@@ -352,11 +366,12 @@ def main():
                 "kernel": "whole layer call (for RGCN at H<=256: fused_rgcn_kernel + 2 weight-pack kernels); see profiles/"}
     cpu = None
     if not args.skip_cpu_baseline and kind == "rgcn":
-        threads = os.cpu_count() or 1
+        threads, _, host_cores = best_cpu_threads(wl, h_np, adjs_np, w_np)
         eps, m_sample, t_step = run_cpu_port(wl, h_np, adjs_np, w_np, min(M, 2_000_000), 2, 1, threads)
         cpu = {"value": eps, "unit": "edges/s", "cores": threads, "kind": "port",
                "sample": f"first {m_sample} of {M} edges on the full V={V} node table, 1 layer, 2 timed runs; "
-                         f"torch-CPU restatement of the reference op order (TensorFlow absent)"}
+                         f"torch-CPU restatement of the reference op order (TensorFlow absent); fastest thread "
+                         f"count on a {host_cores}-core host"}
     line = {
         "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

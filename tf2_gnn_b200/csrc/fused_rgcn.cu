@@ -20,6 +20,7 @@
 // bounded by the memory system, not by registers.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "gemm.cuh"
@@ -28,12 +29,9 @@
 namespace tfgnn {
 
 constexpr int kFuBM = 128;
-constexpr int kFuBK = 32;
-constexpr int kFuATileBytes = kFuBM * 128;
 constexpr int kFuGatherWarps = 16;
 constexpr int kFuFirstGatherWarp = 12;
 constexpr int kFuThreads = 32 * (kFuFirstGatherWarp + kFuGatherWarps);
-constexpr int kFuPrefetchWindow = 16;  // edges whose rows are L2-prefetched ahead of the register loads
 constexpr int kFuSlots = 3;
 constexpr int kFuTmemCols = 512;
 constexpr int kFuAccStride = 256;
@@ -49,6 +47,7 @@ struct FusedParams {
   const int* src;
   int V, L, D;
   int normalize;
+  int prefetch_window;  // edges whose rows are L2-prefetched ahead of the register loads (0 = off)
   // ring
   float* ring;  // [grid * kFuSlots * 128, D]
   // GEMM
@@ -108,9 +107,9 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, i
     const int n = min(32, e_end - base);
     const int my_src = lane < n ? __ldg(p.src + base + lane) : 0;
     const int lines = (p.D * 4 + 127) >> 7;                 // 128 B lines per source row
-    // prime the window: rows of the first kFuPrefetchWindow edges
+    // prime the window: rows of the first p.prefetch_window edges
     {
-      const int we = min(n, kFuPrefetchWindow);
+      const int we = min(n, p.prefetch_window);
       for (int t0 = 0; t0 < we * lines; t0 += 32) {
         const int t = t0 + lane;
         const int ed = t / lines;
@@ -121,7 +120,7 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, i
     for (int j0 = 0; j0 < n; j0 += U) {
       {
         // roll the window: prefetch the rows of edges [j0 + W, j0 + W + U)
-        const int w0 = j0 + kFuPrefetchWindow;
+        const int w0 = j0 + p.prefetch_window;
         const int we = min(n, w0 + U) - w0;
         for (int t0 = 0; t0 < we * lines; t0 += 32) {
           const int t = t0 + lane;
@@ -165,14 +164,20 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, i
   }
 }
 
-template <int NV>
+// BK = floats per K block: 32 (128 B rows, SWIZZLE_128B) or 16 (64 B rows, SWIZZLE_64B).  The smaller block
+// halves the bytes per pipeline stage, so twice as many stages fit: under the gather's L2 traffic a TMA round
+// trip takes ~3 us, and it is bytes-in-flight / latency that bounds the operand feed of the tensor core.
+template <int NV, int BK>
 __global__ void __launch_bounds__(kFuThreads, 1)
 fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kFuBK = BK;
+  constexpr int kRowBytes = BK * 4;
+  constexpr int kFuATileBytes = kFuBM * kRowBytes;
   const int S = p.num_stages;
-  const int b_tile_bytes = p.block_n * 128;
+  const int b_tile_bytes = p.block_n * kRowBytes;
   const int stage_bytes = 2 * kFuATileBytes + 2 * b_tile_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
   uint64_t* full = bars;
@@ -263,10 +268,10 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         ptx::tc_fence_after_sync();
         if (lane == 0) {
           const uint32_t st = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t a_hi = ptx::umma_desc_k_sw128(st);
-          const uint64_t a_lo = ptx::umma_desc_k_sw128(st + kFuATileBytes);
-          const uint64_t b_hi = ptx::umma_desc_k_sw128(st + 2 * kFuATileBytes);
-          const uint64_t b_lo = ptx::umma_desc_k_sw128(st + 2 * kFuATileBytes + b_tile_bytes);
+          const uint64_t a_hi = ptx::umma_desc_k<kRowBytes>(st);
+          const uint64_t a_lo = ptx::umma_desc_k<kRowBytes>(st + kFuATileBytes);
+          const uint64_t b_hi = ptx::umma_desc_k<kRowBytes>(st + 2 * kFuATileBytes);
+          const uint64_t b_lo = ptx::umma_desc_k<kRowBytes>(st + 2 * kFuATileBytes + b_tile_bytes);
 #pragma unroll
           for (int k = 0; k < kFuBK / 8; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
@@ -416,7 +421,7 @@ static EncodeTiledFn fu_encode_fn() {
 }
 
 bool fused_rgcn_supported(long long V, int L, int D, int H, const float* h, const float* out, int ldo) {
-  if (V < 1 || L < 1 || D % kFuBK != 0 || D > 512 || H % 16 != 0 || H < 16 || H > 256) return false;
+  if (V < 1 || L < 1 || D % 32 != 0 || D > 512 || H % 16 != 0 || H < 16 || H > 256) return false;
   if ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(out)) & 15) return false;
   if (ldo % 4 != 0) return false;
   // one N tile per 128 targets so that every source row is gathered exactly once: the whole H must fit one
@@ -441,12 +446,17 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   FusedParams p{};
   p.h = h; p.ldh = D; p.row_ptr = row_ptr; p.src = src; p.V = V; p.L = L; p.D = D; p.normalize = normalize;
   p.ring = ring;
+  static const int pf_window = [] { const char* e = getenv("TFGNN_B200_PREFETCH_WINDOW"); return e ? atoi(e) : 16; }();
+  p.prefetch_window = pf_window < 0 ? 0 : (pf_window > 32 ? 32 : pf_window);
   p.N = H; p.block_n = H; p.n_tiles = 1;
   p.m_tiles = ((long long)V + kFuBM - 1) / kFuBM;
+  static const int bk_env = [] { const char* e = getenv("TFGNN_B200_FUSED_BK"); return e ? atoi(e) : 16; }();
+  const int kFuBK = bk_env == 32 ? 32 : 16;
+  const int kFuATileBytes = kFuBM * kFuBK * 4;
   p.kb_per_type = D / kFuBK;
-  const int stage_bytes = 2 * kFuATileBytes + 2 * p.block_n * 128;
+  const int stage_bytes = 2 * kFuATileBytes + 2 * p.block_n * kFuBK * 4;
   int stages = (kFuSmemLimit - 2048 - kFuEpiBytes) / stage_bytes;
-  if (stages > 4) stages = 4;
+  if (stages > 6) stages = 6;
   TFGNN_REQUIRE(stages >= 2, "fused RGCN: tile does not fit shared memory");
   p.num_stages = stages;
   p.C = out; p.ldc = ldo; p.epi = epi;
@@ -461,7 +471,8 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
     cuuint32_t box[2] = {(cuuint32_t)kFuBK, (cuuint32_t)kFuBM};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ring, dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, kFuBK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error(TFGNN_ERR_CUDA, "cuTensorMapEncodeTiled(ring) failed with code " + std::to_string((int)r));
@@ -474,7 +485,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
     cuuint32_t box[2] = {(cuuint32_t)kFuBK, (cuuint32_t)p.block_n};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(packedB), dims, strides, box,
-                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, kFuBK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error(TFGNN_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed with code " + std::to_string((int)r));
@@ -487,19 +498,36 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    cudaError_t e1 = cudaFuncSetAttribute(fused_rgcn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit);
-    cudaError_t e2 = cudaFuncSetAttribute(fused_rgcn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit);
-    cudaError_t e3 = cudaFuncSetAttribute(fused_rgcn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit);
-    cudaError_t e4 = cudaFuncSetAttribute(fused_rgcn_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit);
-    attr_err = e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3 != cudaSuccess ? e3 : e4;
+    cudaError_t e[8] = {
+        cudaFuncSetAttribute(fused_rgcn_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit),
+        cudaFuncSetAttribute(fused_rgcn_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit),
+        cudaFuncSetAttribute(fused_rgcn_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit),
+        cudaFuncSetAttribute(fused_rgcn_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit),
+        cudaFuncSetAttribute(fused_rgcn_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit),
+        cudaFuncSetAttribute(fused_rgcn_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit),
+        cudaFuncSetAttribute(fused_rgcn_kernel<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit),
+        cudaFuncSetAttribute(fused_rgcn_kernel<4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit)};
+    for (cudaError_t x : e)
+      if (x != cudaSuccess) attr_err = x;
   });
   TFGNN_CUDA(attr_err);
-  switch (nv) {
-    case 1: fused_rgcn_kernel<1><<<grid, kFuThreads, smem_bytes, st>>>(map_a, map_b, p); break;
-    case 2: fused_rgcn_kernel<2><<<grid, kFuThreads, smem_bytes, st>>>(map_a, map_b, p); break;
-    case 3: fused_rgcn_kernel<3><<<grid, kFuThreads, smem_bytes, st>>>(map_a, map_b, p); break;
-    default: fused_rgcn_kernel<4><<<grid, kFuThreads, smem_bytes, st>>>(map_a, map_b, p); break;
+#define TFGNN_FU_LAUNCH(NV, BK) fused_rgcn_kernel<NV, BK><<<grid, kFuThreads, smem_bytes, st>>>(map_a, map_b, p)
+  if (kFuBK == 32) {
+    switch (nv) {
+      case 1: TFGNN_FU_LAUNCH(1, 32); break;
+      case 2: TFGNN_FU_LAUNCH(2, 32); break;
+      case 3: TFGNN_FU_LAUNCH(3, 32); break;
+      default: TFGNN_FU_LAUNCH(4, 32); break;
+    }
+  } else {
+    switch (nv) {
+      case 1: TFGNN_FU_LAUNCH(1, 16); break;
+      case 2: TFGNN_FU_LAUNCH(2, 16); break;
+      case 3: TFGNN_FU_LAUNCH(3, 16); break;
+      default: TFGNN_FU_LAUNCH(4, 16); break;
+    }
   }
+#undef TFGNN_FU_LAUNCH
   TFGNN_LAUNCH_CHECK();
   return 0;
 }

@@ -158,6 +158,20 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;            // SWIZZLE_128B
   return d;
 }
+// Same for 64-byte rows (16 tf32 per K block): SWIZZLE_64B (layout code 4), 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;   // SBO = 512 B
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;            // SWIZZLE_64B
+  return d;
+}
+template <int ROW_BYTES>
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t smem_addr) {
+  return ROW_BYTES == 128 ? umma_desc_k_sw128(smem_addr) : umma_desc_k_sw64(smem_addr);
+}
 // Instruction descriptor kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = n
 // (cute::UMMA::InstrDescriptor: c_format[4,6)=1 a_format[7,10)=2 b_format[10,13)=2 n>>3 [17,23) m>>4 [24,29)).
 __host__ __device__ __forceinline__ uint32_t umma_idesc_tf32_m128(uint32_t n) {
