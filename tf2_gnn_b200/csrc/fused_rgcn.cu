@@ -495,6 +495,21 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4 + 2 * kFuSlots + 4) * sizeof(uint64_t) +
                             kFuEpiBytes + 1024;
   const int nv = (D + 127) / 128;
+  // L2 set-aside for the evict_last (persisting) lines: the ring + the packed weights.  Without a carve-out
+  // the evict_last hint is advisory only and the ring gets written back to HBM (measured: +4 GB/layer).
+  static std::once_flag l2_once;
+  std::call_once(l2_once, [&] {
+    int dev2 = 0, max_persist = 0;
+    if (cudaGetDevice(&dev2) == cudaSuccess &&
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev2) == cudaSuccess &&
+        max_persist > 0) {
+      size_t want = (size_t)72 << 20;
+      if (const char* e = getenv("TFGNN_B200_L2_PERSIST_MB")) want = (size_t)atoi(e) << 20;
+      if (want > (size_t)max_persist) want = (size_t)max_persist;
+      if (want > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+    }
+    cudaGetLastError();
+  });
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
