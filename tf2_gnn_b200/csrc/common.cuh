@@ -63,6 +63,34 @@ __device__ __forceinline__ float apply_act_t(float x) {
   return apply_act(x, ACT);
 }
 
+// Activation of N register values with the switch hoisted OUT of the element loop: only the selected
+// case's (short) loop is ever fetched.  Inlining apply_act() per element put every libdevice expansion
+// (tanhf, expm1f, ...) N times into the epilogue: ~80 KB of straight-line SASS that thrashed the
+// instruction cache (measured: ~30 us per 128x128 output tile in the tcgen05 epilogue).
+template <int ACT, int N>
+__device__ __noinline__ void apply_act_vec_t(float* v) {
+#pragma unroll
+  for (int j = 0; j < N; ++j) v[j] = apply_act(v[j], ACT);
+}
+template <int N>
+__device__ __forceinline__ void apply_act_vec(float* v, int act) {
+  switch (act) {
+    case TFGNN_ACT_RELU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = fmaxf(v[j], 0.0f);
+      break;
+    case TFGNN_ACT_LEAKY_RELU:
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = v[j] > 0.0f ? v[j] : kLeakyReluAlpha * v[j];
+      break;
+    case TFGNN_ACT_TANH: apply_act_vec_t<TFGNN_ACT_TANH, N>(v); break;
+    case TFGNN_ACT_ELU: apply_act_vec_t<TFGNN_ACT_ELU, N>(v); break;
+    case TFGNN_ACT_SELU: apply_act_vec_t<TFGNN_ACT_SELU, N>(v); break;
+    case TFGNN_ACT_GELU: apply_act_vec_t<TFGNN_ACT_GELU, N>(v); break;
+    default: break;
+  }
+}
+
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 }

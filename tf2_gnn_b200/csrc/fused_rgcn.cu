@@ -330,25 +330,37 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const float rn = row_ok ? fu_row_norm(p.epi, row) : 1.0f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kFuAccStride;
       float* stage = epi_stage + (size_t)(warp - 8) * 32 * kFuEpiPitch;
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        const int ncols = min(32, p.block_n - c0);
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {   // 16 columns per TMEM round trip (72-register budget)
+        const int ncols = 16;
+        {
+          // TMEM -> registers: main and correction accumulators of up to 32 columns, ONE wait
+          uint32_t mv[2][16], cv[2][16];
+          const int nh = ncols > 16 ? 2 : 1;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (half * 16 < ncols) {
-            float v[16], w[16];
-            ptx::tmem_ld_x16(taddr + c0 + half * 16, v);
-            ptx::tmem_ld_x16(taddr + corr_off + c0 + half * 16, w);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float x = v[j] + w[j];
-              if (p.epi.row_norm) x = x / rn;
-              if (p.epi.bias) x += __ldg(p.epi.bias + n0 + c0 + half * 16 + j);
-              v[j] = apply_act(x, p.epi.act);
+          for (int half = 0; half < 2; ++half) {
+            if (half < nh) {
+              ptx::tmem_ld_x16_nowait(taddr + c0 + half * 16, mv[half]);
+              ptx::tmem_ld_x16_nowait(taddr + corr_off + c0 + half * 16, cv[half]);
             }
+          }
+          ptx::tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4*>(stage + lane * kFuEpiPitch + half * 16 + j) =
-                  make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int half = 0; half < 2; ++half) {
+            if (half < nh) {
+              float v[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float x = __uint_as_float(mv[half][j]) + __uint_as_float(cv[half][j]);
+                if (p.epi.row_norm) x = x / rn;
+                if (p.epi.bias) x += __ldg(p.epi.bias + n0 + c0 + half * 16 + j);
+                v[j] = x;
+              }
+              apply_act_vec<16>(v, p.epi.act);
+#pragma unroll
+              for (int j = 0; j < 16; j += 4)
+                *reinterpret_cast<float4*>(stage + lane * kFuEpiPitch + half * 16 + j) =
+                    make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
           }
         }
         __syncwarp();

@@ -145,6 +145,18 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Same without the wait: issue several loads, then ONE tmem_wait_ld() (each wait is a full round trip
+// through the tcgen05 pipe, which also carries the queued MMAs).
+__device__ __forceinline__ void tmem_ld_x16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 // ---- descriptors ---------------------------------------------------------------------------
 // Shared-memory operand descriptor, K-major tile with 128-byte swizzle: rows of 128 B (32 tf32),
 // 8-row groups 1024 B apart (SBO), tile base 1024 B aligned.  (cute::UMMA::SmemDescriptor:
