@@ -47,6 +47,7 @@ struct FusedParams {
   const int* src;
   int V, L, D;
   int normalize;
+  int discard_ring;     // discard.global.L2 on consumed ring slots
   int prefetch_window;  // edges whose rows are L2-prefetched ahead of the register loads (0 = off)
   // ring
   float* ring;  // [grid * kFuSlots * 128, D]
@@ -295,7 +296,16 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           ptx::mbar_wait(&full[s], ph);
-          if (kb == p.kb_per_type - 1) ptx::mbar_arrive(&slot_free[slot_it % kFuSlots]);  // all TMA reads of the slot landed
+          if (kb == p.kb_per_type - 1) {
+            // all TMA reads of the slot have landed: its lines are dead.  Discard them from L2 so that they are
+            // never written back to HBM (the ring is pure on-chip hand-off), then hand the slot back.
+            if (p.discard_ring) {
+              const char* sb = reinterpret_cast<const char*>(p.ring + ((size_t)ring_row0 + (size_t)(slot_it % kFuSlots) * kFuBM) * p.D);
+              const int lines = kFuBM * p.D * 4 / 128;
+              for (int i = tid; i < lines; i += 128) ptx::discard_l2_128(sb + (size_t)i * 128);
+            }
+            ptx::mbar_arrive(&slot_free[slot_it % kFuSlots]);
+          }
           float4* a = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
           float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + kFuATileBytes);
 #pragma unroll 2
@@ -460,6 +470,8 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   p.ring = ring;
   static const int pf_window = [] { const char* e = getenv("TFGNN_B200_PREFETCH_WINDOW"); return e ? atoi(e) : 16; }();
   p.prefetch_window = pf_window < 0 ? 0 : (pf_window > 32 ? 32 : pf_window);
+  static const int discard_env = [] { const char* e = getenv("TFGNN_B200_RING_DISCARD"); return e ? atoi(e) : 1; }();
+  p.discard_ring = discard_env;
   p.N = H; p.block_n = H; p.n_tiles = 1;
   p.m_tiles = ((long long)V + kFuBM - 1) / kFuBM;
   static const int bk_env = [] { const char* e = getenv("TFGNN_B200_FUSED_BK"); return e ? atoi(e) : 16; }();

@@ -84,6 +84,10 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
 __device__ __forceinline__ void prefetch_l2(const void* ptr) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
 }
+// Drop a 128 B line from L2 WITHOUT writing it back (producer/consumer scratch that is dead after the read).
+__device__ __forceinline__ void discard_l2_128(const void* ptr) {
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(ptr) : "memory");
+}
 __device__ __forceinline__ float4 ld_nc_f4_hint(const float* ptr, uint64_t policy) {
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
