@@ -107,28 +107,15 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, i
   for (int base = e_begin; base < e_end; base += 32) {
     const int n = min(32, e_end - base);
     const int my_src = lane < n ? __ldg(p.src + base + lane) : 0;
-    const int lines = (p.D * 4 + 127) >> 7;                 // 128 B lines per source row
-    // prime the window: rows of the first p.prefetch_window edges
-    {
-      const int we = min(n, p.prefetch_window);
-      for (int t0 = 0; t0 < we * lines; t0 += 32) {
-        const int t = t0 + lane;
-        const int ed = t / lines;
-        const int s = __shfl_sync(0xffffffffu, my_src, ed & 31);
-        if (t < we * lines) ptx::prefetch_l2(p.h + (long long)s * p.ldh + (t - ed * lines) * 32);
-      }
-    }
+    const uint32_t row_bytes = (uint32_t)p.D * 4;
+    // prime the L2 prefetch window: ONE bulk request per source row (cp.async.bulk.prefetch.L2)
+    if (lane < min(n, p.prefetch_window)) ptx::bulk_prefetch_l2(p.h + (long long)my_src * p.ldh, row_bytes);
     for (int j0 = 0; j0 < n; j0 += U) {
       {
-        // roll the window: prefetch the rows of edges [j0 + W, j0 + W + U)
+        // roll the window: rows of edges [j0 + W, j0 + W + U)
         const int w0 = j0 + p.prefetch_window;
-        const int we = min(n, w0 + U) - w0;
-        for (int t0 = 0; t0 < we * lines; t0 += 32) {
-          const int t = t0 + lane;
-          const int ed = w0 + t / lines;
-          const int s = __shfl_sync(0xffffffffu, my_src, ed & 31);
-          if (t < we * lines) ptx::prefetch_l2(p.h + (long long)s * p.ldh + (t % lines) * 32);
-        }
+        if (p.prefetch_window > 0 && lane >= w0 && lane < min(n, w0 + U))
+          ptx::bulk_prefetch_l2(p.h + (long long)my_src * p.ldh, row_bytes);
       }
       float4 r[U][NV];
 #pragma unroll

@@ -16,4 +16,7 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
 int edge_mlp_literal(tfgnn_batch* b, const float* h, int D, const float* const* mlp_weights, int n_hidden, int H,
                      uint32_t flags, int aggregation, int activation, const float* FB, int ldf, int path, float* out,
                      int ldo, cudaStream_t st);
+// RGAT edge-level aggregation (rgat.cu): warp per target + chunked hub path; needs (H/K) % 4 == 0
+int launch_rgat_aggregate(tfgnn_batch* b, const float* P, const float* s_src, const float* s_tgt, int K, int d,
+                          int activation, float* out, cudaStream_t st);
 }  // namespace tfgnn

@@ -88,6 +88,10 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr) {
 __device__ __forceinline__ void discard_l2_128(const void* ptr) {
   asm volatile("discard.global.L2 [%0], 128;" ::"l"(ptr) : "memory");
 }
+// One request prefetches `bytes` (multiple of 16) contiguous bytes into L2.
+__device__ __forceinline__ void bulk_prefetch_l2(const void* ptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ float4 ld_nc_f4_hint(const float* ptr, uint64_t policy) {
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"

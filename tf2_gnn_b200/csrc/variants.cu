@@ -308,16 +308,12 @@ extern "C" int tfgnn_b200_rgat_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
                                                             (float*)stt);
     TFGNN_LAUNCH_CHECK();
   }
-  const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-  const long long threads = V * (vec ? H / 4 : H);
-  if (vec)
-    rgat_aggregate_kernel<true><<<ceil_div(threads, 128), 128, 0, st>>>(
-        (const float*)P, (const float*)ss, (const float*)stt, b->row_ptr, b->src_sorted, V, b->tgt_off, L, K, d,
-        activation, out);
-  else
-    rgat_aggregate_kernel<false><<<ceil_div(threads, 128), 128, 0, st>>>(
-        (const float*)P, (const float*)ss, (const float*)stt, b->row_ptr, b->src_sorted, V, b->tgt_off, L, K, d,
-        activation, out);
+  const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && L > 0;
+  if (vec) return launch_rgat_aggregate(b, (const float*)P, (const float*)ss, (const float*)stt, K, d, activation, out, st);
+  const long long threads = V * H;
+  rgat_aggregate_kernel<false><<<ceil_div(threads, 128), 128, 0, st>>>(
+      (const float*)P, (const float*)ss, (const float*)stt, b->row_ptr, b->src_sorted, V, b->tgt_off, L, K, d,
+      activation, out);
   TFGNN_LAUNCH_CHECK();
   return 0;
 }
