@@ -76,25 +76,11 @@ __device__ __forceinline__ float fu_row_norm(const GemmEpilogue& e, long long ro
 // row loads in flight per lane (the dependent row_ptr -> index chain is paid once per 8 rows, not per row).
 // h rows are read with L2 evict_first (each row is used once per incoming edge, no reuse window); the ring
 // rows are written with L2 evict_last so that they are still resident when the TMA reads them back.
-//
-// Software pipeline over units: `rp` (row_ptr of the 8 segments) and `first_src` (source ids of the first 32
-// edges) of THIS unit were loaded while the previous unit was being reduced; the same is done here for the
-// next unit (`next_rp_ptr`), hiding the two dependent index round trips behind the row loads.
 template <int NV, int U>
-__device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int rp, int first_src, int nrows, int lane,
-                                                  float* dst, uint64_t pol_stream, uint64_t pol_keep,
-                                                  const int* next_rp_ptr, int next_nrows, int& next_rp,
-                                                  int& next_src) {
+__device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, int v0, int nrows, int lane,
+                                                  float* dst, uint64_t pol_stream, uint64_t pol_keep) {
   const int C4 = p.D >> 2;
-  next_rp = (next_rp_ptr != nullptr && lane <= next_nrows) ? __ldg(next_rp_ptr + lane) : 0;   // in flight
-  bool next_src_issued = false;
-  auto issue_next_src = [&]() {
-    if (next_src_issued) return;
-    next_src_issued = true;
-    const int nb = __shfl_sync(0xffffffffu, next_rp, 0);
-    const int ne = __shfl_sync(0xffffffffu, next_rp, next_nrows > 0 ? next_nrows : 0);
-    next_src = (next_rp_ptr != nullptr && lane < ne - nb) ? __ldg(p.src + nb + lane) : 0;
-  };
+  const int rp = lane <= nrows ? __ldg(p.row_ptr + (long long)l * p.V + v0 + lane) : 0;
   const int e_begin = __shfl_sync(0xffffffffu, rp, 0);
   const int e_end = __shfl_sync(0xffffffffu, rp, nrows);
   int row = 0;
@@ -120,7 +106,7 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int rp, 
 
   for (int base = e_begin; base < e_end; base += 32) {
     const int n = min(32, e_end - base);
-    const int my_src = base == e_begin ? first_src : (lane < n ? __ldg(p.src + base + lane) : 0);
+    const int my_src = lane < n ? __ldg(p.src + base + lane) : 0;
     const uint32_t row_bytes = (uint32_t)p.D * 4;
     // prime the L2 prefetch window: ONE bulk request per source row (cp.async.bulk.prefetch.L2)
     if (lane < min(n, p.prefetch_window)) ptx::bulk_prefetch_l2(p.h + (long long)my_src * p.ldh, row_bytes);
@@ -143,7 +129,6 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int rp, 
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
-      issue_next_src();   // next unit's ids: its row_ptr has had one round of row loads to arrive
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (j0 + u < n) {
@@ -165,7 +150,6 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int rp, 
     flush(row);
     ++row;
   }
-  issue_next_src();   // units without edges
 }
 
 // BK = floats per K block: 32 (128 B rows, SWIZZLE_128B) or 16 (64 B rows, SWIZZLE_64B).  The smaller block
@@ -401,48 +385,17 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint64_t pol_stream = ptx::policy_evict_first();
     const uint64_t pol_keep = ptx::policy_evict_last();
     uint32_t slot_it = 0;
-    // unit = (tile, edge type); coordinates of a unit for this warp
-    auto unit_rows = [&](long long tile, int& v0, int& nrows) {
-      v0 = (int)((tile / p.n_tiles) * kFuBM) + gw * kRowsPerWarp;
-      nrows = min(kRowsPerWarp, p.V - v0);
-      if (nrows < 0) nrows = 0;
-    };
-    int rp = 0, first_src = 0;
-    {
-      // pipeline prologue: indices of the first unit
-      int v0, nrows;
-      unit_rows(blockIdx.x, v0, nrows);
-      if ((long long)blockIdx.x < total_tiles && nrows > 0) {
-        rp = lane <= nrows ? __ldg(p.row_ptr + v0 + lane) : 0;
-        const int nb = __shfl_sync(0xffffffffu, rp, 0), ne = __shfl_sync(0xffffffffu, rp, nrows);
-        first_src = lane < ne - nb ? __ldg(p.src + nb + lane) : 0;
-      }
-    }
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int v0, nrows;
-      unit_rows(tile, v0, nrows);
+      const int m0 = (int)((tile / p.n_tiles) * kFuBM);
+      const int v0 = m0 + gw * kRowsPerWarp;
+      const int nrows = min(kRowsPerWarp, p.V - v0);   // <= 0 for warps past the last node
       for (int l = 0; l < p.L; ++l, ++slot_it) {
-        // next unit of this warp: next edge type of the same rows, or type 0 of the next tile
-        const bool last_type = l + 1 == p.L;
-        const long long ntile = last_type ? tile + gridDim.x : tile;
-        int nv0 = v0, nnrows = nrows;
-        if (last_type) unit_rows(ntile, nv0, nnrows);
-        const bool has_next = ntile < total_tiles && nnrows > 0;
-        const int* next_ptr = has_next ? p.row_ptr + (long long)(last_type ? 0 : l + 1) * p.V + nv0 : nullptr;
         const int slot = slot_it % kFuSlots;
         ptx::mbar_wait(&slot_free[slot], ((slot_it / kFuSlots) & 1) ^ 1);
         float* slot_base = p.ring + ((size_t)ring_row0 + (size_t)slot * kFuBM) * p.D;
-        int next_rp = 0, next_src = 0;
-        if (nrows > 0) {
-          gather_rows_batch<NV, U>(p, rp, first_src, nrows, lane, slot_base + (size_t)(gw * kRowsPerWarp) * p.D,
-                                   pol_stream, pol_keep, next_ptr, nnrows, next_rp, next_src);
-        } else if (has_next) {
-          next_rp = lane <= nnrows ? __ldg(next_ptr + lane) : 0;
-          const int nb = __shfl_sync(0xffffffffu, next_rp, 0), ne = __shfl_sync(0xffffffffu, next_rp, nnrows);
-          next_src = lane < ne - nb ? __ldg(p.src + nb + lane) : 0;
-        }
-        rp = next_rp;
-        first_src = next_src;
+        if (nrows > 0)
+          gather_rows_batch<NV, U>(p, l, v0, nrows, lane, slot_base + (size_t)(gw * kRowsPerWarp) * p.D, pol_stream,
+                                   pol_keep);
         // generic-proxy global writes -> visible to the TMA (async proxy) reads of this CTA
         asm volatile("fence.proxy.async.global;" ::: "memory");
         __syncwarp();
@@ -502,7 +455,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   FusedParams p{};
   p.h = h; p.ldh = D; p.row_ptr = row_ptr; p.src = src; p.V = V; p.L = L; p.D = D; p.normalize = normalize;
   p.ring = ring;
-  static const int pf_window = [] { const char* e = getenv("TFGNN_B200_PREFETCH_WINDOW"); return e ? atoi(e) : 32; }();
+  static const int pf_window = [] { const char* e = getenv("TFGNN_B200_PREFETCH_WINDOW"); return e ? atoi(e) : 16; }();
   p.prefetch_window = pf_window < 0 ? 0 : (pf_window > 32 ? 32 : pf_window);
   static const int discard_env = [] { const char* e = getenv("TFGNN_B200_RING_DISCARD"); return e ? atoi(e) : 1; }();
   p.discard_ring = discard_env;
