@@ -467,7 +467,10 @@ def test_target_range_shards_match_full(kind, extra):
                     parts.append(out.cpu().numpy())
                 else:
                     first = out.cpu().numpy()
-            assert np.array_equal(first, parts[-1])      # unfiltered and pre-filtered edge lists agree
+            if kind == "rgat":   # hub targets are combined with float atomics (rgat.cu): equal up to rounding
+                assert_states_close(first, parts[-1].astype(np.float64), tol=2e-6)
+            else:
+                assert np.array_equal(first, parts[-1])  # unfiltered and pre-filtered edge lists agree
         assert_states_close(np.concatenate(parts, axis=0), full.astype(np.float64), tol=2e-6)
 
 

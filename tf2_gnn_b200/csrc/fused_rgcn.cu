@@ -455,7 +455,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   FusedParams p{};
   p.h = h; p.ldh = D; p.row_ptr = row_ptr; p.src = src; p.V = V; p.L = L; p.D = D; p.normalize = normalize;
   p.ring = ring;
-  static const int pf_window = [] { const char* e = getenv("TFGNN_B200_PREFETCH_WINDOW"); return e ? atoi(e) : 16; }();
+  static const int pf_window = [] { const char* e = getenv("TFGNN_B200_PREFETCH_WINDOW"); return e ? atoi(e) : 32; }();
   p.prefetch_window = pf_window < 0 ? 0 : (pf_window > 32 ? 32 : pf_window);
   static const int discard_env = [] { const char* e = getenv("TFGNN_B200_RING_DISCARD"); return e ? atoi(e) : 1; }();
   p.discard_ring = discard_env;
