@@ -117,7 +117,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -310,13 +310,17 @@ def main():
     torch.cuda.synchronize()
     prepare_ms = (time.perf_counter() - t0) * 1e3
     inp = MessagePassingInput(h_dev, adj_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # nvidia-smi needs ~0.5 s to produce its first line: start before the warm-up
     for _ in range(args.warmup):
         out = layer(inp, prepared=prepared)
     torch.cuda.synchronize()
+    t_hold = time.perf_counter()
+    while time.perf_counter() - t_hold < 0.6:      # keep the GPU under the same load while the sampler spins up
+        out = layer(inp, prepared=prepared)
+    torch.cuda.synchronize()
     barrier(world)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = _ffi.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     torch.cuda.synchronize()
@@ -386,5 +390,17 @@ def main():
     print(json.dumps(line), flush=True)
 
 
+def _shutdown():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    finally:
+        _shutdown()

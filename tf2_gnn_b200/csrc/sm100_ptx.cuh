@@ -88,6 +88,13 @@ __device__ __forceinline__ void prefetch_l2(const void* ptr) {
 __device__ __forceinline__ void discard_l2_128(const void* ptr) {
   asm volatile("discard.global.L2 [%0], 128;" ::"l"(ptr) : "memory");
 }
+// cp.async (LDGSTS): 16 B global -> shared without holding a register; completion via commit/wait groups.
+__device__ __forceinline__ void cp_async16_hint(uint32_t smem_addr, const void* gptr, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // One request prefetches `bytes` (multiple of 16) contiguous bytes into L2.
 __device__ __forceinline__ void bulk_prefetch_l2(const void* ptr, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
