@@ -316,10 +316,6 @@ def main():
     for _ in range(args.warmup):
         out = layer(inp, prepared=prepared)
     torch.cuda.synchronize()
-    t_hold = time.perf_counter()
-    while time.perf_counter() - t_hold < 0.6:      # keep the GPU under the same load while the sampler spins up
-        out = layer(inp, prepared=prepared)
-    torch.cuda.synchronize()
     barrier(world)
     launches0 = _ffi.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]

@@ -49,6 +49,7 @@ struct FusedParams {
   int V, L, D;
   int normalize;
   int discard_ring;     // discard.global.L2 on consumed ring slots
+  int stage_rows;       // 1: R rows per round travel by cp.async through shared memory
   int prefetch_window;  // edges whose rows are L2-prefetched ahead of the register loads (0 = off)
   // ring
   float* ring;  // [grid * kFuSlots * 128, D]
@@ -124,18 +125,19 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, i
         seg_end = __shfl_sync(0xffffffffu, rp, row + 1);
       }
     };
-    for (int j0 = 0; j0 < n; j0 += U + R) {
+    const int RR = p.stage_rows ? R : 0;
+    for (int j0 = 0; j0 < n; j0 += U + RR) {
       {
         // roll the L2 prefetch window: rows of edges [j0 + W, j0 + W + U + R)
         const int w0 = j0 + p.prefetch_window;
-        if (p.prefetch_window > 0 && lane >= w0 && lane < min(n, w0 + U + R))
+        if (p.prefetch_window > 0 && lane >= w0 && lane < min(n, w0 + U + RR))
           ptx::bulk_prefetch_l2(p.h + (long long)my_src * p.ldh, row_bytes);
       }
       // (1) R rows by cp.async into the warp's staging buffer: edges j0 .. j0+R-1
 #pragma unroll
       for (int q = 0; q < R; ++q) {
         const int s = __shfl_sync(0xffffffffu, my_src, (j0 + q) & 31);
-        if (j0 + q < n) {
+        if (q < RR && j0 + q < n) {
           const float* rowp = p.h + (long long)s * p.ldh;
 #pragma unroll
           for (int j = 0; j < NV; ++j) {
@@ -149,12 +151,12 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, i
       float4 r[U][NV];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int s = __shfl_sync(0xffffffffu, my_src, (j0 + R + u) & 31);
+        const int s = __shfl_sync(0xffffffffu, my_src, (j0 + RR + u) & 31);
         const float* rowp = p.h + (long long)s * p.ldh;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
           const int c4 = lane + 32 * j;
-          r[u][j] = (j0 + R + u < n && c4 < C4) ? ptx::ld_nc_f4_hint(rowp + 4 * c4, pol_stream)
+          r[u][j] = (j0 + RR + u < n && c4 < C4) ? ptx::ld_nc_f4_hint(rowp + 4 * c4, pol_stream)
                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
@@ -162,7 +164,7 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, i
       ptx::cp_async_wait_all();
 #pragma unroll
       for (int q = 0; q < R; ++q) {
-        if (j0 + q < n) {
+        if (q < RR && j0 + q < n) {
           add_edge(base + j0 + q);
 #pragma unroll
           for (int j = 0; j < NV; ++j) {
@@ -176,8 +178,8 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, i
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (j0 + R + u < n) {
-          add_edge(base + j0 + R + u);
+        if (j0 + RR + u < n) {
+          add_edge(base + j0 + RR + u);
 #pragma unroll
           for (int j = 0; j < NV; ++j) {
             acc[j].x += r[u][j].x; acc[j].y += r[u][j].y; acc[j].z += r[u][j].z; acc[j].w += r[u][j].w;
@@ -501,6 +503,8 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   p.prefetch_window = pf_window < 0 ? 0 : (pf_window > 32 ? 32 : pf_window);
   static const int discard_env = [] { const char* e = getenv("TFGNN_B200_RING_DISCARD"); return e ? atoi(e) : 1; }();
   p.discard_ring = discard_env;
+  static const int stage_env = [] { const char* e = getenv("TFGNN_B200_GATHER_STAGE"); return e ? atoi(e) : 0; }();
+  p.stage_rows = stage_env;
   p.N = H; p.block_n = H; p.n_tiles = 1;
   p.m_tiles = ((long long)V + kFuBM - 1) / kFuBM;
   static const int bk_env = [] { const char* e = getenv("TFGNN_B200_FUSED_BK"); return e ? atoi(e) : 16; }();
@@ -508,7 +512,8 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   const int kFuATileBytes = kFuBM * kFuBK * 4;
   p.kb_per_type = D / kFuBK;
   const int stage_bytes = 2 * kFuATileBytes + 2 * p.block_n * kFuBK * 4;
-  int stages = (kFuSmemLimit - 2048 - kFuEpiBytes - kFuGatherWarps * kFuGatherStageBytes) / stage_bytes;
+  const int gather_stage_bytes = p.stage_rows ? kFuGatherWarps * kFuGatherStageBytes : 0;
+  int stages = (kFuSmemLimit - 2048 - kFuEpiBytes - gather_stage_bytes) / stage_bytes;
   if (stages > 6) stages = 6;
   TFGNN_REQUIRE(stages >= 2, "fused RGCN: tile does not fit shared memory");
   p.num_stages = stages;
@@ -546,7 +551,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
     }
   }
   const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4 + 2 * kFuSlots + 4) * sizeof(uint64_t) +
-                            kFuEpiBytes + kFuGatherWarps * kFuGatherStageBytes + 1024;
+                            kFuEpiBytes + gather_stage_bytes + 1024;
   const int nv = (D + 127) / 128;
   // L2 set-aside for the evict_last (persisting) lines: the ring + the packed weights.  Without a carve-out
   // the evict_last hint is advisory only and the ring gets written back to HBM (measured: +4 GB/layer).
