@@ -46,6 +46,9 @@ WORKLOADS = {
                  desc="GGNN QM9-shaped 500k nodes / 1.5M edges / 5 edge types, hidden_dim=128 (BASELINE.json configs[3])"),
     "cfg5_shard": dict(V=2_000_000, E=[5_333_333] * 6, H=320, kind="gnn_film", graph="er",
                        desc="GNN-FiLM 1/8 shard of BASELINE.json configs[4]: 2M nodes / 32M edges / 6 edge types, hidden_dim=320"),
+    "h320": dict(V=1_000_000, E=[6_666_667] * 3, H=320, kind="rgcn", graph="er",
+                 desc="RGCN synthetic Erdos-Renyi 1M nodes / 20M edges / 3 edge types, hidden_dim=320 "
+                      "(north_star hidden size on a graph that exceeds L2)"),
     "tiny": dict(V=20_000, E=[100_000] * 4, H=256, kind="rgcn", graph="er", desc="smoke-sized cfg2"),
 }
 METRIC = "edges/sec (fused gather-msg-scatter)"

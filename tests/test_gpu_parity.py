@@ -222,6 +222,9 @@ def test_rgcn_pipelined_two_stream(chunk_rows, V, monkeypatch):
     (40000, 256, 256, 3, 150000, dict(hub=True), "sqrt_n"),
     (20000, 320, 256, 2, 60000, {}, "sum"),
     (1000, 96, 48, 5, 4000, {}, "sum"),
+    (3000, 320, 320, 3, 20000, dict(self_loops=True), "sum"),     # PPI hidden size: two N passes over the ring
+    (20000, 320, 320, 3, 100000, dict(hub=True), "mean"),
+    (2500, 128, 512, 2, 9000, {}, "sum"),
 ])
 def test_rgcn_fused_kernel(V, D, H, L, E, opts, agg):
     """fused_rgcn_kernel: gather -> segment-sum -> tcgen05 3xTF32 -> activation in one persistent kernel."""

@@ -201,7 +201,7 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
                            (reinterpret_cast<uintptr_t>(h) & 15) == 0;
     const bool fused_ok = !use_target && fused_rgcn_supported(V, L, D, H, h, out, ldo);
     if (path == TFGNN_PATH_FUSED_TC && !fused_ok)
-      return unsupported("TFGNN_PATH_FUSED_TC needs D % 32 == 0, 16 <= H <= 256, H % 16 == 0, no target-state input");
+      return unsupported("TFGNN_PATH_FUSED_TC needs D % 32 == 0, 16 <= H <= 512 (H % 16 == 0; H > 256: H % 32 == 0 and <= 7 edge types), no target-state input");
     static const bool fused_auto = [] { const char* e = getenv("TFGNN_B200_FUSED"); return !e || atoi(e) != 0; }();
     if (fused_ok && (path == TFGNN_PATH_FUSED_TC || (path == TFGNN_PATH_AUTO && fused_auto))) {
       void *packed = nullptr, *ring = nullptr;
@@ -209,7 +209,7 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
       if (rc) return rc;
       rc = batch_scratch(b, 6, gemm_tc_packed_bytes(H, K), &packed);
       if (rc) return rc;
-      rc = batch_scratch(b, 15, fused_rgcn_ring_bytes(D), &ring);
+      rc = batch_scratch(b, 15, fused_rgcn_ring_bytes(D, L, H), &ring);
       if (rc) return rc;
       rc = launch_pack_weights_tc((const float*)Wcat, H, K, H, (float*)packed, st);
       if (rc) return rc;

@@ -32,7 +32,7 @@ constexpr int kFuBM = 128;
 constexpr int kFuGatherWarps = 16;
 constexpr int kFuFirstGatherWarp = 12;
 constexpr int kFuThreads = 32 * (kFuFirstGatherWarp + kFuGatherWarps);
-constexpr int kFuSlots = 3;
+constexpr int kFuMaxSlots = 8;                  // ring slots per CTA: 3, or L+1 when the N dimension needs two passes
 constexpr int kFuTmemCols = 512;
 constexpr int kFuAccStride = 256;
 constexpr int kFuSmemLimit = 227 * 1024;
@@ -52,7 +52,8 @@ struct FusedParams {
   int stage_rows;       // 1: R rows per round travel by cp.async through shared memory
   int prefetch_window;  // edges whose rows are L2-prefetched ahead of the register loads (0 = off)
   // ring
-  float* ring;  // [grid * kFuSlots * 128, D]
+  float* ring;  // [grid * num_slots * 128, D]
+  int num_slots;
   // GEMM
   int N, block_n, n_tiles;
   long long m_tiles;
@@ -216,13 +217,15 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* tmem_full = bars + 3 * S;
   uint64_t* tmem_empty = bars + 3 * S + 2;
   uint64_t* slot_ready = bars + 3 * S + 4;
-  uint64_t* slot_free = bars + 3 * S + 4 + kFuSlots;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4 + 2 * kFuSlots);
-  float* epi_stage = reinterpret_cast<float*>(bars + ((3 * S + 4 + 2 * kFuSlots + 2 + 1) & ~1));
+  uint64_t* slot_free = bars + 3 * S + 4 + kFuMaxSlots;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4 + 2 * kFuMaxSlots);
+  float* epi_stage = reinterpret_cast<float*>(bars + ((3 * S + 4 + 2 * kFuMaxSlots + 2 + 1) & ~1));
   float* gather_stage = epi_stage + kFuEpiBytes / 4;   // kFuGatherWarps x kFuGatherStageBytes
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long total_tiles = p.m_tiles * p.n_tiles;
+  const long long total_tiles = p.m_tiles;      // one tile = 128 targets; the N dimension is covered in n_pass passes
+  const int n_pass = p.n_tiles;
+  const int kFuSlots = p.num_slots;
   const int kb_per_tile = p.L * p.kb_per_type;
 
   if (warp == 0 && lane == 0) {
@@ -237,7 +240,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       ptx::mbar_init(&tmem_full[a], 1);
       ptx::mbar_init(&tmem_empty[a], 128);
     }
-    for (int r = 0; r < kFuSlots; ++r) {
+    for (int r = 0; r < kFuMaxSlots; ++r) {
       ptx::mbar_init(&slot_ready[r], kFuGatherWarps);
       ptx::mbar_init(&slot_free[r], 128);
     }
@@ -255,18 +258,21 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t corr_off = p.block_n <= 128 ? 128 : 256;
   const int ring_row0 = blockIdx.x * kFuSlots * kFuBM;  // first ring row of this CTA
 
-  // NOTE on tiles: with n_tiles > 1 the same 128 targets would be gathered once per N tile; the host
-  // only launches this kernel with n_tiles == 1 ... or accepts the re-gather (see launch_fused_rgcn).
+  // N passes: main + correction accumulators need 2*block_n <= 512 TMEM columns, so H in (256, 512] is covered
+  // in two passes of block_n = H/2 columns over the SAME gathered ring slots (the ring then holds all L types of
+  // the tile: num_slots = L + 1); every source row is still gathered exactly once.
   if (warp == 0) {
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t it = 0, slot_it = 0;
       const uint64_t pol_keep = ptx::policy_evict_last();   // ring slots and the 2 MB of weights stay in L2
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n0 = (int)(tile % p.n_tiles) * p.block_n;
-        for (int l = 0; l < p.L; ++l, ++slot_it) {
-          const int slot = slot_it % kFuSlots;
-          ptx::mbar_wait(&slot_ready[slot], (slot_it / kFuSlots) & 1);
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, slot_it += p.L) {
+       for (int pass = 0; pass < n_pass; ++pass) {
+        const int n0 = pass * p.block_n;
+        for (int l = 0; l < p.L; ++l) {
+          const uint32_t sq = slot_it + l;
+          const int slot = sq % kFuSlots;
+          ptx::mbar_wait(&slot_ready[slot], (sq / kFuSlots) & 1);
           for (int kb = 0; kb < p.kb_per_type; ++kb, ++it) {
             const int s = it % S;
             const uint32_t ph = (it / S) & 1;
@@ -279,13 +285,15 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             ptx::tma_load_2d_hint(st + 2 * kFuATileBytes + b_tile_bytes, &map_b, &full[s], kcol, p.N + n0, pol_keep);
           }
         }
+       }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     const uint32_t idesc = ptx::umma_idesc_tf32_m128((uint32_t)p.block_n);
     uint32_t it = 0, tile_count = 0;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_count) {
+    for (long long tp = (long long)blockIdx.x * n_pass; tp < total_tiles * n_pass;
+         tp = (tp % n_pass == n_pass - 1) ? tp + (long long)(gridDim.x - 1) * n_pass + 1 : tp + 1, ++tile_count) {
       const uint32_t acc = tile_count % n_acc, acc_ph = (tile_count / n_acc) & 1;
       ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
       ptx::tc_fence_after_sync();
@@ -319,14 +327,16 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else if (warp >= 4 && warp < 8) {
     // ================= A splitters =================
     const int tid = threadIdx.x - 128;
-    uint32_t it = 0, slot_it = 0;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      for (int l = 0; l < p.L; ++l, ++slot_it) {
+    uint32_t it = 0, slot_base_it = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, slot_base_it += p.L) {
+     for (int pass = 0; pass < n_pass; ++pass) {
+      for (int l = 0; l < p.L; ++l) {
+        const uint32_t slot_it = slot_base_it + l;
         for (int kb = 0; kb < p.kb_per_type; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           ptx::mbar_wait(&full[s], ph);
-          if (kb == p.kb_per_type - 1) {
+          if (kb == p.kb_per_type - 1 && pass == n_pass - 1) {
             // all TMA reads of the slot have landed: its lines are dead.  Discard them from L2 so that they are
             // never written back to HBM (the ring is pure on-chip hand-off), then hand the slot back.
             if (p.discard_ring) {
@@ -353,15 +363,17 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           ptx::mbar_arrive(&split[s]);
         }
       }
+     }
     }
   } else if (warp >= 8 && warp < kFuFirstGatherWarp) {
     // ================= epilogue (warps 8..11 -> TMEM lane quarters 0..3) =================
     const int q = warp & 3;
     uint32_t tile_count = 0;
     const uint64_t pol_stream = ptx::policy_evict_first();
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++tile_count) {
-      const long long m0 = (tile / p.n_tiles) * kFuBM;
-      const int n0 = (int)(tile % p.n_tiles) * p.block_n;
+    for (long long tp = (long long)blockIdx.x * n_pass; tp < total_tiles * n_pass;
+         tp = (tp % n_pass == n_pass - 1) ? tp + (long long)(gridDim.x - 1) * n_pass + 1 : tp + 1, ++tile_count) {
+      const long long m0 = (tp / n_pass) * kFuBM;
+      const int n0 = (int)(tp % n_pass) * p.block_n;
       const uint32_t acc = tile_count % n_acc, acc_ph = (tile_count / n_acc) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_ph);
       ptx::tc_fence_after_sync();
@@ -430,7 +442,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const uint64_t pol_keep = ptx::policy_evict_last();
     uint32_t slot_it = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (int)((tile / p.n_tiles) * kFuBM);
+      const int m0 = (int)(tile * kFuBM);
       const int v0 = m0 + gw * kRowsPerWarp;
       const int nrows = min(kRowsPerWarp, p.V - v0);   // <= 0 for warps past the last node
       for (int l = 0; l < p.L; ++l, ++slot_it) {
@@ -474,16 +486,20 @@ static EncodeTiledFn fu_encode_fn() {
 }
 
 bool fused_rgcn_supported(long long V, int L, int D, int H, const float* h, const float* out, int ldo) {
-  if (V < 1 || L < 1 || D % 32 != 0 || D > 512 || H % 16 != 0 || H < 16 || H > 256) return false;
+  if (V < 1 || L < 1 || D % 32 != 0 || D > 512 || H % 16 != 0 || H < 16 || H > 512) return false;
+  if (H > 256 && ((H / 2) % 16 != 0 || L + 1 > kFuMaxSlots)) return false;   // two N passes: ring holds L+1 slots
   if ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(out)) & 15) return false;
   if (ldo % 4 != 0) return false;
-  // one N tile per 128 targets so that every source row is gathered exactly once: the whole H must fit one
-  // accumulator pair in TMEM (main + correction): H <= 256.
+  // every source row is gathered exactly once; H <= 256 fits one accumulator pair (main + correction) in TMEM,
+  // H <= 512 takes two passes over the ring.
   return gemm_tc_supported(V, H, L * D, h, D, out, ldo) && fu_encode_fn() != nullptr;
 }
 
 constexpr int kFuMaxGrid = 160;
-size_t fused_rgcn_ring_bytes(int D) { return (size_t)kFuMaxGrid * kFuSlots * kFuBM * D * sizeof(float); }
+static int fused_num_slots(int L, int H) { return H > 256 ? L + 1 : 3; }
+size_t fused_rgcn_ring_bytes(int D, int L, int H) {
+  return (size_t)kFuMaxGrid * fused_num_slots(L, H) * kFuBM * D * sizeof(float);
+}
 
 int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src, int V, int L, int normalize,
                       const float* packedB, int H, float* ring, float* out, int ldo, const GemmEpilogue& epi,
@@ -505,7 +521,10 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   p.discard_ring = discard_env;
   static const int stage_env = [] { const char* e = getenv("TFGNN_B200_GATHER_STAGE"); return e ? atoi(e) : 0; }();
   p.stage_rows = stage_env;
-  p.N = H; p.block_n = H; p.n_tiles = 1;
+  p.N = H;
+  p.n_tiles = H > 256 ? 2 : 1;            // N passes
+  p.block_n = H / p.n_tiles;
+  p.num_slots = fused_num_slots(L, H);
   p.m_tiles = ((long long)V + kFuBM - 1) / kFuBM;
   static const int bk_env = [] { const char* e = getenv("TFGNN_B200_FUSED_BK"); return e ? atoi(e) : 16; }();
   const int kFuBK = bk_env == 32 ? 32 : 16;
@@ -524,7 +543,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   const int Kp = L * D;
   CUtensorMap map_a, map_b;
   {
-    cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)grid * kFuSlots * kFuBM};
+    cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)grid * p.num_slots * kFuBM};
     cuuint64_t strides[1] = {(cuuint64_t)D * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)kFuBK, (cuuint32_t)kFuBM};
     cuuint32_t estr[2] = {1, 1};
@@ -550,7 +569,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
       return TFGNN_ERR_CUDA;
     }
   }
-  const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4 + 2 * kFuSlots + 4) * sizeof(uint64_t) +
+  const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4 + 2 * kFuMaxSlots + 4) * sizeof(uint64_t) +
                             kFuEpiBytes + gather_stage_bytes + 1024;
   const int nv = (D + 127) / 128;
   // L2 set-aside for the evict_last (persisting) lines: the ring + the packed weights.  Without a carve-out
