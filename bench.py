@@ -120,7 +120,7 @@ class ClockSampler:
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
@@ -264,6 +264,7 @@ def main():
     ap.add_argument("--path", default="auto")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="do not poll nvidia-smi during the run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     wl = WORKLOADS[args.workload]
@@ -314,7 +315,7 @@ def main():
     prepare_ms = (time.perf_counter() - t0) * 1e3
     inp = MessagePassingInput(h_dev, adj_dev)
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clock_sampler:
         sampler.start()          # nvidia-smi needs ~0.5 s to produce its first line: start before the warm-up
     for _ in range(args.warmup):
         out = layer(inp, prepared=prepared)
