@@ -36,9 +36,8 @@ constexpr int kFuMaxSlots = 8;                  // ring slots per CTA: 3, or L+1
 constexpr int kFuTmemCols = 512;
 constexpr int kFuAccStride = 256;
 constexpr int kFuSmemLimit = 227 * 1024;
-constexpr int kFuEpiPitch = 20;                  // 16-column staging tile + 4 pad floats
+constexpr int kFuEpiPitch = 36;
 constexpr int kFuEpiBytes = 4 * 32 * kFuEpiPitch * 4;
-constexpr int kFuGatherStageBytes = 4096;       // per gather warp: rows staged in shared memory by cp.async
 
 struct FusedParams {
   // graph
@@ -49,7 +48,6 @@ struct FusedParams {
   int V, L, D;
   int normalize;
   int discard_ring;     // discard.global.L2 on consumed ring slots
-  int stage_rows;       // 1: R rows per round travel by cp.async through shared memory
   int prefetch_window;  // edges whose rows are L2-prefetched ahead of the register loads (0 = off)
   // ring
   float* ring;  // [grid * num_slots * 128, D]
@@ -79,14 +77,9 @@ __device__ __forceinline__ float fu_row_norm(const GemmEpilogue& e, long long ro
 // row loads in flight per lane (the dependent row_ptr -> index chain is paid once per 8 rows, not per row).
 // h rows are read with L2 evict_first (each row is used once per incoming edge, no reuse window); the ring
 // rows are written with L2 evict_last so that they are still resident when the TMA reads them back.
-//
-// Bytes in flight are what bounds this gather (loaded memory latency ~3 us); registers allow U rows per lane,
-// so R more rows per round travel by cp.async into a small per-warp shared-memory buffer (no registers held):
-// each lane copies exactly the 16 B chunks it later reads back, so no cross-lane synchronisation is needed.
-template <int NV, int U, int R>
+template <int NV, int U>
 __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, int v0, int nrows, int lane,
-                                                  float* dst, uint64_t pol_stream, uint64_t pol_keep,
-                                                  float* stage) {
+                                                  float* dst, uint64_t pol_stream, uint64_t pol_keep) {
   const int C4 = p.D >> 2;
   const int rp = lane <= nrows ? __ldg(p.row_ptr + (long long)l * p.V + v0 + lane) : 0;
   const int e_begin = __shfl_sync(0xffffffffu, rp, 0);
@@ -118,69 +111,34 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, i
     const uint32_t row_bytes = (uint32_t)p.D * 4;
     // prime the L2 prefetch window: ONE bulk request per source row (cp.async.bulk.prefetch.L2)
     if (lane < min(n, p.prefetch_window)) ptx::bulk_prefetch_l2(p.h + (long long)my_src * p.ldh, row_bytes);
-    const uint32_t stage_u32 = ptx::smem_u32(stage);
-    auto add_edge = [&](int e) {
-      while (e >= seg_end) {   // warp-uniform: close finished (possibly empty) segments
-        flush(row);
-        ++row;
-        seg_end = __shfl_sync(0xffffffffu, rp, row + 1);
-      }
-    };
-    const int RR = p.stage_rows ? R : 0;
-    for (int j0 = 0; j0 < n; j0 += U + RR) {
+    for (int j0 = 0; j0 < n; j0 += U) {
       {
-        // roll the L2 prefetch window: rows of edges [j0 + W, j0 + W + U + R)
+        // roll the window: rows of edges [j0 + W, j0 + W + U)
         const int w0 = j0 + p.prefetch_window;
-        if (p.prefetch_window > 0 && lane >= w0 && lane < min(n, w0 + U + RR))
+        if (p.prefetch_window > 0 && lane >= w0 && lane < min(n, w0 + U))
           ptx::bulk_prefetch_l2(p.h + (long long)my_src * p.ldh, row_bytes);
       }
-      // (1) R rows by cp.async into the warp's staging buffer: edges j0 .. j0+R-1
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        const int s = __shfl_sync(0xffffffffu, my_src, (j0 + q) & 31);
-        if (q < RR && j0 + q < n) {
-          const float* rowp = p.h + (long long)s * p.ldh;
-#pragma unroll
-          for (int j = 0; j < NV; ++j) {
-            const int c4 = lane + 32 * j;
-            if (c4 < C4) ptx::cp_async16_hint(stage_u32 + (uint32_t)((q * NV * 32 + c4) * 16), rowp + 4 * c4, pol_stream);
-          }
-        }
-      }
-      ptx::cp_async_commit();
-      // (2) U rows by register loads: edges j0+R .. j0+R+U-1
       float4 r[U][NV];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int s = __shfl_sync(0xffffffffu, my_src, (j0 + RR + u) & 31);
+        const int s = __shfl_sync(0xffffffffu, my_src, (j0 + u) & 31);
         const float* rowp = p.h + (long long)s * p.ldh;
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
           const int c4 = lane + 32 * j;
-          r[u][j] = (j0 + RR + u < n && c4 < C4) ? ptx::ld_nc_f4_hint(rowp + 4 * c4, pol_stream)
-                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      // (3) reduce in edge order: staged rows first, then the register rows
-      ptx::cp_async_wait_all();
-#pragma unroll
-      for (int q = 0; q < R; ++q) {
-        if (q < RR && j0 + q < n) {
-          add_edge(base + j0 + q);
-#pragma unroll
-          for (int j = 0; j < NV; ++j) {
-            const int c4 = lane + 32 * j;
-            if (c4 < C4) {
-              const float4 x = *reinterpret_cast<const float4*>(stage + (size_t)(q * NV * 32 + c4) * 4);
-              acc[j].x += x.x; acc[j].y += x.y; acc[j].z += x.z; acc[j].w += x.w;
-            }
-          }
+          r[u][j] = (j0 + u < n && c4 < C4) ? ptx::ld_nc_f4_hint(rowp + 4 * c4, pol_stream)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        if (j0 + RR + u < n) {
-          add_edge(base + j0 + RR + u);
+        if (j0 + u < n) {
+          const int e = base + j0 + u;
+          while (e >= seg_end) {   // warp-uniform: close finished (possibly empty) segments
+            flush(row);
+            ++row;
+            seg_end = __shfl_sync(0xffffffffu, rp, row + 1);
+          }
 #pragma unroll
           for (int j = 0; j < NV; ++j) {
             acc[j].x += r[u][j].x; acc[j].y += r[u][j].y; acc[j].z += r[u][j].z; acc[j].w += r[u][j].w;
@@ -220,7 +178,6 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* slot_free = bars + 3 * S + 4 + kFuMaxSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4 + 2 * kFuMaxSlots);
   float* epi_stage = reinterpret_cast<float*>(bars + ((3 * S + 4 + 2 * kFuMaxSlots + 2 + 1) & ~1));
-  float* gather_stage = epi_stage + kFuEpiBytes / 4;   // kFuGatherWarps x kFuGatherStageBytes
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long total_tiles = p.m_tiles;      // one tile = 128 targets; the N dimension is covered in n_pass passes
@@ -437,7 +394,6 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int gw = warp - kFuFirstGatherWarp;
     constexpr int kRowsPerWarp = kFuBM / kFuGatherWarps;
     constexpr int U = NV <= 1 ? 8 : (NV == 2 ? 4 : 2);
-    constexpr int R = NV <= 1 ? 8 : (NV == 2 ? 4 : 2);   // rows staged through shared memory per round (R*NV*512 B <= 4 KB)
     const uint64_t pol_stream = ptx::policy_evict_first();
     const uint64_t pol_keep = ptx::policy_evict_last();
     uint32_t slot_it = 0;
@@ -450,8 +406,8 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         ptx::mbar_wait(&slot_free[slot], ((slot_it / kFuSlots) & 1) ^ 1);
         float* slot_base = p.ring + ((size_t)ring_row0 + (size_t)slot * kFuBM) * p.D;
         if (nrows > 0)
-          gather_rows_batch<NV, U, R>(p, l, v0, nrows, lane, slot_base + (size_t)(gw * kRowsPerWarp) * p.D, pol_stream,
-                                      pol_keep, gather_stage + (size_t)gw * (kFuGatherStageBytes / 4));
+          gather_rows_batch<NV, U>(p, l, v0, nrows, lane, slot_base + (size_t)(gw * kRowsPerWarp) * p.D, pol_stream,
+                                   pol_keep);
         // generic-proxy global writes -> visible to the TMA (async proxy) reads of this CTA
         asm volatile("fence.proxy.async.global;" ::: "memory");
         __syncwarp();
@@ -519,8 +475,6 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   p.prefetch_window = pf_window < 0 ? 0 : (pf_window > 32 ? 32 : pf_window);
   static const int discard_env = [] { const char* e = getenv("TFGNN_B200_RING_DISCARD"); return e ? atoi(e) : 1; }();
   p.discard_ring = discard_env;
-  static const int stage_env = [] { const char* e = getenv("TFGNN_B200_GATHER_STAGE"); return e ? atoi(e) : 0; }();
-  p.stage_rows = stage_env;
   p.N = H;
   p.n_tiles = H > 256 ? 2 : 1;            // N passes
   p.block_n = H / p.n_tiles;
@@ -531,8 +485,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   const int kFuATileBytes = kFuBM * kFuBK * 4;
   p.kb_per_type = D / kFuBK;
   const int stage_bytes = 2 * kFuATileBytes + 2 * p.block_n * kFuBK * 4;
-  const int gather_stage_bytes = p.stage_rows ? kFuGatherWarps * kFuGatherStageBytes : 0;
-  int stages = (kFuSmemLimit - 2048 - kFuEpiBytes - gather_stage_bytes) / stage_bytes;
+  int stages = (kFuSmemLimit - 2048 - kFuEpiBytes) / stage_bytes;
   if (stages > 6) stages = 6;
   TFGNN_REQUIRE(stages >= 2, "fused RGCN: tile does not fit shared memory");
   p.num_stages = stages;
@@ -570,7 +523,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
     }
   }
   const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4 + 2 * kFuMaxSlots + 4) * sizeof(uint64_t) +
-                            kFuEpiBytes + gather_stage_bytes + 1024;
+                            kFuEpiBytes + 1024;
   const int nv = (D + 127) / 128;
   // L2 set-aside for the evict_last (persisting) lines: the ring + the packed weights.  Without a carve-out
   // the evict_last hint is advisory only and the ring gets written back to HBM (measured: +4 GB/layer).
