@@ -452,7 +452,11 @@ bool fused_rgcn_supported(long long V, int L, int D, int H, const float* h, cons
 }
 
 constexpr int kFuMaxGrid = 160;
-static int fused_num_slots(int L, int H) { return H > 256 ? L + 1 : 3; }
+static int fused_num_slots(int L, int H) {
+  static const int env_slots = [] { const char* e = getenv("TFGNN_B200_RING_SLOTS"); return e ? atoi(e) : 0; }();
+  if (H > 256) return L + 1;
+  return (env_slots >= 2 && env_slots <= kFuMaxSlots) ? env_slots : 3;
+}
 size_t fused_rgcn_ring_bytes(int D, int L, int H) {
   return (size_t)kFuMaxGrid * fused_num_slots(L, H) * kFuBM * D * sizeof(float);
 }
