@@ -48,6 +48,7 @@ struct FusedParams {
   int V, L, D;
   int normalize;
   int discard_ring;     // discard.global.L2 on consumed ring slots
+  int debug_skip;       // timing experiments only (results invalid): 1 = no edge gathers, 2 = one K block per slot
   int prefetch_window;  // edges whose rows are L2-prefetched ahead of the register loads (0 = off)
   // ring
   float* ring;  // [grid * num_slots * 128, D]
@@ -83,7 +84,7 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, i
   const int C4 = p.D >> 2;
   const int rp = lane <= nrows ? __ldg(p.row_ptr + (long long)l * p.V + v0 + lane) : 0;
   const int e_begin = __shfl_sync(0xffffffffu, rp, 0);
-  const int e_end = __shfl_sync(0xffffffffu, rp, nrows);
+  const int e_end = p.debug_skip == 1 ? e_begin : __shfl_sync(0xffffffffu, rp, nrows);
   int row = 0;
   int seg_end = __shfl_sync(0xffffffffu, rp, 1);
   float4 acc[NV];
@@ -479,6 +480,8 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   p.prefetch_window = pf_window < 0 ? 0 : (pf_window > 32 ? 32 : pf_window);
   static const int discard_env = [] { const char* e = getenv("TFGNN_B200_RING_DISCARD"); return e ? atoi(e) : 1; }();
   p.discard_ring = discard_env;
+  static const int dbg_env = [] { const char* e = getenv("TFGNN_B200_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
+  p.debug_skip = dbg_env;
   p.N = H;
   p.n_tiles = H > 256 ? 2 : 1;            // N passes
   p.block_n = H / p.n_tiles;
@@ -488,6 +491,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   const int kFuBK = bk_env == 32 ? 32 : 16;
   const int kFuATileBytes = kFuBM * kFuBK * 4;
   p.kb_per_type = D / kFuBK;
+  if (p.debug_skip == 2) p.kb_per_type = 1;
   const int stage_bytes = 2 * kFuATileBytes + 2 * p.block_n * kFuBK * 4;
   int stages = (kFuSmemLimit - 2048 - kFuEpiBytes) / stage_bytes;
   if (stages > 6) stages = 6;
