@@ -93,6 +93,17 @@ def make_inputs(wl, seed):
     return h, adjs, weights
 
 
+def load_traffic(workload, path):
+    """Measured DRAM bytes per launch of the dominant kernel (one ncu --set full capture, profiles/traffic_r1.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic_r1.json")
+    try:
+        with open(p) as f:
+            e = json.load(f).get(f"{workload}:{path}")
+        return None if e is None else int(e["dram_bytes_read"]) + int(e["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -366,7 +377,7 @@ def main():
     alg = algorithmic_bytes(kind, V, wl["E"], H, H, params)
     achieved = alg / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
+                "traffic": load_traffic(args.workload, args.path), "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
                 "kernel": "whole layer call (for RGCN at H<=256: fused_rgcn_kernel + 2 weight-pack kernels); see profiles/"}
     cpu = None
     if not args.skip_cpu_baseline and kind == "rgcn":

@@ -48,7 +48,7 @@ struct FusedParams {
   int V, L, D;
   int normalize;
   int discard_ring;     // discard.global.L2 on consumed ring slots
-  int debug_skip;       // timing experiments only (results invalid): 1 = no edge gathers, 2 = one K block per slot
+  int debug_skip;       // timing experiments only (results invalid), bit mask: 1 = no edge gathers, 2 = one K block per slot, 4 = no epilogue work
   int prefetch_window;  // edges whose rows are L2-prefetched ahead of the register loads (0 = off)
   // ring
   float* ring;  // [grid * num_slots * 128, D]
@@ -84,7 +84,7 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, i
   const int C4 = p.D >> 2;
   const int rp = lane <= nrows ? __ldg(p.row_ptr + (long long)l * p.V + v0 + lane) : 0;
   const int e_begin = __shfl_sync(0xffffffffu, rp, 0);
-  const int e_end = p.debug_skip == 1 ? e_begin : __shfl_sync(0xffffffffu, rp, nrows);
+  const int e_end = (p.debug_skip & 1) ? e_begin : __shfl_sync(0xffffffffu, rp, nrows);
   int row = 0;
   int seg_end = __shfl_sync(0xffffffffu, rp, 1);
   float4 acc[NV];
@@ -340,7 +340,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const float rn = row_ok ? fu_row_norm(p.epi, row) : 1.0f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kFuAccStride;
       float* stage = epi_stage + (size_t)(warp - 8) * 32 * kFuEpiPitch;
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {   // 16 columns per TMEM round trip (72-register budget)
+      for (int c0 = 0; c0 < ((p.debug_skip & 4) ? 0 : p.block_n); c0 += 16) {   // 16 columns per TMEM round trip
         const int ncols = 16;
         {
           // TMEM -> registers: main and correction accumulators of up to 32 columns, ONE wait
@@ -491,7 +491,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   const int kFuBK = bk_env == 32 ? 32 : 16;
   const int kFuATileBytes = kFuBM * kFuBK * 4;
   p.kb_per_type = D / kFuBK;
-  if (p.debug_skip == 2) p.kb_per_type = 1;
+  if (p.debug_skip & 2) p.kb_per_type = 1;
   const int stage_bytes = 2 * kFuATileBytes + 2 * p.block_n * kFuBK * 4;
   int stages = (kFuSmemLimit - 2048 - kFuEpiBytes) / stage_bytes;
   if (stages > 6) stages = 6;
