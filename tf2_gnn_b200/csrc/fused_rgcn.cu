@@ -337,7 +337,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       ptx::tc_fence_after_sync();
       const long long row = m0 + q * 32 + lane;
       const bool row_ok = row < p.V;
-      const float rn = row_ok ? fu_row_norm(p.epi, row) : 1.0f;
+      const float inv_rn = row_ok ? 1.0f / fu_row_norm(p.epi, row) : 1.0f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kFuAccStride;
       float* stage = epi_stage + (size_t)(warp - 8) * 32 * kFuEpiPitch;
       for (int c0 = 0; c0 < ((p.debug_skip & 4) ? 0 : p.block_n); c0 += 16) {   // 16 columns per TMEM round trip
@@ -359,11 +359,20 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             if (half < nh) {
               float v[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                float x = __uint_as_float(mv[half][j]) + __uint_as_float(cv[half][j]);
-                if (p.epi.row_norm) x = x / rn;
-                if (p.epi.bias) x += __ldg(p.epi.bias + n0 + c0 + half * 16 + j);
-                v[j] = x;
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(mv[half][j]) + __uint_as_float(cv[half][j]);
+              // uniform branches hoisted out of the element loops (predicated-off code still costs issue slots
+              // and instruction-cache space: the epilogue was ~48 us per 128x256 tile before)
+              if (p.epi.row_norm) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] *= inv_rn;
+              }
+              if (p.epi.bias) {
+                const float4* bp = reinterpret_cast<const float4*>(p.epi.bias + n0 + c0 + half * 16);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 bb = __ldg(bp + j);
+                  v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+                }
               }
               apply_act_vec<16>(v, p.epi.act);
 #pragma unroll
