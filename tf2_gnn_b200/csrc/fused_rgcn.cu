@@ -48,6 +48,7 @@ struct FusedParams {
   int V, L, D;
   int normalize;
   int discard_ring;     // discard.global.L2 on consumed ring slots
+  int prefetch_warp;    // 1: a dedicated warp bulk-prefetches source rows into L2 a few row-waves ahead of the gather
   int debug_skip;       // timing experiments only (results invalid), bit mask: 1 = no edge gathers, 2 = one K block per slot, 4 = no epilogue work
   int prefetch_window;  // edges whose rows are L2-prefetched ahead of the register loads (0 = off)
   // ring
@@ -80,7 +81,8 @@ __device__ __forceinline__ float fu_row_norm(const GemmEpilogue& e, long long ro
 // rows are written with L2 evict_last so that they are still resident when the TMA reads them back.
 template <int NV, int U>
 __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, int v0, int nrows, int lane,
-                                                  float* dst, uint64_t pol_stream, uint64_t pol_keep) {
+                                                  float* dst, uint64_t pol_stream, uint64_t pol_keep,
+                                                  volatile uint32_t* progress) {
   const int C4 = p.D >> 2;
   const int rp = lane <= nrows ? __ldg(p.row_ptr + (long long)l * p.V + v0 + lane) : 0;
   const int e_begin = __shfl_sync(0xffffffffu, rp, 0);
@@ -104,6 +106,7 @@ __device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, i
                         pol_keep);
       acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    if (lane == 0) atomicAdd(const_cast<uint32_t*>(progress), 1u);
   };
 
   for (int base = e_begin; base < e_end; base += 32) {
@@ -178,6 +181,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* slot_ready = bars + 3 * S + 4;
   uint64_t* slot_free = bars + 3 * S + 4 + kFuMaxSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4 + 2 * kFuMaxSlots);
+  volatile uint32_t* progress = tmem_slot + 1;   // rows finished by the gather warps (paces the prefetch warp)
   float* epi_stage = reinterpret_cast<float*>(bars + ((3 * S + 4 + 2 * kFuMaxSlots + 2 + 1) & ~1));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -187,6 +191,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int kb_per_tile = p.L * p.kb_per_type;
 
   if (warp == 0 && lane == 0) {
+    tmem_slot[1] = 0;
     ptx::prefetch_tensormap(&map_a);
     ptx::prefetch_tensormap(&map_b);
     for (int s = 0; s < S; ++s) {
@@ -280,6 +285,48 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (kb == kb_per_tile - 1) ptx::mma_commit(&tmem_full[acc]);
         }
         __syncwarp();
+      }
+    }
+  } else if ((warp == 2 || warp == 3) && p.prefetch_warp) {
+    // ================= L2 prefetch warps (the two otherwise idle warps of warpgroup 0) =================
+    // They walk the same (tile, edge type) sequence as the gather warps, a few "row waves" ahead (wave w = row w
+    // of each of the 16 gather warps' 8-row groups), and issue one bulk L2 prefetch per source row.  DRAM latency
+    // is then paid by requests that hold no registers; the gather's own loads mostly hit L2.
+    constexpr int kRowsPerWarpG = kFuBM / kFuGatherWarps;       // 8 rows per gather warp = 8 waves per slot
+    constexpr int kLeadRows = 3 * kFuGatherWarps;              // stay <= ~3 waves ahead of the finished rows
+    const uint32_t row_bytes = (uint32_t)p.D * 4;
+    const int pw = warp - 2;
+    uint32_t rows_base = 0;                                    // valid rows of all previous (tile, type) units
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m0 = (int)(tile * kFuBM);
+      const int valid_rows = min(kFuBM, p.V - m0);
+      auto wave_rows = [&](int w) {                             // valid rows in wave w: groups g with g*8 + w < valid
+        const int c = (valid_rows - w + kRowsPerWarpG - 1) / kRowsPerWarpG;
+        return c < 0 ? 0 : (c > kFuGatherWarps ? kFuGatherWarps : c);
+      };
+      for (int l = 0; l < p.L; ++l, rows_base += (uint32_t)valid_rows) {
+        for (int w0 = 2 * pw; w0 < kRowsPerWarpG; w0 += 4) {   // two waves (32 rows) per iteration, one row per lane
+          uint32_t before = rows_base;
+          for (int w = 0; w < w0; ++w) before += (uint32_t)wave_rows(w);
+          // pace against the rows the gather warps have finished (bounded: it is only a heuristic)
+          for (int spin = 0; spin < 100000 && (int)(before - *progress) > kLeadRows; ++spin) __nanosleep(100);
+          const int g = lane & 15, w = w0 + (lane >> 4);
+          const int r = g * kRowsPerWarpG + w;
+          int beg = 0, end = 0;
+          if (r < valid_rows) {
+            const long long seg = (long long)l * p.V + m0 + r;
+            beg = __ldg(p.row_ptr + seg);
+            end = __ldg(p.row_ptr + seg + 1);
+          }
+          for (int e = beg; e < end; e += 8) {
+            int ids[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ids[q] = e + q < end ? __ldg(p.src + e + q) : -1;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (ids[q] >= 0) ptx::bulk_prefetch_l2(p.h + (long long)ids[q] * p.ldh, row_bytes);
+          }
+        }
       }
     }
   } else if (warp >= 4 && warp < 8) {
@@ -417,7 +464,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         float* slot_base = p.ring + ((size_t)ring_row0 + (size_t)slot * kFuBM) * p.D;
         if (nrows > 0)
           gather_rows_batch<NV, U>(p, l, v0, nrows, lane, slot_base + (size_t)(gw * kRowsPerWarp) * p.D, pol_stream,
-                                   pol_keep);
+                                   pol_keep, progress);
         // generic-proxy global writes -> visible to the TMA (async proxy) reads of this CTA
         asm volatile("fence.proxy.async.global;" ::: "memory");
         __syncwarp();
@@ -489,6 +536,9 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   p.prefetch_window = pf_window < 0 ? 0 : (pf_window > 32 ? 32 : pf_window);
   static const int discard_env = [] { const char* e = getenv("TFGNN_B200_RING_DISCARD"); return e ? atoi(e) : 1; }();
   p.discard_ring = discard_env;
+  static const int pfw_env = [] { const char* e = getenv("TFGNN_B200_PREFETCH_WARP"); return e ? atoi(e) : 1; }();
+  p.prefetch_warp = pfw_env;
+  if (p.prefetch_warp) p.prefetch_window = 0;   // the dedicated warp replaces the in-gather prefetch window
   static const int dbg_env = [] { const char* e = getenv("TFGNN_B200_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
   p.debug_skip = dbg_env;
   p.N = H;
