@@ -536,7 +536,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   p.prefetch_window = pf_window < 0 ? 0 : (pf_window > 32 ? 32 : pf_window);
   static const int discard_env = [] { const char* e = getenv("TFGNN_B200_RING_DISCARD"); return e ? atoi(e) : 1; }();
   p.discard_ring = discard_env;
-  static const int pfw_env = [] { const char* e = getenv("TFGNN_B200_PREFETCH_WARP"); return e ? atoi(e) : 1; }();
+  static const int pfw_env = [] { const char* e = getenv("TFGNN_B200_PREFETCH_WARP"); return e ? atoi(e) : 0; }();  // measured: no gain over the in-gather window
   p.prefetch_warp = pfw_env;
   if (p.prefetch_warp) p.prefetch_window = 0;   // the dedicated warp replaces the in-gather prefetch window
   static const int dbg_env = [] { const char* e = getenv("TFGNN_B200_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
