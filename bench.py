@@ -114,7 +114,11 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    NVML (nvidia-ml-py) polled from a thread every 10 ms; `nvidia-smi -lms` in a subprocess if NVML cannot be
+    loaded.  Samples are stamped with time.monotonic() and only those between begin() and end() are reported
+    (all samples since start() if the window caught none, noted in "window")."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -124,19 +128,87 @@ class ClockSampler:
         self.gpu_index = gpu_index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.samples = []          # (t, sm_mhz, max_mhz, reasons tuple)
+        self.t_begin = None
+        self.t_end = None
+        self._stop = False
+
+    def _nvml_loop(self, nv, handle):
+        bits = []
+        for name, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                           ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                           ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                           ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+            alt = attr.replace("ClocksEventReason", "ClocksThrottleReason")
+            val = getattr(nv, attr, getattr(nv, alt, None))
+            if val is not None:
+                bits.append((name, val))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons",
+                              getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM))
+                mask = get_reasons(handle) if get_reasons else 0
+                self.samples.append((time.monotonic(), sm, mx, tuple(n for n, b in bits if mask & b)))
+            except Exception:
+                pass
+            time.sleep(0.010)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            idx = self.gpu_index
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.gpu_index < len(ids) and ids[self.gpu_index].isdigit():
+                    idx = int(ids[self.gpu_index])
+            handle = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+                 "-lms", "50"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
+    def begin(self):
+        self.t_begin = time.monotonic()
+
+    def end(self):
+        self.t_end = time.monotonic()
+
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": None}
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            rows = self.samples
+            window = "timed region"
+            if self.t_begin is not None and self.t_end is not None:
+                inside = [r for r in rows if self.t_begin <= r[0] <= self.t_end]
+                if inside:
+                    rows = inside
+                else:
+                    window = "warm-up + timed region (no sample fell inside the timed region)"
+            if rows:
+                reasons = set()
+                for r in rows:
+                    reasons.update(r[3])
+                out.update(sm_mhz=float(np.median([r[1] for r in rows])), sm_max_mhz=float(max(r[2] for r in rows)),
+                           reasons=sorted(reasons), samples=len(rows), source="nvml, 10 ms poll", window=window)
+            return out
         if self.proc is None:
             return out
         try:
@@ -162,7 +234,7 @@ class ClockSampler:
                 continue
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                       samples=len(sm))
+                       samples=len(sm), source="nvidia-smi -lms 50", window="warm-up + timed region")
         return out
 
 
@@ -327,7 +399,7 @@ def main():
     inp = MessagePassingInput(h_dev, adj_dev)
     sampler = ClockSampler(local)
     if rank == 0 and not args.no_clock_sampler:
-        sampler.start()          # nvidia-smi needs ~0.5 s to produce its first line: start before the warm-up
+        sampler.start()          # before the warm-up, so the poller is running when the timed region starts
     for _ in range(args.warmup):
         out = layer(inp, prepared=prepared)
     torch.cuda.synchronize()
@@ -335,11 +407,13 @@ def main():
     launches0 = _ffi.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     torch.cuda.synchronize()
+    sampler.begin()
     ev[0].record()
     for i in range(args.steps):
         out = layer(inp, prepared=prepared)
         ev[i + 1].record()
     torch.cuda.synchronize()
+    sampler.end()
     barrier(world)
     launches = _ffi.launch_count() - launches0
     total_ms = ev[0].elapsed_time(ev[-1])

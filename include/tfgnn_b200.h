@@ -64,7 +64,10 @@ enum {
   TFGNN_PATH_SORTED_TC = 3,  /* CSR segmented reduce + 3xTF32 tcgen05 node-level GEMM    */
   TFGNN_PATH_FUSED_TC = 4    /* one kernel: gather-reduce -> tcgen05 -> activation       */
 };
-enum { TFGNN_PREPARE_VALIDATE = 1u << 0 };
+enum {
+  TFGNN_PREPARE_VALIDATE = 1u << 0,
+  TFGNN_PREPARE_TRANSPOSE = 1u << 1 /* key the CSR by SOURCE: the edge list of the backward pass (messages flow tgt->src) */
+};
 
 int tfgnn_b200_abi_version(void);
 const char* tfgnn_b200_last_error(void);
@@ -121,6 +124,16 @@ int tfgnn_b200_edge_mlp_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
 int tfgnn_b200_rgcn_fwd(tfgnn_batch_t* batch, const float* h, int32_t D, const float* const* W,
                         int32_t H, uint32_t flags, int32_t aggregation, int32_t activation,
                         int32_t path, float* out, void* stream);
+
+/* Backward of tfgnn_b200_rgcn_fwd (the reference differentiates with tf.GradientTape,
+ * models/graph_task_model.py:338-365).  batch_t is the SAME adjacency prepared with TFGNN_PREPARE_TRANSPOSE.
+ * out = saved forward output, grad_out = dL/dout [V,H]; writes grad_h [V,D] (may be NULL) and grad_W[l] [D,H].
+ * Supported: sum/mean/sqrt_n aggregation, activation after aggregation, activations none/relu/tanh/leaky_relu/
+ * elu/selu (derivative from the output); D and H multiples of 4. */
+int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* batch, tfgnn_batch_t* batch_t, const float* h, int32_t D,
+                        const float* const* W, int32_t H, uint32_t flags, int32_t aggregation,
+                        int32_t activation, const float* out, const float* grad_out, float* grad_h,
+                        float* const* grad_W, void* stream);
 
 /* GGNN (ggnn.py:68-89): edge-MLP messages (class default: 0 hidden layers, source state only,
  * normalised), aggregation, NO message activation, then Keras GRUCell(units=H, reset_after=True):

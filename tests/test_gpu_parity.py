@@ -477,6 +477,65 @@ def test_target_range_shards_match_full(kind, extra):
         assert_states_close(np.concatenate(parts, axis=0), full.astype(np.float64), tol=2e-6)
 
 
+def _torch_reference_layer(h, adjs, Ws, normalize, agg, act):
+    """float64 autograd restatement of the RGCN layer (reference op order) for gradient parity."""
+    V = h.shape[0]
+    msgs, tgts = [], []
+    for adj, W in zip(adjs, Ws):
+        src, tgt = adj[:, 0].long(), adj[:, 1].long()
+        m = h.index_select(0, src) @ W
+        if normalize:
+            c = torch.zeros(V, dtype=h.dtype).index_add_(0, tgt, torch.ones(len(tgt), dtype=h.dtype))
+            m = (1.0 / (c.index_select(0, tgt) + 1e-7)).unsqueeze(-1) * m
+        msgs.append(m)
+        tgts.append(tgt)
+    M, T = torch.cat(msgs), torch.cat(tgts)
+    out = torch.zeros((V, Ws[0].shape[1]), dtype=h.dtype).index_add_(0, T, M)
+    if agg in ("mean", "sqrt_n"):
+        n = torch.zeros(V, dtype=h.dtype).index_add_(0, T, torch.ones(len(T), dtype=h.dtype)).clamp(min=1)
+        out = out / (n if agg == "mean" else n.sqrt()).unsqueeze(-1)
+    return {"relu": torch.relu, "tanh": torch.tanh, "elu": torch.nn.functional.elu, "selu": torch.selu,
+            "leaky_relu": lambda x: torch.nn.functional.leaky_relu(x, 0.2)}[act](out)
+
+
+@pytest.mark.parametrize("V,D,H,L,E,agg,act,normalize", [
+    (300, 32, 48, 3, 2500, "sum", "relu", True),
+    (1000, 64, 64, 2, 9000, "mean", "tanh", True),
+    (20000, 128, 128, 4, 150000, "sum", "tanh", False),
+    (400, 64, 32, 2, 2500, "sum", "leaky_relu", False),
+    (700, 256, 256, 3, 5000, "sqrt_n", "elu", True),
+    (500, 36, 20, 2, 3000, "sum", "selu", True),
+])
+def test_rgcn_backward_matches_autograd_reference(V, D, H, L, E, agg, act, normalize):
+    """gradients w.r.t. node states and per-type weights vs float64 autograd of the
+    reference op order (tf.GradientTape in the reference, graph_task_model.py:338-365)."""
+    _need_gpu()
+    from tf2_gnn_b200.layers import MessagePassingInput, RGCN
+    rng = np.random.default_rng(V + H)
+    adjs = random_graph(rng, V, L, E, hub=True, dups=True)
+    p = RGCN.get_default_hyperparameters()
+    p.update(hidden_dim=H, aggregation_function=agg, message_activation_function=act,
+             normalize_by_num_incoming=normalize)
+    h = rng.uniform(-1, 1, (V, D)).astype(np.float32)
+    Ws = [mo.glorot_uniform(rng, (D, H)) for _ in range(L)]
+    g = rng.uniform(-1, 1, (V, H)).astype(np.float32)
+    layer = make_layer("rgcn", p, D, L, {"edge_mlps": [[w] for w in Ws]})
+    for v in layer.variables:
+        v.requires_grad_()
+    ht = torch.from_numpy(h).cuda().requires_grad_()
+    out = layer(MessagePassingInput(ht, tuple(torch.from_numpy(a).cuda() for a in adjs)), training=True)
+    out.backward(torch.from_numpy(g).cuda())
+    # float64 reference
+    h64 = torch.from_numpy(h).double().requires_grad_()
+    W64 = [torch.from_numpy(w).double().requires_grad_() for w in Ws]
+    ref = _torch_reference_layer(h64, [torch.from_numpy(a) for a in adjs], W64, normalize, agg, act)
+    ref.backward(torch.from_numpy(g).double())
+    assert_states_close(out.detach().cpu().numpy(), ref.detach().numpy())
+    assert_states_close(ht.grad.cpu().numpy(), h64.grad.numpy(), tol=2e-5)
+    for var, w64 in zip(layer.variables, W64):
+        assert_states_close(var.grad.cpu().numpy(), w64.grad.numpy(), tol=2e-5)
+
+
 # ------------------------------------------------------------------------------------------
 # Node-level dense and error behaviour
 # ------------------------------------------------------------------------------------------

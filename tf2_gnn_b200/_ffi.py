@@ -21,11 +21,12 @@ ACT = {None: 0, "relu": 1, "tanh": 2, "leaky_relu": 3, "elu": 4, "selu": 5, "gel
 FLAG_NORMALIZE, FLAG_ACT_BEFORE_AGG, FLAG_USE_TARGET = 1, 2, 4
 PATH = {"auto": 0, "atomic": 1, "sorted": 2, "sorted_tc": 3, "fused_tc": 4}
 PREPARE_VALIDATE = 1
+PREPARE_TRANSPOSE = 2
 MAX_EDGE_TYPES = 32
 
 EXPORTED_SYMBOLS = (
     "tfgnn_b200_abi_version", "tfgnn_b200_last_error", "tfgnn_b200_prepare", "tfgnn_b200_prepare_sharded", "tfgnn_b200_free_batch",
-    "tfgnn_b200_batch_info", "tfgnn_b200_batch_export_csr", "tfgnn_b200_in_degree", "tfgnn_b200_edge_mlp_fwd", "tfgnn_b200_rgcn_fwd",
+    "tfgnn_b200_batch_info", "tfgnn_b200_batch_export_csr", "tfgnn_b200_in_degree", "tfgnn_b200_edge_mlp_fwd", "tfgnn_b200_rgcn_fwd", "tfgnn_b200_rgcn_bwd",
     "tfgnn_b200_ggnn_fwd", "tfgnn_b200_rgin_fwd", "tfgnn_b200_film_fwd", "tfgnn_b200_rgat_fwd",
     "tfgnn_b200_dense_fwd", "tfgnn_b200_gather_rows", "tfgnn_b200_unsorted_segment_reduce",
     "tfgnn_b200_activation", "tfgnn_b200_residual_average", "tfgnn_b200_layer_norm",
@@ -64,6 +65,8 @@ def lib() -> ctypes.CDLL:
                                           c_int32, c_int32, c_void_p, c_void_p]
     L.tfgnn_b200_rgcn_fwd.argtypes = [c_void_p, c_void_p, c_int32, _PP, c_int32, c_uint32, c_int32, c_int32,
                                       c_int32, c_void_p, c_void_p]
+    L.tfgnn_b200_rgcn_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, _PP, c_int32, c_uint32, c_int32, c_int32,
+                                      c_void_p, c_void_p, c_void_p, _PP, c_void_p]
     L.tfgnn_b200_ggnn_fwd.argtypes = [c_void_p, c_void_p, c_int32, _PP, c_int32, c_int32, c_uint32, c_int32,
                                       c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]
     L.tfgnn_b200_rgin_fwd.argtypes = [c_void_p, c_void_p, c_int32, _PP, c_int32, c_int32, c_uint32, c_int32,

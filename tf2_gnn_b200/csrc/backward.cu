@@ -1,0 +1,267 @@
+// Backward pass of the RGCN-style layer: the reference differentiates through the layer
+// with tf.GradientTape (tf2_gnn/models/graph_task_model.py:338-365); here the gradients of
+//     out = act( rn(v) * sum_l A_l W_l ),   A_l[v] = s_{v,l} * sum_{(u,v) in A_l} h_u,   s = 1/(c_{v,l}+eps) or 1
+// are computed with the same building blocks as the forward pass:
+//   dZ      = dOut * act'(out) * rn(v)                        (elementwise, from the saved OUTPUT)
+//   dW_l    = A_l^T dZ                                        (A recomputed by the CSR reduce; TN GEMM, reduction
+//                                                              over the V nodes in fixed chunks -> deterministic)
+//   dA      = dZ [W_0;..;W_{L-1}]^T, then dA_l[v] *= s_{v,l}   (3xTF32 tcgen05 GEMM + row/type scale)
+//   dh[u]   = sum_l sum_{(u,v) in A_l} dA_l[v]                (CSR reduce over the SOURCE-keyed CSR: no atomics)
+// Supported: 0 hidden layers, source state only, sum / mean / sqrt_n aggregation, activation after the
+// aggregation, activations whose derivative is a function of the output (none, relu, tanh, leaky_relu, elu, selu).
+#include "layers.cuh"
+
+namespace tfgnn {
+
+__device__ __forceinline__ float act_grad_from_output(float y, int act) {
+  switch (act) {
+    case TFGNN_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case TFGNN_ACT_TANH: return 1.f - y * y;
+    case TFGNN_ACT_LEAKY_RELU: return y > 0.f ? 1.f : kLeakyReluAlpha;
+    case TFGNN_ACT_ELU: return y > 0.f ? 1.f : y + 1.f;                               // d/dx (e^x - 1) = y + 1
+    case TFGNN_ACT_SELU: return y > 0.f ? kSeluScale : y + kSeluScale * kSeluAlpha;   // scale*alpha*e^x = y + scale*alpha
+    default: return 1.f;
+  }
+}
+
+__global__ void act_grad_kernel(const float* __restrict__ g, const float* __restrict__ out, long long V, int H,
+                                int act, const int* __restrict__ row_ptr, int L, int row_norm,
+                                float* __restrict__ dz) {
+  const long long total = V * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i / H;
+    float s = 1.f;
+    if (row_norm) {
+      int cnt = 0;
+      for (int l = 0; l < L; ++l) cnt += row_ptr[(long long)l * V + v + 1] - row_ptr[(long long)l * V + v];
+      const float n = (float)max(cnt, 1);
+      s = 1.f / (row_norm == 1 ? n : sqrtf(n));
+    }
+    dz[i] = g[i] * act_grad_from_output(out[i], act) * s;
+  }
+}
+
+// dA[v, l*D + c] *= 1/(c_{v,l}+eps)
+__global__ void scale_by_type_kernel(float* __restrict__ dA, long long V, int L, int D,
+                                     const int* __restrict__ row_ptr) {
+  const long long total = V * L * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i / ((long long)L * D);
+    const int l = (int)((i / D) % L);
+    const long long seg = (long long)l * V + v;
+    dA[i] *= 1.0f / ((float)(row_ptr[seg + 1] - row_ptr[seg]) + kSmallNumber);
+  }
+}
+
+// WcatT[hh, l*D + d] = W_l[d, hh]   (operand of dA = dZ Wcat^T)
+__global__ void pack_transposed_kernel(PtrTable W, int L, int D, int H, float* __restrict__ out) {
+  const long long total = (long long)L * D * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % ((long long)L * D));
+    const int hh = (int)(i / ((long long)L * D));
+    const int l = col / D, d = col - l * D;
+    out[i] = reinterpret_cast<const float*>(W.p[l])[(long long)d * H + hh];
+  }
+}
+
+// TN GEMM with the reduction over the (huge) node dimension: Cpart[chunk][k][n] = sum_{m in chunk} A[m,k] B[m,n].
+// 128x128 output tile, 256 threads, 8x8 per thread; both operands are read row-wise (row m contiguous), so no
+// transposition is needed in shared memory.  fp32 FFMA (deterministic; a tcgen05 version is future work).
+constexpr int kTnTile = 128, kTnMB = 16, kTnChunk = 8192;
+
+__global__ void __launch_bounds__(256, 2)
+gemm_tn_partial_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, long long M,
+                       int Kd, int N, float* __restrict__ Cpart) {
+  __shared__ __align__(16) float As[2][kTnMB][kTnTile];
+  __shared__ __align__(16) float Bs[2][kTnMB][kTnTile];
+  const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
+  const int k0 = blockIdx.x * kTnTile, n0 = blockIdx.y * kTnTile;
+  const long long m_begin = (long long)blockIdx.z * kTnChunk;
+  const long long m_end = m_begin + kTnChunk < M ? m_begin + kTnChunk : M;
+  const int lr = t >> 5, lc = (t & 31) * 4;     // load coordinates: rows lr, lr+8 ; 4 consecutive columns
+  float4 ra[2], rb[2];
+  auto load = [&](long long m0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const long long m = m0 + lr + 8 * i;
+      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+      if (m < m_end) {
+        const float* pa = A + m * lda + k0 + lc;
+        const float* pb = B + m * ldb + n0 + lc;
+        if (k0 + lc + 3 < Kd) va = __ldg(reinterpret_cast<const float4*>(pa));
+        else {
+          if (k0 + lc < Kd) va.x = pa[0];
+          if (k0 + lc + 1 < Kd) va.y = pa[1];
+          if (k0 + lc + 2 < Kd) va.z = pa[2];
+        }
+        if (n0 + lc + 3 < N) vb = __ldg(reinterpret_cast<const float4*>(pb));
+        else {
+          if (n0 + lc < N) vb.x = pb[0];
+          if (n0 + lc + 1 < N) vb.y = pb[1];
+          if (n0 + lc + 2 < N) vb.z = pb[2];
+        }
+      }
+      ra[i] = va;
+      rb[i] = vb;
+    }
+  };
+  auto store = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      *reinterpret_cast<float4*>(&As[buf][lr + 8 * i][lc]) = ra[i];
+      *reinterpret_cast<float4*>(&Bs[buf][lr + 8 * i][lc]) = rb[i];
+    }
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  load(m_begin);
+  store(0);
+  __syncthreads();
+  int buf = 0;
+  for (long long m0 = m_begin; m0 < m_end; m0 += kTnMB, buf ^= 1) {
+    if (m0 + kTnMB < m_end) load(m0 + kTnMB);
+#pragma unroll
+    for (int mm = 0; mm < kTnMB; ++mm) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][mm][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][mm][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][mm][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][mm][64 + tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (m0 + kTnMB < m_end) {
+      store(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  float* cp = Cpart + (long long)blockIdx.z * Kd * N;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int k = k0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (k >= Kd) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n < N) cp[(long long)k * N + n] = acc[i][j];
+    }
+  }
+}
+
+// dW_l[d, :] = sum over chunks of Cpart[chunk][l*D + d, :]   (fixed order: deterministic)
+__global__ void reduce_partials_kernel(const float* __restrict__ Cpart, int chunks, int L, int D, int N,
+                                       PtrTable dW) {
+  const long long total = (long long)L * D * N;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int c = 0; c < chunks; ++c) s += Cpart[(long long)c * total + i];
+    const int row = (int)(i / N), n = (int)(i - (long long)row * N);
+    const int l = row / D, d = row - l * D;
+    reinterpret_cast<float*>(const_cast<void*>(dW.p[l]))[(long long)d * N + n] = s;
+  }
+}
+
+static int grid_cap(long long n) {
+  int g = ceil_div(n, 256);
+  return g < 1 ? 1 : (g > 148 * 32 ? 148 * 32 : g);
+}
+
+}  // namespace tfgnn
+
+using namespace tfgnn;
+
+extern "C" int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* b, tfgnn_batch_t* bt, const float* h, int32_t D,
+                                   const float* const* W, int32_t H, uint32_t flags, int32_t aggregation,
+                                   int32_t activation, const float* out, const float* grad_out, float* grad_h,
+                                   float* const* grad_W, void* stream) {
+  TFGNN_REQUIRE(b != nullptr && bt != nullptr, "batch / transposed batch is NULL");
+  TFGNN_REQUIRE(D > 0 && H > 0, "D and H must be positive");
+  TFGNN_REQUIRE(valid_act(activation) && valid_agg(aggregation), "unknown activation / aggregation code");
+  const long long V = b->V;
+  const int L = b->L;
+  TFGNN_REQUIRE(bt->V == V && bt->L == L && b->V_src == V && bt->V_src == V,
+                "forward and transposed batches must describe the same (unsharded) graph");
+  if (flags & (TFGNN_FLAG_ACT_BEFORE_AGGREGATION | TFGNN_FLAG_USE_TARGET_STATE))
+    return unsupported("rgcn_bwd: activation-before-aggregation / target-state input are not built yet");
+  if (aggregation == TFGNN_AGG_MAX) return unsupported("rgcn_bwd: max aggregation is not built yet");
+  if (activation == TFGNN_ACT_GELU) return unsupported("rgcn_bwd: gelu needs the pre-activation (not saved)");
+  if (D % 4 != 0 || H % 4 != 0) return unsupported("rgcn_bwd needs D and H to be multiples of 4");
+  if (V == 0) return 0;
+  TFGNN_REQUIRE(h && out && grad_out, "NULL pointer");
+  TFGNN_REQUIRE(L == 0 || (W && grad_W), "weight / weight-gradient table is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool normalize = flags & TFGNN_FLAG_NORMALIZE_BY_NUM_INCOMING;
+  const int K = L * D;
+  if (L == 0) {
+    if (grad_h) TFGNN_CUDA(cudaMemsetAsync(grad_h, 0, (size_t)V * D * sizeof(float), st));
+    return 0;
+  }
+  PtrTable wt{}, gwt{};
+  for (int l = 0; l < L; ++l) {
+    TFGNN_REQUIRE(W[l] && grad_W[l], "a weight pointer is NULL");
+    wt.p[l] = W[l];
+    gwt.p[l] = grad_W[l];
+  }
+  void *dz = nullptr, *A = nullptr, *WT = nullptr, *part = nullptr;
+  int rc = batch_scratch(b, 8, (size_t)V * H * sizeof(float), &dz);
+  if (rc) return rc;
+  rc = batch_scratch(b, 2, (size_t)V * K * sizeof(float), &A);     // A (forward operand), then dA
+  if (rc) return rc;
+  rc = batch_scratch(b, 3, (size_t)K * H * sizeof(float), &WT);
+  if (rc) return rc;
+  const int chunks = (int)((V + kTnChunk - 1) / kTnChunk);
+  rc = batch_scratch(b, 9, (size_t)chunks * K * H * sizeof(float), &part);
+  if (rc) return rc;
+
+  // 1. dZ = dOut * act'(out) * rn(v)
+  act_grad_kernel<<<grid_cap(V * H), 256, 0, st>>>(grad_out, out, V, H, activation, b->row_ptr, L,
+                                                   agg_row_norm(aggregation), (float*)dz);
+  TFGNN_LAUNCH_CHECK();
+  // 2. A_l (recomputed, normalised) and dW = A^T dZ
+  {
+    EdgeReduceParams p;
+    p.X = h; p.ldx = D; p.x_type_stride = 0;
+    p.row_ptr = b->row_ptr; p.src = b->src_sorted;
+    p.out = (float*)A; p.ldo = K; p.out_type_stride = D;
+    p.V = (int)V; p.L = L; p.C = D; p.normalize = normalize;
+    rc = launch_edge_reduce(p, /*merged=*/false, st);
+    if (rc) return rc;
+    dim3 grid((K + kTnTile - 1) / kTnTile, (H + kTnTile - 1) / kTnTile, chunks);
+    gemm_tn_partial_kernel<<<grid, 256, 0, st>>>((const float*)A, K, (const float*)dz, H, V, K, H, (float*)part);
+    TFGNN_LAUNCH_CHECK();
+    reduce_partials_kernel<<<grid_cap((long long)K * H), 256, 0, st>>>((const float*)part, chunks, L, D, H, gwt);
+    TFGNN_LAUNCH_CHECK();
+  }
+  if (!grad_h) return 0;
+  // 3. dA = dZ Wcat^T (overwrites A), scaled per (v,l)
+  pack_transposed_kernel<<<grid_cap((long long)K * H), 256, 0, st>>>(wt, L, D, H, (float*)WT);
+  TFGNN_LAUNCH_CHECK();
+  GemmEpilogue none;
+  rc = node_gemm((const float*)dz, H, (const float*)WT, K, (float*)A, K, V, K, H, none, TFGNN_PATH_AUTO, b, 6, st);
+  if (rc) return rc;
+  if (normalize) {
+    scale_by_type_kernel<<<grid_cap(V * K), 256, 0, st>>>((float*)A, V, L, D, b->row_ptr);
+    TFGNN_LAUNCH_CHECK();
+  }
+  // 4. dh[u] = sum over the edges LEAVING u (source-keyed CSR), all types merged
+  {
+    EdgeReduceParams p;
+    p.X = (const float*)A; p.ldx = K; p.x_type_stride = D;
+    p.row_ptr = bt->row_ptr; p.src = bt->src_sorted;
+    p.out = grad_h; p.ldo = D;
+    p.V = (int)V; p.L = L; p.C = D;
+    rc = launch_edge_reduce(p, /*merged=*/true, st);
+    if (rc) return rc;
+  }
+  return 0;
+}

@@ -9,7 +9,7 @@
 namespace tfgnn {
 
 // ---- 1. histogram of targets per (type, node) -------------------------------------------
-__global__ void count_targets_kernel(PtrTable adj, CountTable E, int V, int V_src, int off,
+__global__ void count_targets_kernel(PtrTable adj, CountTable E, int V, int V_src, int off, int transpose,
                                      int* __restrict__ counts, int* __restrict__ invalid) {
   const int l = blockIdx.y;
   const long long n = E.n[l];
@@ -18,6 +18,7 @@ __global__ void count_targets_kernel(PtrTable adj, CountTable E, int V, int V_sr
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
     int2 st = __ldg(edges + e);
+    if (transpose) { const int t0 = st.x; st.x = st.y; st.y = t0; }     // CSR keyed by source (backward pass)
     if ((unsigned)st.x < (unsigned)V_src && (unsigned)st.y < (unsigned)V_src) {
       const unsigned t = (unsigned)(st.y - off);
       if (t < (unsigned)V) atomicAdd(counts + (long long)l * V + t, 1);   // else: another shard's target
@@ -107,7 +108,7 @@ __global__ void scan_apply_kernel(int* __restrict__ data, long long n, const int
 }
 
 // ---- 3. fill: sources into their (type,target) segment -------------------------------------
-__global__ void fill_sources_kernel(PtrTable adj, CountTable E, int V, int V_src, int off,
+__global__ void fill_sources_kernel(PtrTable adj, CountTable E, int V, int V_src, int off, int transpose,
                                     int* __restrict__ cursor, int* __restrict__ src_sorted) {
   const int l = blockIdx.y;
   const long long n = E.n[l];
@@ -115,6 +116,7 @@ __global__ void fill_sources_kernel(PtrTable adj, CountTable E, int V, int V_src
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
        e += (long long)gridDim.x * blockDim.x) {
     int2 st = __ldg(edges + e);
+    if (transpose) { const int t0 = st.x; st.x = st.y; st.y = t0; }
     if ((unsigned)st.x < (unsigned)V_src && (unsigned)st.y < (unsigned)V_src) {
       const unsigned t = (unsigned)(st.y - off);
       if (t < (unsigned)V) {
@@ -272,6 +274,7 @@ static int prepare_impl(const int32_t* const* adj, const int64_t* num_edges, int
   TFGNN_REQUIRE(M < (1ll << 31) - 1 && S < (1ll << 31) - 1,
                 "batch too large for int32 CSR (shard it across GPUs)");
   cudaStream_t st = (cudaStream_t)stream;
+  const int transpose = (prepare_flags & TFGNN_PREPARE_TRANSPOSE) ? 1 : 0;
 
   tfgnn_batch* b = new tfgnn_batch();
   b->V = V;
@@ -311,7 +314,7 @@ static int prepare_impl(const int32_t* const* adj, const int64_t* num_edges, int
     if (bx > 148 * 16) bx = 148 * 16;
     if (bx < 1) bx = 1;
     dim3 grid(bx, L);
-    count_targets_kernel<<<grid, 256, 0, st>>>(pt, ct, (int)V, (int)V_total, (int)tgt_begin, b->row_ptr,
+    count_targets_kernel<<<grid, 256, 0, st>>>(pt, ct, (int)V, (int)V_total, (int)tgt_begin, transpose, b->row_ptr,
                                                b->invalid_count);
     g_launch_count.fetch_add(1);
     TRY_CUDA(cudaGetLastError());
@@ -330,7 +333,7 @@ static int prepare_impl(const int32_t* const* adj, const int64_t* num_edges, int
     int bx = ceil_div(maxE, 256);
     if (bx > 148 * 16) bx = 148 * 16;
     dim3 grid(bx, L);
-    fill_sources_kernel<<<grid, 256, 0, st>>>(pt, ct, (int)V, (int)V_total, (int)tgt_begin, (int*)cursor,
+    fill_sources_kernel<<<grid, 256, 0, st>>>(pt, ct, (int)V, (int)V_total, (int)tgt_begin, transpose, (int*)cursor,
                                               b->src_sorted);
     g_launch_count.fetch_add(1);
     TRY_CUDA(cudaGetLastError());

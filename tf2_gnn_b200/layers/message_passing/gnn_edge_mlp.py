@@ -11,6 +11,37 @@ from .message_passing import (MessagePassing, MessagePassingInput, Variable, _la
                               register_message_passing_implementation)
 
 
+class _EdgeMLPLayerFunction(torch.autograd.Function):
+    """Autograd hook of the fused layer: forward = tfgnn_b200_edge_mlp_fwd, backward =
+    tfgnn_b200_rgcn_bwd.  The reference gets these gradients from tf.GradientTape
+    (models/graph_task_model.py:338-365)."""
+
+    @staticmethod
+    def forward(ctx, h, prepared, cfg, *weights):
+        out = torch.empty((prepared.num_nodes, cfg["H"]), dtype=torch.float32, device=h.device)
+        _ffi.check(_ffi.lib().tfgnn_b200_edge_mlp_fwd(
+            prepared.handle, h.data_ptr(), int(h.shape[1]), _ffi.ptr_array(weights), cfg["n_hidden"], cfg["H"],
+            cfg["flags"], cfg["agg"], cfg["act"], cfg["path"], out.data_ptr(), stream_ptr()))
+        ctx.prepared, ctx.cfg = prepared, cfg
+        ctx.save_for_backward(h, out, *weights)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        h, out, *weights = ctx.saved_tensors
+        cfg, prepared = ctx.cfg, ctx.prepared
+        if cfg["n_hidden"] != 0:
+            raise NotImplementedError("backward is built for edge MLPs without hidden layers (RGCN-style) only")
+        grad_out = grad_out.contiguous()
+        grad_h = torch.empty_like(h) if ctx.needs_input_grad[0] else None
+        grad_w = [torch.empty_like(w) for w in weights]
+        _ffi.check(_ffi.lib().tfgnn_b200_rgcn_bwd(
+            prepared.handle, prepared.transposed().handle, h.data_ptr(), int(h.shape[1]), _ffi.ptr_array(weights),
+            cfg["H"], cfg["flags"], cfg["agg"], cfg["act"], out.data_ptr(), grad_out.data_ptr(),
+            grad_h.data_ptr() if grad_h is not None else None, _ffi.ptr_array(grad_w), stream_ptr()))
+        return (grad_h, None, None, *grad_w)
+
+
 class EdgeMLP:
     """Weights of one dpu_utils.tf2utils.MLP(out_size=H, hidden_layers=n, use_biases=False):
     n hidden Dense(H, relu) + linear Dense(H) (gnn_edge_mlp.py:76-79)."""
@@ -84,8 +115,12 @@ class GNN_Edge_MLP(MessagePassing):
              prepared: Optional[PreparedBatch] = None):
         h, prepared = self._device_inputs(inputs, prepared)
         self._check_types(prepared)
+        ptrs, tensors = self._mlp_weight_ptrs()
+        if torch.is_grad_enabled() and (h.requires_grad or any(t.requires_grad for t in tensors)):
+            cfg = dict(H=self._hidden_dim, n_hidden=int(self._num_edge_MLP_hidden_layers), flags=self._flags(),
+                       agg=self._aggregation_fn.code, act=self._activation_fn.code, path=_ffi.PATH[self._path])
+            return _EdgeMLPLayerFunction.apply(h, prepared, cfg, *tensors)
         out = torch.empty((prepared.num_nodes, self._hidden_dim), dtype=torch.float32, device=h.device)
-        ptrs, _keep = self._mlp_weight_ptrs()
         _ffi.check(_ffi.lib().tfgnn_b200_edge_mlp_fwd(
             prepared.handle, h.data_ptr(), int(h.shape[1]), ptrs, int(self._num_edge_MLP_hidden_layers),
             self._hidden_dim, self._flags(), self._aggregation_fn.code, self._activation_fn.code,

@@ -54,10 +54,20 @@ class Variable:
         new = to_device_f32(new_value, self.value.device)
         if tuple(new.shape) != tuple(self.value.shape):
             raise ValueError(f"shape mismatch assigning {self.name}: {tuple(new.shape)} vs {tuple(self.value.shape)}")
-        self.value.copy_(new)
+        with torch.no_grad():
+            self.value.copy_(new)
 
     def numpy(self):
         return self.value.detach().cpu().numpy()
+
+    def requires_grad_(self, flag: bool = True) -> "Variable":
+        """Mark the weight as a leaf that accumulates .grad in the autograd-enabled (training) path."""
+        self.value.requires_grad_(flag)
+        return self
+
+    @property
+    def grad(self):
+        return self.value.grad
 
     def __repr__(self):
         return f"<Variable {self.name} shape={tuple(self.value.shape)}>"

@@ -69,7 +69,7 @@ class PreparedBatch:
     and shared by all layers (the adjacency is layer-invariant, gnn.py:278,301)."""
 
     def __init__(self, adjacency_lists: Sequence[torch.Tensor], num_nodes: int, validate: bool = False,
-                 target_range: Optional[Tuple[int, int]] = None):
+                 target_range: Optional[Tuple[int, int]] = None, transpose: bool = False):
         """target_range=(lo, hi): this batch is one rank's target-range shard of a graph with `num_nodes`
         nodes (sharding.py case 2); layer outputs then have hi-lo rows and `node_embeddings` passed to the
         layers must be the full [num_nodes, D] table."""
@@ -86,7 +86,9 @@ class PreparedBatch:
         counts = (c_int64 * max(self.num_edge_types, 1))(*self.num_edges)
         _ffi.check(_ffi.lib().tfgnn_b200_prepare_sharded(
             ptrs, counts, self.num_edge_types, self.num_source_nodes, self.target_range[0], self.num_nodes,
-            _ffi.PREPARE_VALIDATE if validate else 0, byref(self._handle), stream_ptr()))
+            (_ffi.PREPARE_VALIDATE if validate else 0) | (_ffi.PREPARE_TRANSPOSE if transpose else 0),
+            byref(self._handle), stream_ptr()))
+        self._transposed: Optional["PreparedBatch"] = None
         self._finalizer = weakref.finalize(self, PreparedBatch._free, self._handle.value)
 
     @staticmethod
@@ -100,6 +102,14 @@ class PreparedBatch:
     @property
     def handle(self) -> c_void_p:
         return self._handle
+
+    def transposed(self) -> "PreparedBatch":
+        """The same edges keyed by SOURCE (built lazily, once): the CSR of the backward pass."""
+        if self._transposed is None:
+            if self.target_range != (0, self.num_source_nodes):
+                raise NotImplementedError("backward through a target-range shard is not built yet")
+            self._transposed = PreparedBatch(self.adjacency_lists, self.num_source_nodes, transpose=True)
+        return self._transposed
 
     def in_degree(self) -> torch.Tensor:
         """float32 [L, V] — calculate_type_to_num_incoming_edges (message_passing.py:230-263)."""
