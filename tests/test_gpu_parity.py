@@ -240,6 +240,30 @@ def test_rgcn_fused_kernel(V, D, H, L, E, opts, agg):
     assert np.array_equal(a.cpu().numpy(), a2.cpu().numpy())   # bitwise reproducible
 
 
+@pytest.mark.parametrize("pair", ["0", "2"])
+@pytest.mark.parametrize("V,D,H,L,E,agg", [
+    (300, 32, 16, 2, 1500, "sum"),            # 3 tiles: the peer CTA of the last pair has no tile
+    (1000, 96, 48, 5, 4000, "mean"),
+    (5000, 256, 256, 4, 30000, "sum"),
+    (3000, 320, 320, 3, 20000, "sqrt_n"),     # two N passes, 80 weight rows per CTA
+    (25000, 64, 80, 2, 80000, "sum"),         # 196 tiles > SM count: pairs by the default rule as well
+])
+def test_rgcn_fused_kernel_cta_pairs(monkeypatch, pair, V, D, H, L, E, agg):
+    """cta_group::2 variant of the fused kernel (M = 256 over two SMs) against the single-CTA variant and the
+    fp32 CSR path; TFGNN_B200_FUSED_PAIR=2 forces pairs on graphs smaller than one tile per SM."""
+    _need_gpu()
+    monkeypatch.setenv("TFGNN_B200_FUSED_PAIR", pair)
+    rng = np.random.default_rng(V + D + H + 1)
+    adjs = random_graph(rng, V, L, E, hub=True, self_loops=True)
+    p = mo.default_hyperparameters("rgcn")
+    p.update(hidden_dim=H, aggregation_function=agg, message_activation_function="relu")
+    a = run_case("rgcn", p, V, D, L, adjs, seed=V, path="fused_tc")
+    b = run_case("rgcn", p, V, D, L, adjs, seed=V, path="sorted")
+    assert_states_close(a.cpu().numpy(), b.cpu().numpy().astype(np.float64), tol=1e-5)
+    a2 = run_case("rgcn", p, V, D, L, adjs, seed=V, path="fused_tc")
+    assert np.array_equal(a.cpu().numpy(), a2.cpu().numpy())
+
+
 def test_rgcn_atomic_path_matches():
     _need_gpu()
     rng = np.random.default_rng(5)

@@ -216,7 +216,7 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
       GemmEpilogue epi;
       epi.act = activation;
       epi.row_norm = row_norm; epi.row_ptr = b->row_ptr; epi.V = V; epi.L = L;
-      return launch_fused_rgcn(h, D, b->row_ptr, b->src_sorted, V, L, normalize, (const float*)packed, H,
+      return launch_fused_rgcn(h, D, b->row_ptr, b->src_sorted, b->M_in, V, L, normalize, (const float*)packed, H,
                                (float*)ring, out, ldo, epi, st);
     }
     if (pipelined) {

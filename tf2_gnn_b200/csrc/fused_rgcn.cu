@@ -15,9 +15,9 @@
 //
 // Warp roles (896 threads, by warpgroup so that setmaxnreg can move registers to the gather warps):
 //   WG0: 0 TMA, 1 MMA, 2-3 idle | WG1 (4-7): A splitters | WG2 (8-11): epilogue | WG3-6 (12-27): gather.
-// The gather is latency-bound on register-held loads (72 registers/thread cap at 896 threads), so each
-// gather warp also runs a rolling L2 prefetch window ahead of its loads: DRAM requests in flight are then
-// bounded by the memory system, not by registers.
+// The gather warps hold no row data in registers while it is in flight: each keeps a rolling ring of cp.async
+// copies into its own shared-memory slots (see GatherIssue), so DRAM requests in flight are bounded by the
+// shared memory left over by the GEMM pipeline (64 KB for 16 warps x 4 rows at D = 256), not by registers.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -38,6 +38,7 @@ constexpr int kFuAccStride = 256;
 constexpr int kFuSmemLimit = 227 * 1024;
 constexpr int kFuEpiPitch = 36;
 constexpr int kFuEpiBytes = 4 * 32 * kFuEpiPitch * 4;
+constexpr int kFuMaxQ = 8;                      // bulk row copies in flight per gather warp (upper bound)
 
 struct FusedParams {
   // graph
@@ -47,10 +48,10 @@ struct FusedParams {
   const int* src;
   int V, L, D;
   int normalize;
+  long long M;          // entries of src (bound for the 32-wide index block loads)
   int discard_ring;     // discard.global.L2 on consumed ring slots
-  int prefetch_warp;    // 1: a dedicated warp bulk-prefetches source rows into L2 a few row-waves ahead of the gather
-  int debug_skip;       // timing experiments only (results invalid), bit mask: 1 = no edge gathers, 2 = one K block per slot, 4 = no epilogue work
-  int prefetch_window;  // edges whose rows are L2-prefetched ahead of the register loads (0 = off)
+  int gather_q;         // bulk row copies each gather warp keeps in flight (= its shared-memory row slots)
+  int debug_skip;       // timing experiments only (results invalid), bit mask: 1 = no edge gathers, 2 = one K block per slot, 4 = no epilogue work, 8 = no weight-tile loads, 16 = no ring stores
   // ring
   float* ring;  // [grid * num_slots * 128, D]
   int num_slots;
@@ -74,93 +75,216 @@ __device__ __forceinline__ float fu_row_norm(const GemmEpilogue& e, long long ro
   return e.row_norm == 1 ? c : sqrtf(c);
 }
 
-// One warp reduces `nrows` CONSECUTIVE targets of edge type l: their CSR segments are contiguous, so the
-// warp loads the source ids of all of them with coalesced loads and walks the edges in one flat loop with U
-// row loads in flight per lane (the dependent row_ptr -> index chain is paid once per 8 rows, not per row).
-// h rows are read with L2 evict_first (each row is used once per incoming edge, no reuse window); the ring
-// rows are written with L2 evict_last so that they are still resident when the TMA reads them back.
-template <int NV, int U>
-__device__ __forceinline__ void gather_rows_batch(const FusedParams& p, int l, int v0, int nrows, int lane,
-                                                  float* dst, uint64_t pol_stream, uint64_t pol_keep,
-                                                  volatile uint32_t* progress) {
-  const int C4 = p.D >> 2;
-  const int rp = lane <= nrows ? __ldg(p.row_ptr + (long long)l * p.V + v0 + lane) : 0;
-  const int e_begin = __shfl_sync(0xffffffffu, rp, 0);
-  const int e_end = (p.debug_skip & 1) ? e_begin : __shfl_sync(0xffffffffu, rp, nrows);
-  int row = 0;
-  int seg_end = __shfl_sync(0xffffffffu, rp, 1);
+// ---- gather warps: rolling cp.async ring ---------------------------------------------------------------------
+// Each gather warp owns 8 consecutive targets of every tile and walks their CSR segments, one edge type after
+// the other ("calls": (tile, type) -> one contiguous edge range).  Source rows do not wait in registers: the warp
+// keeps Q rows in flight AT ALL TIMES as cp.async (LDGSTS) copies into its own Q shared-memory row slots - every
+// lane copies and later reads back only its own 16-byte columns, one commit group per row, so
+// `cp.async.wait_group Q-1` means "the oldest row has landed" and no mbarrier or warp barrier is needed.  When a
+// row has been added to the register accumulator its slot is refilled at once with the row Q edges ahead, across
+// segment, call and tile boundaries: the issue cursor and the consume cursor walk the same edge sequence
+// independently, so the pipeline never drains.  tools/gather_ceiling.cu: 16 warps x 4 slots (64 KB of shared
+// memory at D = 256) read 1 KB random rows at 7.4 TB/s, 16 warps x 4 register-held rows at 5.3 TB/s.
+// Summation order inside a segment is ascending CSR order, as in the unfused path.
+struct GatherIssue {
+  const int* row_ptr;
+  const int* src;
+  const float* h;        // + 4 * lane: this lane's first 16-byte column
+  long long M;
+  int V, L, ldh, skip, C4;
+  int lane, gw, Q, ncalls;
+  long long unit0, unit_step;
+  int ctas, rank;
+  uint32_t buf_s;        // shared-window address of this warp's slot 0, + 16 * lane
+  uint32_t row_bytes;
+  int ic;                // call being issued
+  int i_pos, i_end, in_blk, i_blk;
+  int rpA, rpB, rpC;     // row_ptr[v0 + lane] of calls ic, ic+1, ic+2 (prefetched: the loads are two calls old when used)
+  int ids, ids_next, ids0B;
+  uint32_t ibuf;         // slot the next row goes to
+  int islot;
+
+  __device__ __forceinline__ void call_rows(int n, int& l, int& v0, int& nr) const {
+    const int u = n / L;
+    l = n - u * L;
+    const long long tile = (unit0 + (long long)u * unit_step) * ctas + rank;
+    v0 = (int)(tile * kFuBM) + gw * (kFuBM / kFuGatherWarps);
+    nr = V - v0;
+    nr = nr < 0 ? 0 : (nr > kFuBM / kFuGatherWarps ? kFuBM / kFuGatherWarps : nr);
+  }
+  __device__ __forceinline__ int rp_of(int n) const {   // row_ptr of the call's rows, lane r -> first edge of row r
+    if (n >= ncalls) return 0;
+    int l, v0, nr;
+    call_rows(n, l, v0, nr);
+    if (nr == 0) return 0;
+    const int* base = row_ptr + (long long)l * V + v0;
+    return __ldg(base + (skip ? 0 : (lane <= nr ? lane : nr)));
+  }
+  __device__ __forceinline__ int nrows_of(int n) const {
+    int l, v0, nr;
+    call_rows(n, l, v0, nr);
+    return nr;
+  }
+  __device__ __forceinline__ int load_ids(int first) const {
+    const long long i = (long long)first + lane;
+    return i < M ? __ldg(src + i) : 0;
+  }
+  __device__ __forceinline__ void next_call() {
+    ++ic;
+    rpA = rpB;
+    rpB = rpC;
+    rpC = rp_of(ic + 2);
+    i_pos = __shfl_sync(0xffffffffu, rpA, 0);
+    i_end = __shfl_sync(0xffffffffu, rpA, nrows_of(ic));
+    ids = ids0B;
+    in_blk = 0;
+    i_blk = i_pos;
+    ids_next = load_ids(i_blk + 32);
+    ids0B = load_ids(__shfl_sync(0xffffffffu, rpB, 0));
+  }
+  // one commit group per call of issue(): the next edge's row if there is one, else an empty group (only after
+  // the last edge of the last call, so groups and consumed rows stay in step)
+  template <int NV>
+  __device__ __forceinline__ void issue() {
+    while (i_pos == i_end && ic + 1 < ncalls) next_call();
+    if (i_pos < i_end) {
+      if (in_blk == 32) {
+        in_blk = 0;
+        i_blk += 32;
+        ids = ids_next;
+        ids_next = load_ids(i_blk + 32);
+      }
+      const int s = __shfl_sync(0xffffffffu, ids, in_blk);
+      const float* rowp = h + (long long)s * ldh;
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (lane + 32 * j < C4) ptx::cp_async16(ibuf + 512u * j, rowp + 128 * j);
+      ++in_blk;
+      ++i_pos;
+    }
+    ptx::cp_async_commit();
+    if (++islot == Q) {
+      islot = 0;
+      ibuf = buf_s;
+    } else {
+      ibuf += row_bytes;
+    }
+  }
+};
+
+__device__ __forceinline__ void cp_async_wait_oldest(int Q) {   // at most Q-1 groups stay pending
+  switch (Q) {
+    case 1: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 6: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    case 7: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void gather_warp_main(const FusedParams& p, int lane, int gw, int Q, uint8_t* bufs,
+                                                 long long unit0, long long unit_step, long long total_units,
+                                                 int ctas, int rank, int ring_row0, uint64_t* slot_ready,
+                                                 uint64_t* slot_free) {
+  constexpr int kRowsPerWarp = kFuBM / kFuGatherWarps;
+  const int D = p.D, C4 = p.D >> 2, normalize = p.normalize;
+  const bool no_store = p.debug_skip & 16;   // timing experiment: gathered rows are not written to the ring
+  const int kFuSlots = p.num_slots;
+  float* const ring = p.ring;
+  const uint64_t pol_keep = ptx::policy_evict_last();
+  const long long my_units = unit0 < total_units ? (total_units - unit0 + unit_step - 1) / unit_step : 0;
+  GatherIssue g;
+  g.row_ptr = p.row_ptr; g.src = p.src; g.h = p.h + 4 * lane; g.M = p.M; g.V = p.V; g.L = p.L; g.ldh = p.ldh;
+  g.skip = p.debug_skip & 1; g.C4 = C4;
+  g.lane = lane; g.gw = gw; g.Q = Q; g.ncalls = (int)(my_units * p.L);
+  g.unit0 = unit0; g.unit_step = unit_step; g.ctas = ctas; g.rank = rank;
+  g.buf_s = ptx::smem_u32(bufs) + (uint32_t)lane * 16u;
+  g.row_bytes = (uint32_t)p.D * 4;
+  g.ic = 0; g.islot = 0; g.in_blk = 0; g.ibuf = g.buf_s;
+  g.rpA = g.rp_of(0); g.rpB = g.rp_of(1); g.rpC = g.rp_of(2);
+  g.i_pos = __shfl_sync(0xffffffffu, g.rpA, 0);
+  g.i_end = __shfl_sync(0xffffffffu, g.rpA, g.nrows_of(0));
+  g.i_blk = g.i_pos;
+  g.ids = g.load_ids(g.i_blk);
+  g.ids_next = g.load_ids(g.i_blk + 32);
+  g.ids0B = g.load_ids(__shfl_sync(0xffffffffu, g.rpB, 0));
+  // consume side: its own row_ptr registers (the issue side may already be several calls ahead after the fill)
+  int crp = g.rpA, crp_next = g.rpB;
+  int cslot = 0;
+  uint32_t cbuf = g.buf_s;
+  for (int i = 0; i < Q; ++i) g.template issue<NV>();   // fill the ring
+
   float4 acc[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  auto flush = [&](int r) {
-    const int cnt = __shfl_sync(0xffffffffu, rp, r + 1) - __shfl_sync(0xffffffffu, rp, r);
-    const float scale = p.normalize ? 1.0f / ((float)cnt + kSmallNumber) : 1.0f;
-    float* d = dst + (size_t)r * p.D;
+  for (int cc = 0; cc < g.ncalls; ++cc) {
+    int l, v0, nrows;
+    g.call_rows(cc, l, v0, nrows);
+    const int rp = crp;
+    crp = crp_next;
+    crp_next = g.rp_of(cc + 2);
+    const int slot = cc % kFuSlots;
+    ptx::mbar_wait(&slot_free[slot], ((cc / kFuSlots) & 1) ^ 1);
+    float* dst = ring + ((size_t)ring_row0 + (size_t)slot * kFuBM + (size_t)gw * kRowsPerWarp) * D + 4 * lane;
+    int row = 0;
+    int seg_begin = __shfl_sync(0xffffffffu, rp, 0);
+    int seg_end = __shfl_sync(0xffffffffu, rp, 1);
+    const int e_end = __shfl_sync(0xffffffffu, rp, nrows);
+    auto flush = [&]() {   // closes row `row`
+      const float scale = normalize ? 1.0f / ((float)(seg_end - seg_begin) + kSmallNumber) : 1.0f;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      const int c4 = lane + 32 * j;
-      if (c4 < C4)
-        ptx::st_f4_hint(d + 4 * c4,
-                        make_float4(acc[j].x * scale, acc[j].y * scale, acc[j].z * scale, acc[j].w * scale),
-                        pol_keep);
-      acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    if (lane == 0) atomicAdd(const_cast<uint32_t*>(progress), 1u);
-  };
-
-  for (int base = e_begin; base < e_end; base += 32) {
-    const int n = min(32, e_end - base);
-    const int my_src = lane < n ? __ldg(p.src + base + lane) : 0;
-    const uint32_t row_bytes = (uint32_t)p.D * 4;
-    // prime the L2 prefetch window: ONE bulk request per source row (cp.async.bulk.prefetch.L2)
-    if (lane < min(n, p.prefetch_window)) ptx::bulk_prefetch_l2(p.h + (long long)my_src * p.ldh, row_bytes);
-    for (int j0 = 0; j0 < n; j0 += U) {
-      {
-        // roll the window: rows of edges [j0 + W, j0 + W + U)
-        const int w0 = j0 + p.prefetch_window;
-        if (p.prefetch_window > 0 && lane >= w0 && lane < min(n, w0 + U))
-          ptx::bulk_prefetch_l2(p.h + (long long)my_src * p.ldh, row_bytes);
+      for (int j = 0; j < NV; ++j) {
+        if (lane + 32 * j < C4 && !no_store)
+          ptx::st_f4_hint(dst + 128 * j,
+                          make_float4(acc[j].x * scale, acc[j].y * scale, acc[j].z * scale, acc[j].w * scale),
+                          pol_keep);
+        acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      float4 r[U][NV];
+      dst += D;
+      ++row;
+      seg_begin = seg_end;
+      seg_end = __shfl_sync(0xffffffffu, rp, row + 1);
+    };
+    for (int e = seg_begin; e < e_end; ++e) {
+      while (e >= seg_end) flush();   // warp-uniform: close finished (possibly empty) segments
+      cp_async_wait_oldest(Q);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int s = __shfl_sync(0xffffffffu, my_src, (j0 + u) & 31);
-        const float* rowp = p.h + (long long)s * p.ldh;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          const int c4 = lane + 32 * j;
-          r[u][j] = (j0 + u < n && c4 < C4) ? ptx::ld_nc_f4_hint(rowp + 4 * c4, pol_stream)
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < NV; ++j) {
+        if (lane + 32 * j < C4) {
+          const float4 x = ptx::lds_f4(cbuf + 512u * j);
+          acc[j].x += x.x; acc[j].y += x.y; acc[j].z += x.z; acc[j].w += x.w;
         }
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (j0 + u < n) {
-          const int e = base + j0 + u;
-          while (e >= seg_end) {   // warp-uniform: close finished (possibly empty) segments
-            flush(row);
-            ++row;
-            seg_end = __shfl_sync(0xffffffffu, rp, row + 1);
-          }
-#pragma unroll
-          for (int j = 0; j < NV; ++j) {
-            acc[j].x += r[u][j].x; acc[j].y += r[u][j].y; acc[j].z += r[u][j].z; acc[j].w += r[u][j].w;
-          }
-        }
+      if (++cslot == Q) {
+        cslot = 0;
+        cbuf = g.buf_s;
+      } else {
+        cbuf += g.row_bytes;
       }
+      g.template issue<NV>();   // refill the slot just read (same lane, same bytes: no cross-lane hazard)
     }
+    while (row < nrows) flush();
+    // generic-proxy global writes -> visible to the TMA (async proxy) reads of this CTA
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&slot_ready[slot]);
   }
-  while (row < nrows) {
-    flush(row);
-    ++row;
-  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // BK = floats per K block: 32 (128 B rows, SWIZZLE_128B) or 16 (64 B rows, SWIZZLE_64B).  The smaller block
 // halves the bytes per pipeline stage, so twice as many stages fit: under the gather's L2 traffic a TMA round
 // trip takes ~3 us, and it is bytes-in-flight / latency that bounds the operand feed of the tensor core.
-template <int NV, int BK>
+// CTAS = 2: the two CTAs of a cluster (one TPC) form a tcgen05 CTA pair.  Each CTA gathers and splits ITS 128
+// targets exactly as before, but the MMA is one cta_group::2 instruction of M = 256 issued by the leader (rank 0):
+// every CTA stages only HALF of the weight tile's N rows, so the weight stream from L2 (the largest on-chip
+// traffic of the kernel: 2 MB per 128 targets at H = 256) and its shared-memory footprint are halved.
+template <int NV, int BK, int CTAS>
 __global__ void __launch_bounds__(kFuThreads, 1)
 fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const FusedParams p) {
@@ -170,7 +294,8 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   constexpr int kRowBytes = BK * 4;
   constexpr int kFuATileBytes = kFuBM * kRowBytes;
   const int S = p.num_stages;
-  const int b_tile_bytes = p.block_n * kRowBytes;
+  const int b_rows = p.block_n / CTAS;               // N rows of the weight tile staged by this CTA
+  const int b_tile_bytes = b_rows * kRowBytes;
   const int stage_bytes = 2 * kFuATileBytes + 2 * b_tile_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
   uint64_t* full = bars;
@@ -181,27 +306,30 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   uint64_t* slot_ready = bars + 3 * S + 4;
   uint64_t* slot_free = bars + 3 * S + 4 + kFuMaxSlots;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4 + 2 * kFuMaxSlots);
-  volatile uint32_t* progress = tmem_slot + 1;   // rows finished by the gather warps (paces the prefetch warp)
   float* epi_stage = reinterpret_cast<float*>(bars + ((3 * S + 4 + 2 * kFuMaxSlots + 2 + 1) & ~1));
+  uint8_t* gbuf = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(reinterpret_cast<uint8_t*>(epi_stage) + kFuEpiBytes) + 127) & ~uintptr_t(127));  // [16 * Q] rows
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long total_tiles = p.m_tiles;      // one tile = 128 targets; the N dimension is covered in n_pass passes
+  const uint32_t rank = CTAS == 2 ? ptx::cluster_ctarank() : 0u;
+  // one unit = CTAS consecutive 128-target tiles (one per CTA of the pair); the N dimension is covered in n_pass passes
+  const long long total_units = (p.m_tiles + CTAS - 1) / CTAS;
+  const long long unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;
   const int n_pass = p.n_tiles;
   const int kFuSlots = p.num_slots;
   const int kb_per_tile = p.L * p.kb_per_type;
 
   if (warp == 0 && lane == 0) {
-    tmem_slot[1] = 0;
     ptx::prefetch_tensormap(&map_a);
     ptx::prefetch_tensormap(&map_b);
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&split[s], 128);
+      ptx::mbar_init(&split[s], 4 * CTAS);      // one arrival per splitter warp (of both CTAs of a pair)
       ptx::mbar_init(&empty[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 128);
+      ptx::mbar_init(&tmem_empty[a], 4 * CTAS);  // one arrival per epilogue warp
     }
     for (int r = 0; r < kFuMaxSlots; ++r) {
       ptx::mbar_init(&slot_ready[r], kFuGatherWarps);
@@ -209,13 +337,27 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     ptx::fence_barrier_init();
   }
+  if (CTAS == 2) {
+    // both CTAs' barriers must exist before any remote arrive / multicast commit can land on them
+    __syncthreads();
+    ptx::cluster_sync_all();
+  }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, kFuTmemCols);
-    ptx::tmem_relinquish();
+    if (CTAS == 2) {
+      ptx::tmem_alloc_pair(tmem_slot, kFuTmemCols);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(tmem_slot, kFuTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (CTAS == 2) ptx::cluster_sync_all();   // both halves of the pair's TMEM are allocated before the first MMA
   ptx::tc_fence_after_sync();
+  // the leader's barriers that collect arrivals from both CTAs (split[], tmem_empty[])
+  const uint32_t split_remote0 = CTAS == 2 ? ptx::mapa_shared(ptx::smem_u32(&split[0]), 0) : 0u;
+  const uint32_t tmem_empty_remote0 = CTAS == 2 ? ptx::mapa_shared(ptx::smem_u32(&tmem_empty[0]), 0) : 0u;
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t n_acc = p.block_n <= 128 ? 2 : 1;
   const uint32_t corr_off = p.block_n <= 128 ? 128 : 256;
@@ -229,9 +371,9 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     if (lane == 0) {
       uint32_t it = 0, slot_it = 0;
       const uint64_t pol_keep = ptx::policy_evict_last();   // ring slots and the 2 MB of weights stay in L2
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, slot_it += p.L) {
+      for (long long unit = unit0; unit < total_units; unit += unit_step, slot_it += p.L) {
        for (int pass = 0; pass < n_pass; ++pass) {
-        const int n0 = pass * p.block_n;
+        const int n0 = pass * p.block_n + (int)rank * b_rows;
         for (int l = 0; l < p.L; ++l) {
           const uint32_t sq = slot_it + l;
           const int slot = sq % kFuSlots;
@@ -241,22 +383,25 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const uint32_t ph = (it / S) & 1;
             ptx::mbar_wait(&empty[s], ph ^ 1);
             uint8_t* st = smem + (size_t)s * stage_bytes;
-            ptx::mbar_arrive_expect_tx(&full[s], kFuATileBytes + 2 * b_tile_bytes);
+            const bool skip_b = p.debug_skip & 8;   // timing experiment: no weight stream (results invalid)
+            ptx::mbar_arrive_expect_tx(&full[s], kFuATileBytes + (skip_b ? 0 : 2 * b_tile_bytes));
             ptx::tma_load_2d_hint(st, &map_a, &full[s], kb * kFuBK, ring_row0 + slot * kFuBM, pol_keep);
             const int kcol = (l * p.kb_per_type + kb) * kFuBK;
-            ptx::tma_load_2d_hint(st + 2 * kFuATileBytes, &map_b, &full[s], kcol, n0, pol_keep);
-            ptx::tma_load_2d_hint(st + 2 * kFuATileBytes + b_tile_bytes, &map_b, &full[s], kcol, p.N + n0, pol_keep);
+            if (!skip_b) {
+              ptx::tma_load_2d_hint(st + 2 * kFuATileBytes, &map_b, &full[s], kcol, n0, pol_keep);
+              ptx::tma_load_2d_hint(st + 2 * kFuATileBytes + b_tile_bytes, &map_b, &full[s], kcol, p.N + n0, pol_keep);
+            }
           }
         }
        }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    const uint32_t idesc = ptx::umma_idesc_tf32_m128((uint32_t)p.block_n);
+    // ================= MMA issuer (the leader CTA of a pair issues for both) =================
+    const uint32_t idesc = ptx::umma_idesc_tf32(128u * CTAS, (uint32_t)p.block_n);
     uint32_t it = 0, tile_count = 0;
-    for (long long tp = (long long)blockIdx.x * n_pass; tp < total_tiles * n_pass;
-         tp = (tp % n_pass == n_pass - 1) ? tp + (long long)(gridDim.x - 1) * n_pass + 1 : tp + 1, ++tile_count) {
+    for (long long tp = unit0 * n_pass; rank == 0 && tp < total_units * n_pass;
+         tp = (tp % n_pass == n_pass - 1) ? tp + (unit_step - 1) * n_pass + 1 : tp + 1, ++tile_count) {
       const uint32_t acc = tile_count % n_acc, acc_ph = (tile_count / n_acc) & 1;
       ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
       ptx::tc_fence_after_sync();
@@ -266,7 +411,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         ptx::mbar_wait(&full[s], ph);
-        ptx::mbar_wait(&split[s], ph);
+        ptx::mbar_wait(&split[s], ph);   // pair: arrivals of both CTAs' splitter warps = both operand halves staged
         ptx::tc_fence_after_sync();
         if (lane == 0) {
           const uint32_t st = ptx::smem_u32(smem + (size_t)s * stage_bytes);
@@ -277,63 +422,32 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #pragma unroll
           for (int k = 0; k < kFuBK / 8; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
-            ptx::mma_tf32_ss(c_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-            ptx::mma_tf32_ss(c_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-            ptx::mma_tf32_ss(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+            if (CTAS == 2) {
+              ptx::mma_tf32_ss_pair(c_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+              ptx::mma_tf32_ss_pair(c_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+              ptx::mma_tf32_ss_pair(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+            } else {
+              ptx::mma_tf32_ss(c_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+              ptx::mma_tf32_ss(c_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+              ptx::mma_tf32_ss(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+            }
           }
-          ptx::mma_commit(&empty[s]);
-          if (kb == kb_per_tile - 1) ptx::mma_commit(&tmem_full[acc]);
+          if (CTAS == 2) {
+            ptx::mma_commit_pair(&empty[s], 3);     // frees stage s in BOTH CTAs
+            if (kb == kb_per_tile - 1) ptx::mma_commit_pair(&tmem_full[acc], 3);
+          } else {
+            ptx::mma_commit(&empty[s]);
+            if (kb == kb_per_tile - 1) ptx::mma_commit(&tmem_full[acc]);
+          }
         }
         __syncwarp();
-      }
-    }
-  } else if ((warp == 2 || warp == 3) && p.prefetch_warp) {
-    // ================= L2 prefetch warps (the two otherwise idle warps of warpgroup 0) =================
-    // They walk the same (tile, edge type) sequence as the gather warps, a few "row waves" ahead (wave w = row w
-    // of each of the 16 gather warps' 8-row groups), and issue one bulk L2 prefetch per source row.  DRAM latency
-    // is then paid by requests that hold no registers; the gather's own loads mostly hit L2.
-    constexpr int kRowsPerWarpG = kFuBM / kFuGatherWarps;       // 8 rows per gather warp = 8 waves per slot
-    constexpr int kLeadRows = 3 * kFuGatherWarps;              // stay <= ~3 waves ahead of the finished rows
-    const uint32_t row_bytes = (uint32_t)p.D * 4;
-    const int pw = warp - 2;
-    uint32_t rows_base = 0;                                    // valid rows of all previous (tile, type) units
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (int)(tile * kFuBM);
-      const int valid_rows = min(kFuBM, p.V - m0);
-      auto wave_rows = [&](int w) {                             // valid rows in wave w: groups g with g*8 + w < valid
-        const int c = (valid_rows - w + kRowsPerWarpG - 1) / kRowsPerWarpG;
-        return c < 0 ? 0 : (c > kFuGatherWarps ? kFuGatherWarps : c);
-      };
-      for (int l = 0; l < p.L; ++l, rows_base += (uint32_t)valid_rows) {
-        for (int w0 = 2 * pw; w0 < kRowsPerWarpG; w0 += 4) {   // two waves (32 rows) per iteration, one row per lane
-          uint32_t before = rows_base;
-          for (int w = 0; w < w0; ++w) before += (uint32_t)wave_rows(w);
-          // pace against the rows the gather warps have finished (bounded: it is only a heuristic)
-          for (int spin = 0; spin < 100000 && (int)(before - *progress) > kLeadRows; ++spin) __nanosleep(100);
-          const int g = lane & 15, w = w0 + (lane >> 4);
-          const int r = g * kRowsPerWarpG + w;
-          int beg = 0, end = 0;
-          if (r < valid_rows) {
-            const long long seg = (long long)l * p.V + m0 + r;
-            beg = __ldg(p.row_ptr + seg);
-            end = __ldg(p.row_ptr + seg + 1);
-          }
-          for (int e = beg; e < end; e += 8) {
-            int ids[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) ids[q] = e + q < end ? __ldg(p.src + e + q) : -1;
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (ids[q] >= 0) ptx::bulk_prefetch_l2(p.h + (long long)ids[q] * p.ldh, row_bytes);
-          }
-        }
       }
     }
   } else if (warp >= 4 && warp < 8) {
     // ================= A splitters =================
     const int tid = threadIdx.x - 128;
     uint32_t it = 0, slot_base_it = 0;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, slot_base_it += p.L) {
+    for (long long unit = unit0; unit < total_units; unit += unit_step, slot_base_it += p.L) {
      for (int pass = 0; pass < n_pass; ++pass) {
       for (int l = 0; l < p.L; ++l) {
         const uint32_t slot_it = slot_base_it + l;
@@ -365,7 +479,11 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             lo[idx] = ll;
           }
           ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&split[s]);
+          __syncwarp();
+          if (lane == 0) {   // one (possibly remote) arrival per warp: remote mbarrier arrives are DSMEM round trips
+            if (CTAS == 2 && rank != 0) ptx::mbar_arrive_cluster(split_remote0 + (uint32_t)s * 8u);
+            else ptx::mbar_arrive(&split[s]);
+          }
         }
       }
      }
@@ -375,9 +493,9 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int q = warp & 3;
     uint32_t tile_count = 0;
     const uint64_t pol_stream = ptx::policy_evict_first();
-    for (long long tp = (long long)blockIdx.x * n_pass; tp < total_tiles * n_pass;
-         tp = (tp % n_pass == n_pass - 1) ? tp + (long long)(gridDim.x - 1) * n_pass + 1 : tp + 1, ++tile_count) {
-      const long long m0 = (tp / n_pass) * kFuBM;
+    for (long long tp = unit0 * n_pass; tp < total_units * n_pass;
+         tp = (tp % n_pass == n_pass - 1) ? tp + (unit_step - 1) * n_pass + 1 : tp + 1, ++tile_count) {
+      const long long m0 = ((tp / n_pass) * CTAS + rank) * kFuBM;
       const int n0 = (int)(tp % n_pass) * p.block_n;
       const uint32_t acc = tile_count % n_acc, acc_ph = (tile_count / n_acc) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_ph);
@@ -444,40 +562,26 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         __syncwarp();
       }
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&tmem_empty[acc]);
+      __syncwarp();
+      if (lane == 0) {
+        if (CTAS == 2 && rank != 0) ptx::mbar_arrive_cluster(tmem_empty_remote0 + acc * 8u);
+        else ptx::mbar_arrive(&tmem_empty[acc]);
+      }
     }
   } else if (warp >= kFuFirstGatherWarp) {
     // ================= gather warps =================
     const int gw = warp - kFuFirstGatherWarp;
-    constexpr int kRowsPerWarp = kFuBM / kFuGatherWarps;
-    constexpr int U = NV <= 1 ? 8 : (NV == 2 ? 4 : 2);
-    const uint64_t pol_stream = ptx::policy_evict_first();
-    const uint64_t pol_keep = ptx::policy_evict_last();
-    uint32_t slot_it = 0;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m0 = (int)(tile * kFuBM);
-      const int v0 = m0 + gw * kRowsPerWarp;
-      const int nrows = min(kRowsPerWarp, p.V - v0);   // <= 0 for warps past the last node
-      for (int l = 0; l < p.L; ++l, ++slot_it) {
-        const int slot = slot_it % kFuSlots;
-        ptx::mbar_wait(&slot_free[slot], ((slot_it / kFuSlots) & 1) ^ 1);
-        float* slot_base = p.ring + ((size_t)ring_row0 + (size_t)slot * kFuBM) * p.D;
-        if (nrows > 0)
-          gather_rows_batch<NV, U>(p, l, v0, nrows, lane, slot_base + (size_t)(gw * kRowsPerWarp) * p.D, pol_stream,
-                                   pol_keep, progress);
-        // generic-proxy global writes -> visible to the TMA (async proxy) reads of this CTA
-        asm volatile("fence.proxy.async.global;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&slot_ready[slot]);
-      }
-    }
+    gather_warp_main<NV>(p, lane, gw, p.gather_q, gbuf + (size_t)gw * p.gather_q * ((size_t)p.D * 4), unit0,
+                         unit_step, total_units, CTAS, (int)rank, ring_row0, slot_ready, slot_free);
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (CTAS == 2) ptx::cluster_sync_all();   // the leader's MMAs read the peer's shared memory: leave together
   if (warp == 1) {
     ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_base, kFuTmemCols);
+    if (CTAS == 2) ptx::tmem_dealloc_pair(tmem_base, kFuTmemCols);
+    else ptx::tmem_dealloc(tmem_base, kFuTmemCols);
   }
 }
 
@@ -518,8 +622,8 @@ size_t fused_rgcn_ring_bytes(int D, int L, int H) {
   return (size_t)kFuMaxGrid * fused_num_slots(L, H) * kFuBM * D * sizeof(float);
 }
 
-int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src, int V, int L, int normalize,
-                      const float* packedB, int H, float* ring, float* out, int ldo, const GemmEpilogue& epi,
+int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src, long long M, int V, int L,
+                      int normalize, const float* packedB, int H, float* ring, float* out, int ldo, const GemmEpilogue& epi,
                       cudaStream_t st) {
   EncodeTiledFn encode = fu_encode_fn();
   if (!encode) {
@@ -532,13 +636,9 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   FusedParams p{};
   p.h = h; p.ldh = D; p.row_ptr = row_ptr; p.src = src; p.V = V; p.L = L; p.D = D; p.normalize = normalize;
   p.ring = ring;
-  static const int pf_window = [] { const char* e = getenv("TFGNN_B200_PREFETCH_WINDOW"); return e ? atoi(e) : 32; }();
-  p.prefetch_window = pf_window < 0 ? 0 : (pf_window > 32 ? 32 : pf_window);
+  p.M = M;
   static const int discard_env = [] { const char* e = getenv("TFGNN_B200_RING_DISCARD"); return e ? atoi(e) : 1; }();
   p.discard_ring = discard_env;
-  static const int pfw_env = [] { const char* e = getenv("TFGNN_B200_PREFETCH_WARP"); return e ? atoi(e) : 0; }();  // measured: no gain over the in-gather window
-  p.prefetch_warp = pfw_env;
-  if (p.prefetch_warp) p.prefetch_window = 0;   // the dedicated warp replaces the in-gather prefetch window
   static const int dbg_env = [] { const char* e = getenv("TFGNN_B200_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
   p.debug_skip = dbg_env;
   p.N = H;
@@ -551,14 +651,32 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   const int kFuATileBytes = kFuBM * kFuBK * 4;
   p.kb_per_type = D / kFuBK;
   if (p.debug_skip & 2) p.kb_per_type = 1;
-  const int stage_bytes = 2 * kFuATileBytes + 2 * p.block_n * kFuBK * 4;
-  int stages = (kFuSmemLimit - 2048 - kFuEpiBytes) / stage_bytes;
-  if (stages > 6) stages = 6;
-  TFGNN_REQUIRE(stages >= 2, "fused RGCN: tile does not fit shared memory");
-  p.num_stages = stages;
   p.C = out; p.ldc = ldo; p.epi = epi;
   if (sms > kFuMaxGrid) sms = kFuMaxGrid;
-  const int grid = (int)(p.m_tiles < sms ? p.m_tiles : sms);
+  // CTA pairs (cta_group::2) when there is at least one 128-target tile per SM; tiny batches keep single CTAs
+  // TFGNN_B200_FUSED_PAIR: 0 = never, 1 = default rule, 2 = whenever there are two tiles (tests); read per call
+  const char* pair_str = getenv("TFGNN_B200_FUSED_PAIR");
+  const int pair_env = pair_str ? atoi(pair_str) : 1;
+  const bool pair_ok = (p.block_n / 2) % 8 == 0 && sms >= 2;
+  const int ctas = (pair_ok && ((pair_env == 1 && p.m_tiles >= sms) || (pair_env == 2 && p.m_tiles >= 2))) ? 2 : 1;
+  int grid = (int)(p.m_tiles < sms ? p.m_tiles : sms);
+  if (ctas == 2) grid &= ~1;
+  // shared memory: S pipeline stages + epilogue staging + Q row slots for each of the 16 gather warps.
+  // Q = 4 rolling copies per warp saturate HBM in isolation (tools/gather_ceiling.cu); the pipeline gets what is left.
+  const int stage_bytes = 2 * kFuATileBytes + 2 * (p.block_n / ctas) * kFuBK * 4;
+  static const int stage_env = [] { const char* e = getenv("TFGNN_B200_FUSED_STAGES"); return e ? atoi(e) : 0; }();
+  static const int q_env = [] { const char* e = getenv("TFGNN_B200_GATHER_Q"); return e ? atoi(e) : 0; }();
+  const int fixed_bytes = 2048 + kFuEpiBytes + kFuGatherWarps * kFuMaxQ * 8 + 128 + 1024;
+  const int row_bytes = D * 4;
+  int want_q = q_env >= 1 && q_env <= kFuMaxQ ? q_env : 4;
+  int stages = stage_env >= 2 ? stage_env : 3;   // measured on cfg2 (register gather): 3 stages 5.51 ms, 4: 5.83, 6: 5.88
+  auto q_for = [&](int s_) { return (kFuSmemLimit - fixed_bytes - s_ * stage_bytes) / (kFuGatherWarps * row_bytes); };
+  while (stages > 2 && q_for(stages) < want_q) --stages;
+  int q = q_for(stages);
+  if (q > want_q) q = want_q;
+  TFGNN_REQUIRE(q >= 1 && stages >= 2, "fused RGCN: tile does not fit shared memory");
+  p.num_stages = stages;
+  p.gather_q = q;
 
   const int Kp = L * D;
   CUtensorMap map_a, map_b;
@@ -579,7 +697,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   {
     cuuint64_t dims[2] = {(cuuint64_t)Kp, (cuuint64_t)(2 * H)};
     cuuint64_t strides[1] = {(cuuint64_t)Kp * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)kFuBK, (cuuint32_t)p.block_n};
+    cuuint32_t box[2] = {(cuuint32_t)kFuBK, (cuuint32_t)(p.block_n / ctas)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(packedB), dims, strides, box,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, kFuBK == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
@@ -590,7 +708,9 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
     }
   }
   const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4 + 2 * kFuMaxSlots + 4) * sizeof(uint64_t) +
-                            kFuEpiBytes + 1024;
+                            kFuEpiBytes + kFuGatherWarps * kFuMaxQ * 8 + 128 +
+                            (size_t)kFuGatherWarps * q * row_bytes + 1024;
+  TFGNN_REQUIRE(smem_bytes <= (size_t)kFuSmemLimit, "fused RGCN: shared memory budget exceeded");
   const int nv = (D + 127) / 128;
   // L2 set-aside for the evict_last (persisting) lines: the ring + the packed weights.  Without a carve-out
   // the evict_last hint is advisory only and the ring gets written back to HBM (measured: +4 GB/layer).
@@ -610,20 +730,32 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    cudaError_t e[8] = {
-        cudaFuncSetAttribute(fused_rgcn_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit),
-        cudaFuncSetAttribute(fused_rgcn_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit),
-        cudaFuncSetAttribute(fused_rgcn_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit),
-        cudaFuncSetAttribute(fused_rgcn_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit),
-        cudaFuncSetAttribute(fused_rgcn_kernel<1, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit),
-        cudaFuncSetAttribute(fused_rgcn_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit),
-        cudaFuncSetAttribute(fused_rgcn_kernel<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit),
-        cudaFuncSetAttribute(fused_rgcn_kernel<4, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit)};
-    for (cudaError_t x : e)
+    auto set = [&](const void* fn) {
+      cudaError_t x = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kFuSmemLimit);
       if (x != cudaSuccess) attr_err = x;
+    };
+#define TFGNN_FU_SET(NV) \
+    set((const void*)fused_rgcn_kernel<NV, 16, 1>); set((const void*)fused_rgcn_kernel<NV, 32, 1>); \
+    set((const void*)fused_rgcn_kernel<NV, 16, 2>); set((const void*)fused_rgcn_kernel<NV, 32, 2>);
+    TFGNN_FU_SET(1) TFGNN_FU_SET(2) TFGNN_FU_SET(3) TFGNN_FU_SET(4)
+#undef TFGNN_FU_SET
   });
   TFGNN_CUDA(attr_err);
-#define TFGNN_FU_LAUNCH(NV, BK) fused_rgcn_kernel<NV, BK><<<grid, kFuThreads, smem_bytes, st>>>(map_a, map_b, p)
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kFuThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)ctas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define TFGNN_FU_LAUNCH(NV, BK)                                                                             \
+  TFGNN_CUDA(ctas == 2 ? cudaLaunchKernelEx(&cfg, fused_rgcn_kernel<NV, BK, 2>, map_a, map_b, p)            \
+                       : cudaLaunchKernelEx(&cfg, fused_rgcn_kernel<NV, BK, 1>, map_a, map_b, p))
   if (kFuBK == 32) {
     switch (nv) {
       case 1: TFGNN_FU_LAUNCH(1, 32); break;

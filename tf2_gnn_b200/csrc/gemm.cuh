@@ -29,7 +29,7 @@ int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int 
 // Fused RGCN-style layer (fused_rgcn.cu): gather -> segment-sum -> 3xTF32 tcgen05 -> epilogue in one kernel.
 bool fused_rgcn_supported(long long V, int L, int D, int H, const float* h, const float* out, int ldo);
 size_t fused_rgcn_ring_bytes(int D, int L, int H);
-int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src, int V, int L, int normalize,
+int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src, long long M, int V, int L, int normalize,
                       const float* packedB, int H, float* ring, float* out, int ldo, const GemmEpilogue& epi,
                       cudaStream_t st);
 
