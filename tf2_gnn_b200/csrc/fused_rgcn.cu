@@ -669,7 +669,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   const int fixed_bytes = 2048 + kFuEpiBytes + kFuGatherWarps * kFuMaxQ * 8 + 128 + 1024;
   const int row_bytes = D * 4;
   int want_q = q_env >= 1 && q_env <= kFuMaxQ ? q_env : 4;
-  int stages = stage_env >= 2 ? stage_env : 3;   // measured on cfg2 (register gather): 3 stages 5.51 ms, 4: 5.83, 6: 5.88
+  int stages = stage_env >= 2 ? stage_env : 4;   // measured on cfg2 (CTA pairs, Q = 4): 4 stages 4.85 ms, 3 stages 4.96 ms
   auto q_for = [&](int s_) { return (kFuSmemLimit - fixed_bytes - s_ * stage_bytes) / (kFuGatherWarps * row_bytes); };
   while (stages > 2 && q_for(stages) < want_q) --stages;
   int q = q_for(stages);
