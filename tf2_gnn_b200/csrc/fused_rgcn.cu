@@ -3,18 +3,18 @@
 //
 //   out[v] = act( rn(v) * sum_l ( 1/(c_{v,l}+eps) * sum_{(u,v) in A_l} h_u ) W_l )       (rgcn.py:13-48)
 //
-// One CTA per SM owns 128-target tiles.  Inside the CTA, 16 GATHER warps produce, per edge type l, the
-// normalised row sums A_l[128, D] (full 4*D-byte row reads from HBM, register accumulation, no atomics)
-// into a small per-CTA ring in global memory that stays L2-resident (3 slots x 128 x D x 4 B per CTA,
-// 57 MB chip-wide at D=256: the fp32-accurate operand does not fit the 227 KB of shared memory).  The
-// TMA producer pulls each slot back in 128 B K-slices next to the pre-split weight tiles; splitter warps
-// cut A into tf32 hi/lo; one thread issues the tcgen05 MMAs into TMEM (main + correction accumulators,
-// double-buffered); epilogue warps drain TMEM through a staging tile to coalesced stores.  The gather
-// of slot i+1..i+3 overlaps the MMAs of slot i, so the kernel runs at the HBM rate of the gather and the
-// [V, L*D] intermediate never touches HBM.
+// One CTA per SM owns 128-target tiles; the two CTAs of a cluster (one TPC) form a tcgen05 CTA pair.  Inside the
+// CTA, 16 GATHER warps produce, per edge type l, the normalised row sums A_l[128, D] (full 4*D-byte row reads
+// from HBM through a rolling cp.async ring in shared memory, register accumulation, no atomics) into a small
+// per-CTA ring in global memory that stays L2-resident (4 slots x 128 x D x 4 B per CTA, 76 MB chip-wide at
+// D=256: the fp32-accurate operand does not fit the 227 KB of shared memory).  The TMA producer pulls each slot
+// back in 128 B K-slices next to this CTA's HALF of the pre-split weight tile; splitter warps cut A into tf32
+// hi/lo; the leader CTA's MMA thread issues cta_group::2 MMAs of M = 256 into both CTAs' TMEM (main + correction
+// accumulators); epilogue warps drain TMEM through a staging tile to coalesced stores.  The gather of the next
+// slots overlaps the MMAs of slot i, and the [V, L*D] intermediate never touches HBM.
 //
-// Warp roles (896 threads, by warpgroup so that setmaxnreg can move registers to the gather warps):
-//   WG0: 0 TMA, 1 MMA, 2-3 idle | WG1 (4-7): A splitters | WG2 (8-11): epilogue | WG3-6 (12-27): gather.
+// Warp roles (896 threads):
+//   0 TMA, 1 MMA, 2-3 idle | 4-7: A splitters | 8-11: epilogue | 12-27: gather.
 // The gather warps hold no row data in registers while it is in flight: each keeps a rolling ring of cp.async
 // copies into its own shared-memory slots (see GatherIssue), so DRAM requests in flight are bounded by the
 // shared memory left over by the GEMM pipeline (64 KB for 16 warps x 4 rows at D = 256), not by registers.
@@ -616,7 +616,7 @@ constexpr int kFuMaxGrid = 160;
 static int fused_num_slots(int L, int H) {
   static const int env_slots = [] { const char* e = getenv("TFGNN_B200_RING_SLOTS"); return e ? atoi(e) : 0; }();
   if (H > 256) return L + 1;
-  return (env_slots >= 2 && env_slots <= kFuMaxSlots) ? env_slots : 3;
+  return (env_slots >= 2 && env_slots <= kFuMaxSlots) ? env_slots : 4;   // cfg2: 4 slots 4.61 ms, 3: 4.63-4.88, 5: 4.70, 2: 5.05
 }
 size_t fused_rgcn_ring_bytes(int D, int L, int H) {
   return (size_t)kFuMaxGrid * fused_num_slots(L, H) * kFuBM * D * sizeof(float);
@@ -646,11 +646,9 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   p.block_n = H / p.n_tiles;
   p.num_slots = fused_num_slots(L, H);
   p.m_tiles = ((long long)V + kFuBM - 1) / kFuBM;
-  static const int bk_env = [] { const char* e = getenv("TFGNN_B200_FUSED_BK"); return e ? atoi(e) : 16; }();
-  const int kFuBK = bk_env == 32 ? 32 : 16;
-  const int kFuATileBytes = kFuBM * kFuBK * 4;
-  p.kb_per_type = D / kFuBK;
-  if (p.debug_skip & 2) p.kb_per_type = 1;
+  // K block: 32 floats (128 B rows, SWIZZLE_128B) since the CTA-pair kernel; measured on cfg2 4.63 ms vs 4.88 ms with
+  // 16 floats, H=320 6.47 vs 6.61 ms (half as many barrier round trips per byte; 2 stages of 64 KB still fit)
+  static const int bk_env = [] { const char* e = getenv("TFGNN_B200_FUSED_BK"); return e ? atoi(e) : 32; }();
   p.C = out; p.ldc = ldo; p.epi = epi;
   if (sms > kFuMaxGrid) sms = kFuMaxGrid;
   // CTA pairs (cta_group::2) when there is at least one 128-target tile per SM; tiny batches keep single CTAs
@@ -663,18 +661,29 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   if (ctas == 2) grid &= ~1;
   // shared memory: S pipeline stages + epilogue staging + Q row slots for each of the 16 gather warps.
   // Q = 4 rolling copies per warp saturate HBM in isolation (tools/gather_ceiling.cu); the pipeline gets what is left.
-  const int stage_bytes = 2 * kFuATileBytes + 2 * (p.block_n / ctas) * kFuBK * 4;
   static const int stage_env = [] { const char* e = getenv("TFGNN_B200_FUSED_STAGES"); return e ? atoi(e) : 0; }();
   static const int q_env = [] { const char* e = getenv("TFGNN_B200_GATHER_Q"); return e ? atoi(e) : 0; }();
   const int fixed_bytes = 2048 + kFuEpiBytes + kFuGatherWarps * kFuMaxQ * 8 + 128 + 1024;
   const int row_bytes = D * 4;
-  int want_q = q_env >= 1 && q_env <= kFuMaxQ ? q_env : 4;
-  int stages = stage_env >= 2 ? stage_env : 4;   // measured on cfg2 (CTA pairs, Q = 4): 4 stages 4.85 ms, 3 stages 4.96 ms
-  auto q_for = [&](int s_) { return (kFuSmemLimit - fixed_bytes - s_ * stage_bytes) / (kFuGatherWarps * row_bytes); };
-  while (stages > 2 && q_for(stages) < want_q) --stages;
-  int q = q_for(stages);
-  if (q > want_q) q = want_q;
+  const int want_q = q_env >= 1 && q_env <= kFuMaxQ ? q_env : 4;
+  int kFuBK = 0, stage_bytes = 0, stages = 0, q = 0;
+  auto plan = [&](int bk) {   // most stages (<= 4) that still leave want_q row slots per gather warp; at least 2
+    kFuBK = bk;
+    stage_bytes = 2 * kFuBM * bk * 4 + 2 * (p.block_n / ctas) * bk * 4;
+    auto q_for = [&](int s_) { return (kFuSmemLimit - fixed_bytes - s_ * stage_bytes) / (kFuGatherWarps * row_bytes); };
+    stages = stage_env >= 2 ? stage_env : 4;
+    while (stages > 2 && q_for(stages) < want_q) --stages;
+    q = q_for(stages);
+    if (q > want_q) q = want_q;
+  };
+  // K block of 32 floats (128 B rows, SWIZZLE_128B) when two 64-96 KB stages still leave >= 3 row slots (CTA pairs at
+  // H <= 256: cfg2 4.63 ms vs 4.88 ms, H=320 6.47 vs 6.61 ms), else 16 floats (64 B rows, SWIZZLE_64B).
+  plan(bk_env == 16 ? 16 : 32);
+  if (kFuBK == 32 && q < (want_q < 3 ? want_q : 3)) plan(16);
   TFGNN_REQUIRE(q >= 1 && stages >= 2, "fused RGCN: tile does not fit shared memory");
+  const int kFuATileBytes = kFuBM * kFuBK * 4;
+  p.kb_per_type = D / kFuBK;
+  if (p.debug_skip & 2) p.kb_per_type = 1;
   p.num_stages = stages;
   p.gather_q = q;
 

@@ -8,3 +8,5 @@ for wl in h320 cfg1 cfg4 cfg3; do
 done
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 5 --warmup 3 --skip-e2e --skip-cpu-baseline --no-clock-sampler > gpurun_out/launches_final.log 2>&1
 tail -2 gpurun_out/launches_final.csv
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:fused_rgcn -s 3 -c 1 -o gpurun_out/prof_fused_final2 -f python bench.py --steps 3 --warmup 3 --skip-e2e --skip-cpu-baseline --no-clock-sampler > gpurun_out/ncu_final2.log 2>&1
+ls -la gpurun_out/prof_fused_final2.ncu-rep
