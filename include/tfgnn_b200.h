@@ -24,6 +24,7 @@
 #ifndef TFGNN_B200_H_
 #define TFGNN_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -194,6 +195,50 @@ int tfgnn_b200_activation(const float* x, int64_t n, int32_t activation, float* 
 int tfgnn_b200_residual_average(const float* x, const float* last, float* out, int64_t n, void* stream);
 int tfgnn_b200_layer_norm(const float* x, const float* gamma, const float* beta, int64_t V, int32_t H,
                           float epsilon, float* out, void* stream);
+
+/* ---- On-device batch builder ------------------------------------------------------
+ * Bit-exact int32 bookkeeping of the data layer, so that a training loop never leaves the device between the
+ * packed dataset and the layer call.
+ *
+ * process_adjacency_lists (tf2_gnn/data/utils.py:9-58): from the T forward edge lists [E_t,2] build the processed
+ * lists: forward types first (a tied type gets its flipped edges appended, utils.py:102-108), then one fresh type
+ * of flipped edges per untied forward type (:109-113), then, if add_self_loop_edges, the list (i,i) for all nodes
+ * inserted at slot self_loop_edge_type (negative values count from the end, list.insert semantics of :91-99;
+ * values outside [-(n+1), n] are TFGNN_ERR_INVALID_ARGUMENT like the reference's assert).
+ *   tied                 host int32[T], non-zero = tie_fwd_bkwd for that forward type (get_tied_edge_types, :61-77)
+ *   _sizes               host-only: number of processed types and their edge counts (compute_number_of_edge_types, :80-84)
+ *   adjacency_out        host array of num_types_out caller-allocated device lists, sizes as reported by _sizes
+ *   type_to_num_incoming_edges  optional float32[num_types_out, V]: in-degree per processed type (:116-124; the
+ *                        reference returns float64 of the same integer values) */
+int tfgnn_b200_process_adjacency_sizes(const int64_t* num_edges_fwd, int32_t num_fwd_types, int64_t num_nodes,
+                                       int32_t add_self_loop_edges, const int32_t* tied,
+                                       int32_t self_loop_edge_type, int64_t* num_edges_out,
+                                       int32_t* num_types_out);
+int tfgnn_b200_process_adjacency(const int32_t* const* adjacency_fwd, const int64_t* num_edges_fwd,
+                                 int32_t num_fwd_types, int64_t num_nodes, int32_t add_self_loop_edges,
+                                 const int32_t* tied, int32_t self_loop_edge_type,
+                                 int32_t* const* adjacency_out, int32_t num_types_out,
+                                 float* type_to_num_incoming_edges, void* stream);
+
+/* Disjoint-union minibatch (GraphDataset._add_graph_to_batch / _finalise_batch, graph_dataset.py:161-246) from a
+ * dataset stored packed on the device: node_offsets int64[G+1] (graph g owns rows [off[g], off[g+1]) of the node
+ * table), and per edge type t edge_offsets[t] int64[G+1] into edges[t] int32[*,2] holding graph-local node ids.
+ *   graph_ids            device int32[num_graphs_in_batch], in batch order
+ *   num_nodes_in_batch, num_edges_in_batch[t]   sizes of the outputs (the host knows them from its copy of the
+ *                        offset tables; larger values than the real totals are clamped on the device)
+ *   node_to_graph_map    out int32[num_nodes_in_batch]: batch-local graph index of every node (:211-217), or NULL
+ *   node_source_rows     out int32[num_nodes_in_batch]: row of every batch node in the packed node table (feed it to
+ *                        tfgnn_b200_gather_rows to assemble node_features), or NULL
+ *   adjacency_lists      host array of T caller-allocated device lists [num_edges_in_batch[t], 2]: stored pairs plus
+ *                        the running node count of their graph (:218-222)
+ *   workspace            device, tfgnn_b200_assemble_batch_workspace_bytes(T, num_graphs_in_batch) bytes */
+size_t tfgnn_b200_assemble_batch_workspace_bytes(int32_t num_edge_types, int32_t num_graphs_in_batch);
+int tfgnn_b200_assemble_batch(const int64_t* node_offsets, const int64_t* const* edge_offsets,
+                              const int32_t* const* edges, int32_t num_edge_types, int64_t num_graphs_total,
+                              const int32_t* graph_ids, int32_t num_graphs_in_batch,
+                              int64_t num_nodes_in_batch, const int64_t* num_edges_in_batch,
+                              int32_t* node_to_graph_map, int32_t* node_source_rows,
+                              int32_t* const* adjacency_lists, void* workspace, void* stream);
 
 /* Number of kernels this library has launched in the calling process (all threads). */
 int64_t tfgnn_b200_launch_count(void);

@@ -30,6 +30,8 @@ EXPORTED_SYMBOLS = (
     "tfgnn_b200_ggnn_fwd", "tfgnn_b200_rgin_fwd", "tfgnn_b200_film_fwd", "tfgnn_b200_rgat_fwd",
     "tfgnn_b200_dense_fwd", "tfgnn_b200_gather_rows", "tfgnn_b200_unsorted_segment_reduce",
     "tfgnn_b200_activation", "tfgnn_b200_residual_average", "tfgnn_b200_layer_norm",
+    "tfgnn_b200_process_adjacency_sizes", "tfgnn_b200_process_adjacency",
+    "tfgnn_b200_assemble_batch_workspace_bytes", "tfgnn_b200_assemble_batch",
     "tfgnn_b200_launch_count",
 )
 
@@ -83,6 +85,14 @@ def lib() -> ctypes.CDLL:
     L.tfgnn_b200_activation.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_void_p]
     L.tfgnn_b200_residual_average.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
     L.tfgnn_b200_layer_norm.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p]
+    L.tfgnn_b200_process_adjacency_sizes.argtypes = [POINTER(c_int64), c_int32, c_int64, c_int32, POINTER(c_int32),
+                                                     c_int32, POINTER(c_int64), POINTER(c_int32)]
+    L.tfgnn_b200_process_adjacency.argtypes = [_PP, POINTER(c_int64), c_int32, c_int64, c_int32, POINTER(c_int32),
+                                               c_int32, _PP, c_int32, c_void_p, c_void_p]
+    L.tfgnn_b200_assemble_batch_workspace_bytes.argtypes = [c_int32, c_int32]
+    L.tfgnn_b200_assemble_batch_workspace_bytes.restype = ctypes.c_size_t
+    L.tfgnn_b200_assemble_batch.argtypes = [c_void_p, _PP, _PP, c_int32, c_int64, c_void_p, c_int32, c_int64,
+                                            POINTER(c_int64), c_void_p, c_void_p, _PP, c_void_p, c_void_p]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is ctypes.c_int and name not in ("tfgnn_b200_abi_version",):
