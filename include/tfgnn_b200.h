@@ -146,6 +146,17 @@ int tfgnn_b200_ggnn_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
                         const float* gru_recurrent_kernel, const float* gru_bias, int32_t path,
                         float* out, void* stream);
 
+/* Backward of tfgnn_b200_ggnn_fwd (the reference differentiates through GGNN with
+ * tf.GradientTape, models/graph_task_model.py:338-365).  Recomputes the forward intermediates from h; batch_t is
+ * the TFGNN_PREPARE_TRANSPOSE batch of the same adjacency lists.  Writes grad_h [V,H], grad_W[l] [H,H],
+ * grad_gru_kernel [H,3H], grad_gru_recurrent_kernel [H,3H], grad_gru_bias [2,3H].
+ * Supported: 0 hidden layers in the message MLPs, source state only, sum / mean / sqrt_n aggregation, H % 4 == 0. */
+int tfgnn_b200_ggnn_bwd(tfgnn_batch_t* batch, tfgnn_batch_t* batch_t, const float* h, int32_t D,
+                        const float* const* W, int32_t H, uint32_t flags, int32_t aggregation,
+                        const float* gru_kernel, const float* gru_recurrent_kernel, const float* gru_bias,
+                        const float* grad_out, float* grad_h, float* const* grad_W, float* grad_gru_kernel,
+                        float* grad_gru_recurrent_kernel, float* grad_gru_bias, void* stream);
+
 /* RGIN (rgin.py:88-106): edge MLP messages, aggregation, optional aggregation MLP
  * (aggr_weights: host array of num_aggr_layers device pointers [H,H], may be NULL/0), activation. */
 int tfgnn_b200_rgin_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,

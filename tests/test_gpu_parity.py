@@ -264,6 +264,23 @@ def test_rgcn_fused_kernel_cta_pairs(monkeypatch, pair, V, D, H, L, E, agg):
     assert np.array_equal(a.cpu().numpy(), a2.cpu().numpy())
 
 
+@pytest.mark.parametrize("q", ["1", "2", "3", "8"])
+def test_rgcn_fused_kernel_gather_ring_depths(monkeypatch, q):
+    """The rolling cp.async gather ring with Q = 1..8 row slots per warp: long segments (hubs > 32 edges cross the
+    index-block boundary), empty types, a last tile with a single node; all depths give the same bits."""
+    _need_gpu()
+    V, D, H, L = 128 * 37 + 1, 128, 64, 4
+    rng = np.random.default_rng(77)
+    adjs = random_graph(rng, V, L, 60000, hub=True, dups=True, empty_type=2, self_loops=True)
+    p = mo.default_hyperparameters("rgcn")
+    p.update(hidden_dim=H, aggregation_function="mean", message_activation_function="tanh")
+    monkeypatch.setenv("TFGNN_B200_GATHER_Q", q)
+    a = run_case("rgcn", p, V, D, L, adjs, seed=5, path="fused_tc")
+    monkeypatch.setenv("TFGNN_B200_GATHER_Q", "4")
+    b = run_case("rgcn", p, V, D, L, adjs, seed=5, path="fused_tc")
+    assert np.array_equal(a.cpu().numpy(), b.cpu().numpy())
+
+
 def test_rgcn_atomic_path_matches():
     _need_gpu()
     rng = np.random.default_rng(5)
@@ -558,6 +575,75 @@ def test_rgcn_backward_matches_autograd_reference(V, D, H, L, E, agg, act, norma
     assert_states_close(ht.grad.cpu().numpy(), h64.grad.numpy(), tol=2e-5)
     for var, w64 in zip(layer.variables, W64):
         assert_states_close(var.grad.cpu().numpy(), w64.grad.numpy(), tol=2e-5)
+
+
+def _torch_reference_ggnn(h, adjs, Ws, K, U, b, normalize, agg):
+    """float64 autograd restatement of GGNN (ggnn.py:68-89): messages, aggregation, Keras GRUCell reset_after=True."""
+    V, H = h.shape
+    msgs, tgts = [], []
+    for adj, W in zip(adjs, Ws):
+        src, tgt = adj[:, 0].long(), adj[:, 1].long()
+        m = h.index_select(0, src) @ W
+        if normalize:
+            c = torch.zeros(V, dtype=h.dtype).index_add_(0, tgt, torch.ones(len(tgt), dtype=h.dtype))
+            m = (1.0 / (c.index_select(0, tgt) + 1e-7)).unsqueeze(-1) * m
+        msgs.append(m)
+        tgts.append(tgt)
+    M, T = torch.cat(msgs), torch.cat(tgts)
+    aggd = torch.zeros((V, H), dtype=h.dtype).index_add_(0, T, M)
+    if agg in ("mean", "sqrt_n"):
+        n = torch.zeros(V, dtype=h.dtype).index_add_(0, T, torch.ones(len(T), dtype=h.dtype)).clamp(min=1)
+        aggd = aggd / (n if agg == "mean" else n.sqrt()).unsqueeze(-1)
+    gx = aggd @ K + b[0]
+    gh = h @ U + b[1]
+    z = torch.sigmoid(gx[:, :H] + gh[:, :H])
+    r = torch.sigmoid(gx[:, H:2 * H] + gh[:, H:2 * H])
+    hh = torch.tanh(gx[:, 2 * H:] + r * gh[:, 2 * H:])
+    return z * h + (1 - z) * hh
+
+
+@pytest.mark.parametrize("V,H,L,E,agg,normalize", [
+    (300, 32, 3, 2500, "sum", True),
+    (1000, 64, 2, 9000, "mean", False),
+    (20000, 128, 5, 60000, "sum", True),
+    (700, 36, 2, 4000, "sqrt_n", True),
+])
+def test_ggnn_backward_matches_autograd_reference(V, H, L, E, agg, normalize):
+    """GGNN gradients w.r.t. node states, message weights and the GRU parameters vs float64 autograd
+    of the reference op order."""
+    _need_gpu()
+    from tf2_gnn_b200.layers import GGNN, MessagePassingInput
+    rng = np.random.default_rng(V + H + L)
+    adjs = random_graph(rng, V, L, E, hub=True, dups=True)
+    p = GGNN.get_default_hyperparameters()
+    p.update(hidden_dim=H, aggregation_function=agg, normalize_by_num_incoming=normalize)
+    h = rng.uniform(-1, 1, (V, H)).astype(np.float32)
+    Ws = [mo.glorot_uniform(rng, (H, H)) for _ in range(L)]
+    K, U = mo.glorot_uniform(rng, (H, 3 * H)), mo.glorot_uniform(rng, (H, 3 * H))
+    b = rng.uniform(-0.2, 0.2, (2, 3 * H)).astype(np.float32)
+    g = rng.uniform(-1, 1, (V, H)).astype(np.float32)
+    layer = make_layer("ggnn", p, H, L, {"edge_mlps": [[w] for w in Ws], "gru_kernel": K, "gru_recurrent_kernel": U,
+                                         "gru_bias": b})
+    for v in layer.variables:
+        v.requires_grad_()
+    ht = torch.from_numpy(h).cuda().requires_grad_()
+    out = layer(MessagePassingInput(ht, tuple(torch.from_numpy(a).cuda() for a in adjs)))
+    out.backward(torch.from_numpy(g).cuda())
+    h64 = torch.from_numpy(h).double().requires_grad_()
+    W64 = [torch.from_numpy(w).double().requires_grad_() for w in Ws]
+    K64, U64, b64 = (torch.from_numpy(x).double().requires_grad_() for x in (K, U, b))
+    ref = _torch_reference_ggnn(h64, [torch.from_numpy(a) for a in adjs], W64, K64, U64, b64, normalize, agg)
+    ref.backward(torch.from_numpy(g).double())
+    assert_states_close(out.detach().cpu().numpy(), ref.detach().numpy())
+    assert_states_close(ht.grad.cpu().numpy(), h64.grad.numpy(), tol=2e-5)
+    grads = {v.name: v.grad.cpu().numpy() for v in layer.variables}
+    assert_states_close(grads[[n for n in grads if n.endswith("gru_cell/kernel:0")][0]], K64.grad.numpy(), tol=2e-5)
+    assert_states_close(grads[[n for n in grads if n.endswith("gru_cell/recurrent_kernel:0")][0]], U64.grad.numpy(),
+                        tol=2e-5)
+    assert_states_close(grads[[n for n in grads if n.endswith("gru_cell/bias:0")][0]], b64.grad.numpy(), tol=2e-5)
+    assert len(layer._edge_type_mlps) == L
+    for l, mlp in enumerate(layer._edge_type_mlps):
+        assert_states_close(mlp.layers[0].grad.cpu().numpy(), W64[l].grad.numpy(), tol=2e-5)
 
 
 # ------------------------------------------------------------------------------------------

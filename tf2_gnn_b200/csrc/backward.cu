@@ -171,6 +171,59 @@ __global__ void reduce_partials_kernel(const float* __restrict__ Cpart, int chun
   }
 }
 
+// ---- GGNN: Keras GRUCell (reset_after=True) backward, ggnn.py:84-87 -------------------------------------------------
+// forward: z = sig(gx_z+gh_z), r = sig(gx_r+gh_r), hh = tanh(gx_h + r*gh_h), h' = z*h + (1-z)*hh.
+// In place: gx <- dL/dgx, gh <- dL/dgh (each thread reads its six pre-activations before it writes),
+// dh_direct = dL/dh' * z (the path of h through the convex combination).
+__global__ void gru_gate_bwd_kernel(float* __restrict__ gx, float* __restrict__ gh, const float* __restrict__ h, int ldh,
+                                    const float* __restrict__ grad_out, long long V, int H,
+                                    float* __restrict__ dh_direct) {
+  const long long total = V * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i / H;
+    const int c = (int)(i - v * H);
+    float* x = gx + v * 3 * H;
+    float* y = gh + v * 3 * H;
+    const float ghh = y[2 * H + c];
+    const float z = 1.0f / (1.0f + expf(-(x[c] + y[c])));
+    const float r = 1.0f / (1.0f + expf(-(x[H + c] + y[H + c])));
+    const float hh = tanhf(x[2 * H + c] + r * ghh);
+    const float g = grad_out[i];
+    const float da = g * (1.0f - z) * (1.0f - hh * hh);   // d/d(pre-tanh)
+    const float daz = g * (h[v * ldh + c] - hh) * z * (1.0f - z);
+    const float dar = da * ghh * r * (1.0f - r);
+    x[c] = daz;          y[c] = daz;
+    x[H + c] = dar;      y[H + c] = dar;
+    x[2 * H + c] = da;   y[2 * H + c] = da * r;
+    dh_direct[i] = g * z;
+  }
+}
+
+// column sums over the node dimension in fixed 8192-row chunks (deterministic): partial[chunk][n]
+__global__ void colsum_partial_kernel(const float* __restrict__ X, long long V, int N, float* __restrict__ partial) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const long long m0 = (long long)blockIdx.y * kTnChunk;
+  const long long m1 = m0 + kTnChunk < V ? m0 + kTnChunk : V;
+  float s = 0.f;
+  for (long long m = m0; m < m1; ++m) s += X[m * N + n];
+  partial[(long long)blockIdx.y * N + n] = s;
+}
+__global__ void colsum_reduce_kernel(const float* __restrict__ partial, int chunks, int N, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c) s += partial[(long long)c * N + n];
+  out[n] = s;
+}
+
+// grad_h = grad_h (message path) + a + b
+__global__ void add3_kernel(float* __restrict__ acc, const float* __restrict__ a, const float* __restrict__ b, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    acc[i] = acc[i] + a[i] + b[i];
+}
+
 static int grid_cap(long long n) {
   int g = ceil_div(n, 256);
   return g < 1 ? 1 : (g > 148 * 32 ? 148 * 32 : g);
@@ -263,5 +316,102 @@ extern "C" int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* b, tfgnn_batch_t* bt, const fl
     rc = launch_edge_reduce(p, /*merged=*/true, st);
     if (rc) return rc;
   }
+  return 0;
+}
+
+// GGNN backward: gradient of tfgnn_b200_ggnn_fwd w.r.t. the node states, the per-type message
+// weights and the GRU parameters.  Everything is recomputed from h (nothing but h is saved by the forward pass):
+//   agg = sum_l s A_l W_l (forward kernel), gx = agg K + b0, gh = h U + b1 (tensor-core GEMMs),
+//   gate backward in place -> dgx, dgh, dh_direct;  db = column sums;  dK = agg^T dgx, dU = h^T dgh (TN GEMM, fixed-order
+//   partials);  dagg = dgx K^T, dh_rec = dgh U^T (tensor-core GEMMs);  messages: tfgnn_b200_rgcn_bwd with dagg.
+extern "C" int tfgnn_b200_ggnn_bwd(tfgnn_batch_t* b, tfgnn_batch_t* bt, const float* h, int32_t D,
+                                   const float* const* W, int32_t H, uint32_t flags, int32_t aggregation,
+                                   const float* gru_kernel, const float* gru_recurrent_kernel, const float* gru_bias,
+                                   const float* grad_out, float* grad_h, float* const* grad_W, float* grad_gru_kernel,
+                                   float* grad_gru_recurrent_kernel, float* grad_gru_bias, void* stream) {
+  TFGNN_REQUIRE(b != nullptr && bt != nullptr, "batch / transposed batch is NULL");
+  TFGNN_REQUIRE(D == H, "GGNN needs node embedding dimension == hidden_dim (ggnn.py:30)");
+  TFGNN_REQUIRE(valid_agg(aggregation), "unknown aggregation code");
+  const long long V = b->V;
+  const int L = b->L;
+  if (flags & TFGNN_FLAG_USE_TARGET_STATE) return unsupported("ggnn_bwd: target-state input is not built yet");
+  if (aggregation == TFGNN_AGG_MAX) return unsupported("ggnn_bwd: max aggregation is not built yet");
+  if (H % 4 != 0) return unsupported("ggnn_bwd needs hidden_dim to be a multiple of 4");
+  if (V == 0) return 0;
+  TFGNN_REQUIRE(h && grad_out && grad_h, "NULL pointer");
+  TFGNN_REQUIRE(gru_kernel && gru_recurrent_kernel && gru_bias, "GRU weight pointer is NULL");
+  TFGNN_REQUIRE(grad_gru_kernel && grad_gru_recurrent_kernel && grad_gru_bias, "GRU gradient pointer is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N3 = 3 * H;
+  const int chunks = (int)((V + kTnChunk - 1) / kTnChunk);
+  void *agg = nullptr, *gx = nullptr, *gh = nullptr, *dagg = nullptr, *wT = nullptr, *part = nullptr, *dhd = nullptr,
+       *tmp = nullptr;
+  int rc = batch_scratch(b, 11, (size_t)V * H * sizeof(float), &agg);
+  if (rc) return rc;
+  rc = batch_scratch(b, 12, (size_t)V * N3 * sizeof(float), &gx);
+  if (rc) return rc;
+  rc = batch_scratch(b, 13, (size_t)V * N3 * sizeof(float), &gh);
+  if (rc) return rc;
+  rc = batch_scratch(b, 14, (size_t)V * H * sizeof(float), &dagg);
+  if (rc) return rc;
+  rc = batch_scratch(b, 7, (size_t)N3 * H * sizeof(float), &wT);
+  if (rc) return rc;
+  rc = batch_scratch(b, 10, (size_t)chunks * ((size_t)H * N3 + N3) * sizeof(float), &part);
+  if (rc) return rc;
+  rc = batch_scratch(b, 4, (size_t)V * H * sizeof(float), &dhd);
+  if (rc) return rc;
+  rc = batch_scratch(b, 5, (size_t)V * H * sizeof(float), &tmp);
+  if (rc) return rc;
+  // 1. forward quantities: agg (no message activation, ggnn.py:68-83), gx, gh
+  rc = edge_mlp_core(b, h, D, W, 0, H, flags & ~TFGNN_FLAG_ACT_BEFORE_AGGREGATION, aggregation, TFGNN_ACT_NONE,
+                     TFGNN_PATH_AUTO, (float*)agg, H, st);
+  if (rc) return rc;
+  GemmEpilogue e0, e1, none;
+  e0.bias = gru_bias;
+  e1.bias = gru_bias + N3;
+  rc = node_gemm((const float*)agg, H, gru_kernel, N3, (float*)gx, N3, V, N3, H, e0, TFGNN_PATH_AUTO, b, 6, st);
+  if (rc) return rc;
+  rc = node_gemm(h, D, gru_recurrent_kernel, N3, (float*)gh, N3, V, N3, H, e1, TFGNN_PATH_AUTO, b, 6, st);
+  if (rc) return rc;
+  // 2. gates
+  gru_gate_bwd_kernel<<<grid_cap(V * H), 256, 0, st>>>((float*)gx, (float*)gh, h, D, grad_out, V, H, (float*)dhd);
+  TFGNN_LAUNCH_CHECK();
+  // 3. bias gradients: rows 0 / 1 of gru_bias belong to gx / gh
+  float* cpart = (float*)part + (size_t)chunks * H * N3;
+  for (int which = 0; which < 2; ++which) {
+    dim3 grid((N3 + 127) / 128, chunks);
+    colsum_partial_kernel<<<grid, 128, 0, st>>>((const float*)(which ? gh : gx), V, N3, cpart);
+    TFGNN_LAUNCH_CHECK();
+    colsum_reduce_kernel<<<(N3 + 127) / 128, 128, 0, st>>>(cpart, chunks, N3, grad_gru_bias + (size_t)which * N3);
+    TFGNN_LAUNCH_CHECK();
+  }
+  // 4. dK = agg^T dgx, dU = h^T dgh
+  for (int which = 0; which < 2; ++which) {
+    PtrTable gt{};
+    gt.p[0] = which ? grad_gru_recurrent_kernel : grad_gru_kernel;
+    dim3 grid((H + kTnTile - 1) / kTnTile, (N3 + kTnTile - 1) / kTnTile, chunks);
+    gemm_tn_partial_kernel<<<grid, 256, 0, st>>>(which ? h : (const float*)agg, which ? D : H,
+                                                 (const float*)(which ? gh : gx), N3, V, H, N3, (float*)part);
+    TFGNN_LAUNCH_CHECK();
+    reduce_partials_kernel<<<grid_cap((long long)H * N3), 256, 0, st>>>((const float*)part, chunks, 1, H, N3, gt);
+    TFGNN_LAUNCH_CHECK();
+  }
+  // 5. dagg = dgx K^T, dh_rec = dgh U^T
+  for (int which = 0; which < 2; ++which) {
+    PtrTable wt{};
+    wt.p[0] = which ? gru_recurrent_kernel : gru_kernel;
+    pack_transposed_kernel<<<grid_cap((long long)H * N3), 256, 0, st>>>(wt, 1, H, N3, (float*)wT);   // [3H, H]
+    TFGNN_LAUNCH_CHECK();
+    rc = node_gemm((const float*)(which ? gh : gx), N3, (const float*)wT, H, (float*)(which ? tmp : dagg), H, V, H, N3,
+                   none, TFGNN_PATH_AUTO, b, 6, st);
+    if (rc) return rc;
+  }
+  // 6. messages: dagg -> grad_h (through the edges) and grad_W
+  rc = tfgnn_b200_rgcn_bwd(b, bt, h, D, W, H, flags & ~TFGNN_FLAG_ACT_BEFORE_AGGREGATION, aggregation, TFGNN_ACT_NONE,
+                           (const float*)dagg, (const float*)dagg, grad_h, grad_W, stream);
+  if (rc) return rc;
+  // 7. grad_h += dh_direct + dh_rec
+  add3_kernel<<<grid_cap(V * H), 256, 0, st>>>(grad_h, (const float*)dhd, (const float*)tmp, V * H);
+  TFGNN_LAUNCH_CHECK();
   return 0;
 }

@@ -662,7 +662,8 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   // shared memory: S pipeline stages + epilogue staging + Q row slots for each of the 16 gather warps.
   // Q = 4 rolling copies per warp saturate HBM in isolation (tools/gather_ceiling.cu); the pipeline gets what is left.
   static const int stage_env = [] { const char* e = getenv("TFGNN_B200_FUSED_STAGES"); return e ? atoi(e) : 0; }();
-  static const int q_env = [] { const char* e = getenv("TFGNN_B200_GATHER_Q"); return e ? atoi(e) : 0; }();
+  const char* q_str = getenv("TFGNN_B200_GATHER_Q");   // read per call: the tests sweep it
+  const int q_env = q_str ? atoi(q_str) : 0;
   const int fixed_bytes = 2048 + kFuEpiBytes + kFuGatherWarps * kFuMaxQ * 8 + 128 + 1024;
   const int row_bytes = D * 4;
   const int want_q = q_env >= 1 && q_env <= kFuMaxQ ? q_env : 4;
