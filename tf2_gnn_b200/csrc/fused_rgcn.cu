@@ -664,7 +664,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   static const int stage_env = [] { const char* e = getenv("TFGNN_B200_FUSED_STAGES"); return e ? atoi(e) : 0; }();
   const char* q_str = getenv("TFGNN_B200_GATHER_Q");   // read per call: the tests sweep it
   const int q_env = q_str ? atoi(q_str) : 0;
-  const int fixed_bytes = 2048 + kFuEpiBytes + kFuGatherWarps * kFuMaxQ * 8 + 128 + 1024;
+  const int fixed_bytes = 2048 + kFuEpiBytes + 128 + 1024;   // barriers, epilogue staging, alignment slack
   const int row_bytes = D * 4;
   const int want_q = q_env >= 1 && q_env <= kFuMaxQ ? q_env : 4;
   int kFuBK = 0, stage_bytes = 0, stages = 0, q = 0;
@@ -718,8 +718,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
     }
   }
   const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 4 + 2 * kFuMaxSlots + 4) * sizeof(uint64_t) +
-                            kFuEpiBytes + kFuGatherWarps * kFuMaxQ * 8 + 128 +
-                            (size_t)kFuGatherWarps * q * row_bytes + 1024;
+                            kFuEpiBytes + 128 + (size_t)kFuGatherWarps * q * row_bytes + 1024;
   TFGNN_REQUIRE(smem_bytes <= (size_t)kFuSmemLimit, "fused RGCN: shared memory budget exceeded");
   const int nv = (D + 127) / 128;
   // L2 set-aside for the evict_last (persisting) lines: the ring + the packed weights.  Without a carve-out

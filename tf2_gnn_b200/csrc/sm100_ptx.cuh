@@ -81,70 +81,19 @@ __device__ __forceinline__ uint64_t policy_evict_last() {
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-__device__ __forceinline__ void prefetch_l2(const void* ptr) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
-}
 // Drop a 128 B line from L2 WITHOUT writing it back (producer/consumer scratch that is dead after the read).
 __device__ __forceinline__ void discard_l2_128(const void* ptr) {
   asm volatile("discard.global.L2 [%0], 128;" ::"l"(ptr) : "memory");
 }
-// cp.async (LDGSTS): 16 B global -> shared without holding a register; completion via commit/wait groups.
-__device__ __forceinline__ void cp_async16_hint(uint32_t smem_addr, const void* gptr, uint64_t policy) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "l"(policy)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {   // LDGSTS, L1 bypass
+// LDGSTS, L1 bypass.  (The .L2::cache_hint form of cp.async raised "illegal instruction" on B200 with CUDA 12.9 in
+// tools/gather_ceiling.cu, so the gather ring copies without an eviction hint.)
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-// One request prefetches `bytes` (multiple of 16) contiguous bytes into L2.
-__device__ __forceinline__ void bulk_prefetch_l2(const void* ptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
-}
-// bulk (non-tensor) copy global -> this CTA's shared memory, completion on an mbarrier; 16 B aligned, size % 16 == 0
-__device__ __forceinline__ void bulk_load_hint(void* smem_dst, const void* gptr, uint32_t bytes, uint64_t* bar,
-                                               uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(gptr), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-      : "memory");
-}
-// raw shared-window (32-bit) address forms: keep hot loops free of generic-address arithmetic
-__device__ __forceinline__ void bulk_load_s(uint32_t smem_dst, const void* gptr, uint32_t bytes, uint32_t bar,
-                                            uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-          smem_dst),
-      "l"(gptr), "r"(bytes), "r"(bar), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx_s(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_s(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 ld_nc_f4_hint(const float* ptr, uint64_t policy) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(ptr), "l"(policy));
   return v;
 }
 __device__ __forceinline__ void st_f4_hint(float* ptr, float4 v, uint64_t policy) {
@@ -263,20 +212,6 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t local, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // arrive on another CTA's mbarrier
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// wait that also acquires writes released at cluster scope by the other CTA's arrivals
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-  } while (!done);
 }
 // TMEM allocation for a CTA pair: the same warp index of BOTH CTAs executes it with the same smem slot offset.
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
