@@ -51,7 +51,7 @@ struct FusedParams {
   long long M;          // entries of src (bound for the 32-wide index block loads)
   int discard_ring;     // discard.global.L2 on consumed ring slots
   int gather_q;         // bulk row copies each gather warp keeps in flight (= its shared-memory row slots)
-  int debug_skip;       // timing experiments only (results invalid), bit mask: 1 = no edge gathers, 2 = one K block per slot, 4 = no epilogue work, 8 = no weight-tile loads, 16 = no ring stores
+  int debug_skip;       // timing experiments only (results invalid), bit mask: 1 = no edge gathers, 2 = one K block per slot, 4 = no epilogue work, 8 = no weight-tile loads, 16 = no ring stores, 32 = raw fp32 tile as the hi operand (valid iff the MMA truncates)
   // ring
   float* ring;  // [grid * num_slots * 128, D]
   int num_slots;
@@ -446,6 +446,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else if (warp >= 4 && warp < 8) {
     // ================= A splitters =================
     const int tid = threadIdx.x - 128;
+    const bool raw_hi = p.debug_skip & 32;   // experiment: leave the fp32 tile in place as the hi operand
     uint32_t it = 0, slot_base_it = 0;
     for (long long unit = unit0; unit < total_units; unit += unit_step, slot_base_it += p.L) {
      for (int pass = 0; pass < n_pass; ++pass) {
@@ -475,7 +476,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             hh.x = ptx::tf32_hi(x.x); hh.y = ptx::tf32_hi(x.y); hh.z = ptx::tf32_hi(x.z); hh.w = ptx::tf32_hi(x.w);
             ll.x = ptx::tf32_hi(x.x - hh.x); ll.y = ptx::tf32_hi(x.y - hh.y);
             ll.z = ptx::tf32_hi(x.z - hh.z); ll.w = ptx::tf32_hi(x.w - hh.w);
-            a[idx] = hh;
+            if (!raw_hi) a[idx] = hh;   // raw_hi: the tensor core itself drops the low 13 mantissa bits of the operand
             lo[idx] = ll;
           }
           ptx::fence_proxy_async_smem();
