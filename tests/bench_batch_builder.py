@@ -3,7 +3,8 @@
 Times `DeviceGraphStore.batch` + `process_adjacency_lists` on the GPU (CUDA events, inputs resident in HBM) next to
 the reference's host path restated in numpy (oracle/adjacency_oracle.py: assemble_batch + process_adjacency_lists,
 pinned bit-exactly against the reference's own code), and checks the two results against each other.
-Prints one JSON line per workload.  Run on a GPU box: python tools/bench_batch_builder.py
+Lives under tests/ because it uses the oracle as checker and CPU baseline (only tests/, smoke() and bench.py may).
+Prints one JSON line per workload.  Run on a GPU box: python tests/bench_batch_builder.py
 """
 import json
 import os
