@@ -12,6 +12,9 @@ PINNED: tests/golden/process_adjacency_lists_golden.json is produced by running 
 reference's own tf2_gnn/data/utils.py (pure numpy, importable without TensorFlow) through
 oracle/gen_golden.py, and also contains the 8 expected outputs transcribed from
 tf2_gnn/test/data/test_utils.py:50-115.  Bit-exact (np.array_equal) parity is required.
+assemble_batch is PINNED the same way: tests/golden/batch_assembly_golden.json holds minibatches produced by
+executing the reference's own tf2_gnn/data/graph_dataset.py:161-246 on seeded random graphs (oracle/gen_golden.py
+imports that module with tensorflow / dpu_utils stubbed: they are only used by its tf.data wrapper).
 """
 from __future__ import annotations
 

@@ -11,6 +11,11 @@
    TensorFlow imports are never touched) on the 8 inputs of
    tf2_gnn/test/data/test_utils.py:50-115 plus seeded random inputs; the expected outputs
    written in that test file are stored next to the executed outputs and must agree.
+3. batch_assembly_golden.json — produced by EXECUTING the reference's own minibatch assembly,
+   tf2_gnn/data/graph_dataset.py:161-246 (graph_batch_iterator_from_graph_iterator, _batch_would_be_too_full,
+   _add_graph_to_batch, _finalise_batch).  The module imports tensorflow and dpu_utils only for its tf.data
+   wrapper and type annotations; both are replaced by attribute-swallowing stubs for the import, the batching
+   code itself is pure numpy and runs unmodified on seeded random graphs.
 """
 import importlib.util
 import json
@@ -110,6 +115,102 @@ def process_adjacency_lists_golden():
     return dict(cases=cases)
 
 
+class _Stub:
+    """Stands in for `tensorflow` / `dpu_utils.utils` while the reference module is imported (annotations only)."""
+
+    def __getattr__(self, name):
+        return self
+
+    def __call__(self, *a, **k):
+        return self
+
+    def __getitem__(self, k):
+        return self
+
+
+def _load_reference_graph_dataset():
+    import sys
+    import types
+    saved = {k: sys.modules.get(k) for k in ("tensorflow", "dpu_utils", "dpu_utils.utils")}
+    try:
+        tf_stub = _Stub()
+        du = types.ModuleType("dpu_utils")
+        duu = types.ModuleType("dpu_utils.utils")
+        duu.RichPath = _Stub()
+        duu.DoubleBufferedIterator = _Stub()
+        du.utils = duu
+        sys.modules["tensorflow"] = tf_stub
+        sys.modules["dpu_utils"] = du
+        sys.modules["dpu_utils.utils"] = duu
+        spec = importlib.util.spec_from_file_location("_ref_graph_dataset", os.path.join(REF, "data", "graph_dataset.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def batch_assembly_golden():
+    ref = _load_reference_graph_dataset()
+
+    class _Dataset(ref.GraphDataset):   # the abstract hooks are not touched by the batching code
+        def __init__(self, params, n_types, feat_dim):
+            super().__init__(params)
+            self._n_types, self._feat_dim = n_types, feat_dim
+
+        num_edge_types = property(lambda self: self._n_types)
+        node_feature_shape = property(lambda self: (self._feat_dim,))
+
+        def load_data(self, path, folds_to_load=None):
+            raise NotImplementedError
+
+        def load_data_from_list(self, datapoints, target_fold=None):
+            raise NotImplementedError
+
+        def _graph_iterator(self, data_fold):
+            raise NotImplementedError
+
+    cases = []
+    for seed, (G, T, max_n, F, max_nodes_per_batch) in enumerate([(1, 1, 4, 2, 100), (7, 2, 6, 3, 12), (25, 3, 9, 4, 40),
+                                                                 (12, 4, 29, 15, 100)]):
+        rng = np.random.default_rng(100 + seed)
+        graphs = []
+        for g in range(G):
+            n = int(rng.integers(1, max_n + 1))
+            adj = []
+            for t in range(T):
+                e = 0 if (t == 1 and g % 3 == 0) else int(rng.integers(0, 2 * n + 1))
+                adj.append(rng.integers(0, n, size=(e, 2)).astype(np.int32))
+            graphs.append(dict(node_features=rng.integers(-3, 4, size=(n, F)).astype(np.float32), adjacency_lists=adj))
+        ds = _Dataset({"max_nodes_per_batch": max_nodes_per_batch}, T, F)
+        samples = [ref.GraphSample(adjacency_lists=g["adjacency_lists"], type_to_node_to_num_inedges=None,
+                                   node_features=g["node_features"]) for g in graphs]
+        batches = []
+        first = 0
+        for feats, _labels in ds.graph_batch_iterator_from_graph_iterator(iter(samples)):
+            nb = int(feats["num_graphs_in_batch"])
+            batches.append(dict(
+                graph_ids=list(range(first, first + nb)),
+                node_features=np.asarray(feats["node_features"], np.float32).tolist(),
+                node_to_graph_map=np.asarray(feats["node_to_graph_map"]).astype(int).tolist(),
+                num_graphs_in_batch=nb,
+                adjacency_lists=[np.asarray(feats[f"adjacency_list_{t}"]).astype(int).reshape(-1, 2).tolist()
+                                 for t in range(T)],
+                adjacency_dtypes=[str(np.asarray(feats[f"adjacency_list_{t}"]).dtype) for t in range(T)]))
+            first += nb
+        cases.append(dict(
+            source="executed tf2_gnn/data/graph_dataset.py:161-246", num_edge_types=T, feature_dim=F,
+            max_nodes_per_batch=max_nodes_per_batch,
+            graphs=[dict(node_features=g["node_features"].tolist(),
+                         adjacency_lists=[a.astype(int).tolist() for a in g["adjacency_lists"]]) for g in graphs],
+            batches=batches))
+    return dict(cases=cases)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     with open(os.path.join(OUT, "message_passing_golden.json"), "w") as f:
@@ -117,3 +218,5 @@ if __name__ == "__main__":
     with open(os.path.join(OUT, "process_adjacency_lists_golden.json"), "w") as f:
         json.dump(process_adjacency_lists_golden(), f)
     print("wrote golden fixtures to", os.path.normpath(OUT))
+    with open(os.path.join(OUT, "batch_assembly_golden.json"), "w") as f:
+        json.dump(batch_assembly_golden(), f)

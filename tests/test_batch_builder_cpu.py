@@ -95,3 +95,14 @@ def test_greedy_batching_rule(max_nodes):
 
 def test_workspace_bytes():
     assert _ffi.lib().tfgnn_b200_assemble_batch_workspace_bytes(3, 10) == 4 * 11 * 8
+
+
+def test_greedy_batching_rule_matches_executed_reference():
+    """The partition of graphs into batches produced by the reference's own iterator (batch_assembly_golden.json)."""
+    path = os.path.join(os.path.dirname(GOLDEN), "batch_assembly_golden.json")
+    with open(path) as f:
+        cases = json.load(f)["cases"]
+    for c in cases:
+        counts = [len(g["node_features"]) for g in c["graphs"]]
+        got = [b.tolist() for b in greedy_batches(counts, c["max_nodes_per_batch"])]
+        assert got == [b["graph_ids"] for b in c["batches"]]

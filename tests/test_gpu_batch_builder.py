@@ -101,6 +101,30 @@ def test_assemble_batch_matches_oracle(G, T, max_nodes, F):
             assert np.array_equal(a.cpu().numpy(), expect[f"adjacency_list_{t}"])
 
 
+def test_assemble_batch_matches_executed_reference_golden():
+    """tests/golden/batch_assembly_golden.json: the reference's own graph_dataset.py:161-246, executed."""
+    _need_gpu()
+    from tf2_gnn_b200.data import DeviceGraphStore
+    with open(os.path.join(os.path.dirname(GOLDEN), "batch_assembly_golden.json")) as f:
+        cases = json.load(f)["cases"]
+    for c in cases:
+        T = c["num_edge_types"]
+        graphs = [dict(node_features=np.asarray(g["node_features"], np.float32),
+                       adjacency_lists=[np.asarray(a, np.int32).reshape(-1, 2) for a in g["adjacency_lists"]])
+                  for g in c["graphs"]]
+        store = DeviceGraphStore(graphs, T)
+        ids_per_batch = [b.tolist() for b in store.iter_batch_graph_ids(c["max_nodes_per_batch"])]
+        assert ids_per_batch == [b["graph_ids"] for b in c["batches"]]
+        for b in c["batches"]:
+            got = store.batch(b["graph_ids"])
+            assert got["num_graphs_in_batch"] == b["num_graphs_in_batch"]
+            assert np.array_equal(got["node_to_graph_map"].cpu().numpy(), np.asarray(b["node_to_graph_map"], np.int32))
+            assert np.array_equal(got["node_features"].cpu().numpy(), np.asarray(b["node_features"], np.float32))
+            for t in range(T):
+                assert np.array_equal(got[f"adjacency_list_{t}"].cpu().numpy(),
+                                      np.asarray(b["adjacency_lists"][t], np.int32).reshape(-1, 2))
+
+
 def test_batches_from_the_store_drive_the_layer_like_host_built_ones():
     """The whole device-side data path: packed store -> batch -> process_adjacency_lists -> RGCN layer, equal to the
     same layer on the oracle-built batch."""

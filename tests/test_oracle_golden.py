@@ -103,3 +103,30 @@ def test_activation_table_errors():
     x = np.array([-1.0, 0.5], np.float32)
     np.testing.assert_allclose(mo.get_activation_function("ReLU")(x), [0, 0.5])
     np.testing.assert_allclose(mo.get_activation_function("leaky_relu")(x), [-0.2, 0.5], rtol=1e-6)
+
+
+def test_assemble_batch_matches_executed_reference(golden_dir):
+    """tests/golden/batch_assembly_golden.json: minibatches produced by EXECUTING the reference's own
+    graph_dataset.py:161-246 (oracle/gen_golden.py) -> pins adjacency_oracle.assemble_batch bit-exactly."""
+    import json
+    import os
+    import numpy as np
+    from oracle import adjacency_oracle as ao
+    with open(os.path.join(golden_dir, "batch_assembly_golden.json")) as f:
+        cases = json.load(f)["cases"]
+    assert len(cases) >= 4
+    for c in cases:
+        T = c["num_edge_types"]
+        graphs = [dict(node_features=np.asarray(g["node_features"], np.float32),
+                       adjacency_lists=[np.asarray(a, np.int32).reshape(-1, 2) for a in g["adjacency_lists"]])
+                  for g in c["graphs"]]
+        for b in c["batches"]:
+            got = ao.assemble_batch([graphs[i] for i in b["graph_ids"]], T)
+            assert got["num_graphs_in_batch"] == b["num_graphs_in_batch"]
+            assert np.array_equal(got["node_to_graph_map"], np.asarray(b["node_to_graph_map"], np.int32))
+            assert got["node_to_graph_map"].dtype == np.int32
+            assert np.array_equal(got["node_features"], np.asarray(b["node_features"], np.float32))
+            for t in range(T):
+                expect = np.asarray(b["adjacency_lists"][t], np.int32).reshape(-1, 2)
+                assert np.array_equal(got[f"adjacency_list_{t}"], expect)
+                assert got[f"adjacency_list_{t}"].dtype == np.int32 and b["adjacency_dtypes"][t] == "int32"
