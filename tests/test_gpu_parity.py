@@ -518,13 +518,16 @@ def test_target_range_shards_match_full(kind, extra):
         assert_states_close(np.concatenate(parts, axis=0), full.astype(np.float64), tol=2e-6)
 
 
-def _torch_reference_layer(h, adjs, Ws, normalize, agg, act):
+def _torch_reference_layer(h, adjs, Ws, normalize, agg, act, use_target=False):
     """float64 autograd restatement of the RGCN layer (reference op order) for gradient parity."""
     V = h.shape[0]
     msgs, tgts = [], []
     for adj, W in zip(adjs, Ws):
         src, tgt = adj[:, 0].long(), adj[:, 1].long()
-        m = h.index_select(0, src) @ W
+        x = h.index_select(0, src)
+        if use_target:   # gnn_edge_mlp.py:93-98: MLP input = [h_src || h_tgt]
+            x = torch.cat([x, h.index_select(0, tgt)], dim=-1)
+        m = x @ W
         if normalize:
             c = torch.zeros(V, dtype=h.dtype).index_add_(0, tgt, torch.ones(len(tgt), dtype=h.dtype))
             m = (1.0 / (c.index_select(0, tgt) + 1e-7)).unsqueeze(-1) * m
@@ -644,6 +647,40 @@ def test_ggnn_backward_matches_autograd_reference(V, H, L, E, agg, normalize):
     assert len(layer._edge_type_mlps) == L
     for l, mlp in enumerate(layer._edge_type_mlps):
         assert_states_close(mlp.layers[0].grad.cpu().numpy(), W64[l].grad.numpy(), tol=2e-5)
+
+
+@pytest.mark.parametrize("V,D,H,L,E,agg,act,normalize", [
+    (300, 32, 48, 3, 2500, "sum", "tanh", True),
+    (2000, 64, 64, 2, 15000, "mean", "elu", False),
+    (700, 128, 36, 4, 6000, "sqrt_n", "tanh", True),
+])
+def test_rgcn_backward_with_target_state_input(V, D, H, L, E, agg, act, normalize):
+    """use_target_state_as_input=True (the [2D, H] kernels of test_RGCN.py:40-65): gradients incl. the target half."""
+    _need_gpu()
+    from tf2_gnn_b200.layers import MessagePassingInput, RGCN
+    rng = np.random.default_rng(V + D + H)
+    adjs = random_graph(rng, V, L, E, hub=True, dups=True, self_loops=True)
+    p = RGCN.get_default_hyperparameters()
+    p.update(hidden_dim=H, aggregation_function=agg, message_activation_function=act,
+             normalize_by_num_incoming=normalize, use_target_state_as_input=True)
+    h = rng.uniform(-1, 1, (V, D)).astype(np.float32)
+    Ws = [mo.glorot_uniform(rng, (2 * D, H)) for _ in range(L)]
+    g = rng.uniform(-1, 1, (V, H)).astype(np.float32)
+    layer = make_layer("rgcn", p, D, L, {"edge_mlps": [[w] for w in Ws]})
+    for v in layer.variables:
+        v.requires_grad_()
+    ht = torch.from_numpy(h).cuda().requires_grad_()
+    out = layer(MessagePassingInput(ht, tuple(torch.from_numpy(a).cuda() for a in adjs)))
+    out.backward(torch.from_numpy(g).cuda())
+    h64 = torch.from_numpy(h).double().requires_grad_()
+    W64 = [torch.from_numpy(w).double().requires_grad_() for w in Ws]
+    ref = _torch_reference_layer(h64, [torch.from_numpy(a) for a in adjs], W64, normalize, agg, act, use_target=True)
+    ref.backward(torch.from_numpy(g).double())
+    assert_states_close(out.detach().cpu().numpy(), ref.detach().numpy())
+    assert_states_close(ht.grad.cpu().numpy(), h64.grad.numpy(), tol=2e-5)
+    for var, w64 in zip(layer.variables, W64):
+        assert tuple(var.grad.shape) == (2 * D, H)
+        assert_states_close(var.grad.cpu().numpy(), w64.grad.numpy(), tol=2e-5)
 
 
 # ------------------------------------------------------------------------------------------

@@ -42,28 +42,52 @@ __global__ void act_grad_kernel(const float* __restrict__ g, const float* __rest
   }
 }
 
-// dA[v, l*D + c] *= 1/(c_{v,l}+eps)
-__global__ void scale_by_type_kernel(float* __restrict__ dA, long long V, int L, int D,
+// dA[v, l*D + c] *= 1/(c_{v,l}+eps)   (first L*D columns of rows with leading dimension ld)
+__global__ void scale_by_type_kernel(float* __restrict__ dA, int ld, long long V, int L, int D,
                                      const int* __restrict__ row_ptr) {
   const long long total = V * L * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long v = i / ((long long)L * D);
-    const int l = (int)((i / D) % L);
+    const int col = (int)(i - v * (long long)L * D);
+    const int l = col / D;
     const long long seg = (long long)l * V + v;
-    dA[i] *= 1.0f / ((float)(row_ptr[seg + 1] - row_ptr[seg]) + kSmallNumber);
+    dA[v * ld + col] *= 1.0f / ((float)(row_ptr[seg + 1] - row_ptr[seg]) + kSmallNumber);
   }
 }
 
-// WcatT[hh, l*D + d] = W_l[d, hh]   (operand of dA = dZ Wcat^T)
-__global__ void pack_transposed_kernel(PtrTable W, int L, int D, int H, float* __restrict__ out) {
+// use_target_state_as_input (gnn_edge_mlp.py:93-98): the target half of the node-level operand is
+// T[v, l*D + c] = coeff(v,l) * h_v[c], coeff = c/(c+eps) or c; its gradient flows straight back to h_v:
+// grad_h[v, c] += sum_l coeff(v,l) * dT[v, l*D + c]
+__global__ void target_term_bwd_kernel(const float* __restrict__ dT, int ld, const int* __restrict__ row_ptr, long long V,
+                                       int L, int D, int normalize, float* __restrict__ grad_h) {
+  const long long total = V * D;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i / D;
+    const int c = (int)(i - v * D);
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) {
+      const long long seg = (long long)l * V + v;
+      const float cnt = (float)(row_ptr[seg + 1] - row_ptr[seg]);
+      const float coeff = normalize ? cnt * (1.0f / (cnt + kSmallNumber)) : cnt;
+      s += coeff * dT[v * ld + (long long)l * D + c];
+    }
+    grad_h[i] += s;
+  }
+}
+
+// WcatT[hh, col0 + l*D + d] = W_l[row0 + d, hh]   (operand of dA = dZ Wcat^T; ld_out = columns of WcatT)
+__global__ void pack_transposed_kernel(PtrTable W, int L, int D, int H, float* __restrict__ out, int ld_out = 0,
+                                       int col0 = 0, int row0 = 0) {
   const long long total = (long long)L * D * H;
+  if (ld_out == 0) ld_out = L * D;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int col = (int)(i % ((long long)L * D));
     const int hh = (int)(i / ((long long)L * D));
     const int l = col / D, d = col - l * D;
-    out[i] = reinterpret_cast<const float*>(W.p[l])[(long long)d * H + hh];
+    out[(long long)hh * ld_out + col0 + col] = reinterpret_cast<const float*>(W.p[l])[(long long)(row0 + d) * H + hh];
   }
 }
 
@@ -158,16 +182,19 @@ gemm_tn_partial_kernel(const float* __restrict__ A, int lda, const float* __rest
 }
 
 // dW_l[d, :] = sum over chunks of Cpart[chunk][l*D + d, :]   (fixed order: deterministic)
+// Cpart rows [k0, k0 + L*D) of K_total rows per chunk (K_total = 0: L*D) go to rows [row0, row0 + D) of dW_l.
 __global__ void reduce_partials_kernel(const float* __restrict__ Cpart, int chunks, int L, int D, int N,
-                                       PtrTable dW) {
+                                       PtrTable dW, int K_total = 0, int k0 = 0, int row0 = 0) {
   const long long total = (long long)L * D * N;
+  if (K_total == 0) K_total = L * D;
+  const long long chunk_stride = (long long)K_total * N;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     float s = 0.f;
-    for (int c = 0; c < chunks; ++c) s += Cpart[(long long)c * total + i];
+    for (int c = 0; c < chunks; ++c) s += Cpart[(long long)c * chunk_stride + (long long)k0 * N + i];
     const int row = (int)(i / N), n = (int)(i - (long long)row * N);
     const int l = row / D, d = row - l * D;
-    reinterpret_cast<float*>(const_cast<void*>(dW.p[l]))[(long long)d * N + n] = s;
+    reinterpret_cast<float*>(const_cast<void*>(dW.p[l]))[(long long)(row0 + d) * N + n] = s;
   }
 }
 
@@ -244,8 +271,9 @@ extern "C" int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* b, tfgnn_batch_t* bt, const fl
   const int L = b->L;
   TFGNN_REQUIRE(bt->V == V && bt->L == L && b->V_src == V && bt->V_src == V,
                 "forward and transposed batches must describe the same (unsharded) graph");
-  if (flags & (TFGNN_FLAG_ACT_BEFORE_AGGREGATION | TFGNN_FLAG_USE_TARGET_STATE))
-    return unsupported("rgcn_bwd: activation-before-aggregation / target-state input are not built yet");
+  if (flags & TFGNN_FLAG_ACT_BEFORE_AGGREGATION)
+    return unsupported("rgcn_bwd: activation-before-aggregation is not built yet");
+  const bool use_target = flags & TFGNN_FLAG_USE_TARGET_STATE;   // W_l is then [2D, H]: rows [0,D) source, [D,2D) target
   if (aggregation == TFGNN_AGG_MAX) return unsupported("rgcn_bwd: max aggregation is not built yet");
   if (activation == TFGNN_ACT_GELU) return unsupported("rgcn_bwd: gelu needs the pre-activation (not saved)");
   if (D % 4 != 0 || H % 4 != 0) return unsupported("rgcn_bwd needs D and H to be multiples of 4");
@@ -254,7 +282,8 @@ extern "C" int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* b, tfgnn_batch_t* bt, const fl
   TFGNN_REQUIRE(L == 0 || (W && grad_W), "weight / weight-gradient table is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   const bool normalize = flags & TFGNN_FLAG_NORMALIZE_BY_NUM_INCOMING;
-  const int K = L * D;
+  const int LD = L * D;
+  const int K = use_target ? 2 * LD : LD;
   if (L == 0) {
     if (grad_h) TFGNN_CUDA(cudaMemsetAsync(grad_h, 0, (size_t)V * D * sizeof(float), st));
     return 0;
@@ -289,21 +318,34 @@ extern "C" int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* b, tfgnn_batch_t* bt, const fl
     p.V = (int)V; p.L = L; p.C = D; p.normalize = normalize;
     rc = launch_edge_reduce(p, /*merged=*/false, st);
     if (rc) return rc;
+    if (use_target) {
+      rc = launch_target_term(h, D, b->row_ptr, (int)V, L, D, normalize, (float*)A, K, LD, st);
+      if (rc) return rc;
+    }
     dim3 grid((K + kTnTile - 1) / kTnTile, (H + kTnTile - 1) / kTnTile, chunks);
     gemm_tn_partial_kernel<<<grid, 256, 0, st>>>((const float*)A, K, (const float*)dz, H, V, K, H, (float*)part);
     TFGNN_LAUNCH_CHECK();
-    reduce_partials_kernel<<<grid_cap((long long)K * H), 256, 0, st>>>((const float*)part, chunks, L, D, H, gwt);
+    reduce_partials_kernel<<<grid_cap((long long)LD * H), 256, 0, st>>>((const float*)part, chunks, L, D, H, gwt, K, 0, 0);
     TFGNN_LAUNCH_CHECK();
+    if (use_target) {
+      reduce_partials_kernel<<<grid_cap((long long)LD * H), 256, 0, st>>>((const float*)part, chunks, L, D, H, gwt, K, LD,
+                                                                        D);
+      TFGNN_LAUNCH_CHECK();
+    }
   }
   if (!grad_h) return 0;
   // 3. dA = dZ Wcat^T (overwrites A), scaled per (v,l)
-  pack_transposed_kernel<<<grid_cap((long long)K * H), 256, 0, st>>>(wt, L, D, H, (float*)WT);
+  pack_transposed_kernel<<<grid_cap((long long)LD * H), 256, 0, st>>>(wt, L, D, H, (float*)WT, K, 0, 0);
   TFGNN_LAUNCH_CHECK();
+  if (use_target) {
+    pack_transposed_kernel<<<grid_cap((long long)LD * H), 256, 0, st>>>(wt, L, D, H, (float*)WT, K, LD, D);
+    TFGNN_LAUNCH_CHECK();
+  }
   GemmEpilogue none;
   rc = node_gemm((const float*)dz, H, (const float*)WT, K, (float*)A, K, V, K, H, none, TFGNN_PATH_AUTO, b, 6, st);
   if (rc) return rc;
   if (normalize) {
-    scale_by_type_kernel<<<grid_cap(V * K), 256, 0, st>>>((float*)A, V, L, D, b->row_ptr);
+    scale_by_type_kernel<<<grid_cap(V * LD), 256, 0, st>>>((float*)A, K, V, L, D, b->row_ptr);
     TFGNN_LAUNCH_CHECK();
   }
   // 4. dh[u] = sum over the edges LEAVING u (source-keyed CSR), all types merged
@@ -315,6 +357,11 @@ extern "C" int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* b, tfgnn_batch_t* bt, const fl
     p.V = (int)V; p.L = L; p.C = D;
     rc = launch_edge_reduce(p, /*merged=*/true, st);
     if (rc) return rc;
+  }
+  if (use_target) {   // 5. the target half: grad_h[v] += sum_l coeff(v,l) * dT_l[v]
+    target_term_bwd_kernel<<<grid_cap(V * D), 256, 0, st>>>((const float*)A + LD, K, b->row_ptr, V, L, D, normalize,
+                                                            grad_h);
+    TFGNN_LAUNCH_CHECK();
   }
   return 0;
 }
