@@ -7,7 +7,7 @@
 //                                                              over the V nodes in fixed chunks -> deterministic)
 //   dA      = dZ [W_0;..;W_{L-1}]^T, then dA_l[v] *= s_{v,l}   (3xTF32 tcgen05 GEMM + row/type scale)
 //   dh[u]   = sum_l sum_{(u,v) in A_l} dA_l[v]                (CSR reduce over the SOURCE-keyed CSR: no atomics)
-// Supported: 0 hidden layers, source state only, sum / mean / sqrt_n aggregation, activation after the
+// Supported: 0 hidden layers, source or source+target state input, sum / mean / sqrt_n aggregation, activation after the
 // aggregation, activations whose derivative is a function of the output (none, relu, tanh, leaky_relu, elu, selu).
 #include "layers.cuh"
 
