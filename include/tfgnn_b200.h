@@ -130,7 +130,7 @@ int tfgnn_b200_rgcn_fwd(tfgnn_batch_t* batch, const float* h, int32_t D, const f
  * models/graph_task_model.py:338-365).  batch_t is the SAME adjacency prepared with TFGNN_PREPARE_TRANSPOSE.
  * out = saved forward output, grad_out = dL/dout [V,H]; writes grad_h [V,D] (may be NULL) and grad_W[l] [D,H].
  * Supported: sum/mean/sqrt_n aggregation, activation after aggregation, activations none/relu/tanh/leaky_relu/
- * elu/selu (derivative from the output), source-only or source+target state input (W[l] = [D,H] or [2D,H],
+ * elu/selu (derivative from the output) and gelu (pre-activation recomputed), source-only or source+target state input (W[l] = [D,H] or [2D,H],
  * TFGNN_FLAG_USE_TARGET_STATE); D and H multiples of 4. */
 int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* batch, tfgnn_batch_t* batch_t, const float* h, int32_t D,
                         const float* const* W, int32_t H, uint32_t flags, int32_t aggregation,

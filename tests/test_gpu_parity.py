@@ -538,7 +538,9 @@ def _torch_reference_layer(h, adjs, Ws, normalize, agg, act, use_target=False):
     if agg in ("mean", "sqrt_n"):
         n = torch.zeros(V, dtype=h.dtype).index_add_(0, T, torch.ones(len(T), dtype=h.dtype)).clamp(min=1)
         out = out / (n if agg == "mean" else n.sqrt()).unsqueeze(-1)
-    return {"relu": torch.relu, "tanh": torch.tanh, "elu": torch.nn.functional.elu, "selu": torch.selu,
+    def gelu(x):   # utils/activation.py:7-14
+        return x * 0.5 * (1.0 + torch.tanh(0.7978845608028654 * (x + 0.044715 * x ** 3)))
+    return {"relu": torch.relu, "tanh": torch.tanh, "elu": torch.nn.functional.elu, "selu": torch.selu, "gelu": gelu,
             "leaky_relu": lambda x: torch.nn.functional.leaky_relu(x, 0.2)}[act](out)
 
 
@@ -549,6 +551,7 @@ def _torch_reference_layer(h, adjs, Ws, normalize, agg, act, use_target=False):
     (400, 64, 32, 2, 2500, "sum", "leaky_relu", False),
     (700, 256, 256, 3, 5000, "sqrt_n", "elu", True),
     (500, 36, 20, 2, 3000, "sum", "selu", True),
+    (900, 64, 48, 3, 7000, "mean", "gelu", True),
 ])
 def test_rgcn_backward_matches_autograd_reference(V, D, H, L, E, agg, act, normalize):
     """gradients w.r.t. node states and per-type weights vs float64 autograd of the

@@ -8,7 +8,7 @@
 //   dA      = dZ [W_0;..;W_{L-1}]^T, then dA_l[v] *= s_{v,l}   (3xTF32 tcgen05 GEMM + row/type scale)
 //   dh[u]   = sum_l sum_{(u,v) in A_l} dA_l[v]                (CSR reduce over the SOURCE-keyed CSR: no atomics)
 // Supported: 0 hidden layers, source or source+target state input, sum / mean / sqrt_n aggregation, activation after the
-// aggregation, activations whose derivative is a function of the output (none, relu, tanh, leaky_relu, elu, selu).
+// aggregation, every activation of the reference's table (gelu through a recomputed pre-activation).
 #include "layers.cuh"
 
 namespace tfgnn {
@@ -22,6 +22,13 @@ __device__ __forceinline__ float act_grad_from_output(float y, int act) {
     case TFGNN_ACT_SELU: return y > 0.f ? kSeluScale : y + kSeluScale * kSeluAlpha;   // scale*alpha*e^x = y + scale*alpha
     default: return 1.f;
   }
+}
+// gelu (utils/activation.py:7-14, tanh approximation) is not invertible from its output: derivative from the
+// recomputed PRE-activation x.
+__device__ __forceinline__ float gelu_grad_from_input(float x) {
+  const float c = 0.7978845608028654f;
+  const float t = tanhf(c * (x + 0.044715f * x * x * x));
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * c * (1.0f + 3.0f * 0.044715f * x * x);
 }
 
 __global__ void act_grad_kernel(const float* __restrict__ g, const float* __restrict__ out, long long V, int H,
@@ -38,7 +45,8 @@ __global__ void act_grad_kernel(const float* __restrict__ g, const float* __rest
       const float n = (float)max(cnt, 1);
       s = 1.f / (row_norm == 1 ? n : sqrtf(n));
     }
-    dz[i] = g[i] * act_grad_from_output(out[i], act) * s;
+    // for gelu `out` holds the recomputed pre-activation
+    dz[i] = g[i] * (act == TFGNN_ACT_GELU ? gelu_grad_from_input(out[i]) : act_grad_from_output(out[i], act)) * s;
   }
 }
 
@@ -275,7 +283,6 @@ extern "C" int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* b, tfgnn_batch_t* bt, const fl
     return unsupported("rgcn_bwd: activation-before-aggregation is not built yet");
   const bool use_target = flags & TFGNN_FLAG_USE_TARGET_STATE;   // W_l is then [2D, H]: rows [0,D) source, [D,2D) target
   if (aggregation == TFGNN_AGG_MAX) return unsupported("rgcn_bwd: max aggregation is not built yet");
-  if (activation == TFGNN_ACT_GELU) return unsupported("rgcn_bwd: gelu needs the pre-activation (not saved)");
   if (D % 4 != 0 || H % 4 != 0) return unsupported("rgcn_bwd needs D and H to be multiples of 4");
   if (V == 0) return 0;
   TFGNN_REQUIRE(h && out && grad_out, "NULL pointer");
@@ -305,7 +312,15 @@ extern "C" int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* b, tfgnn_batch_t* bt, const fl
   rc = batch_scratch(b, 9, (size_t)chunks * K * H * sizeof(float), &part);
   if (rc) return rc;
 
-  // 1. dZ = dOut * act'(out) * rn(v)
+  // 1. dZ = dOut * act'(out) * rn(v)   (gelu: act'(pre-activation), recomputed by the forward kernel without activation)
+  if (activation == TFGNN_ACT_GELU) {
+    void* z = nullptr;
+    rc = batch_scratch(b, 12, (size_t)V * H * sizeof(float), &z);
+    if (rc) return rc;
+    rc = edge_mlp_core(b, h, D, W, 0, H, flags, aggregation, TFGNN_ACT_NONE, TFGNN_PATH_AUTO, (float*)z, H, st);
+    if (rc) return rc;
+    out = (const float*)z;
+  }
   act_grad_kernel<<<grid_cap(V * H), 256, 0, st>>>(grad_out, out, V, H, activation, b->row_ptr, L,
                                                    agg_row_norm(aggregation), (float*)dz);
   TFGNN_LAUNCH_CHECK();
