@@ -1,6 +1,5 @@
 """Host-side logic of the on-device batch builder (no GPU): processed-layout sizes against the pinned adjacency oracle
 and the reference's golden cases, the tie / type-count helpers, the greedy batching rule."""
-import ctypes
 import json
 import os
 from ctypes import byref, c_int32, c_int64

@@ -6,7 +6,6 @@ No arithmetic of the message-passing path is done with torch ops.
 """
 from __future__ import annotations
 
-import ctypes
 import weakref
 from ctypes import byref, c_int32, c_int64, c_void_p
 from typing import List, Optional, Sequence, Tuple

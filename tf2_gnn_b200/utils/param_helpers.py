@@ -8,7 +8,7 @@ from typing import Optional
 import torch
 
 from .. import _ffi
-from ..runtime import require_cuda, stream_ptr, to_device_f32
+from ..runtime import stream_ptr, to_device_f32
 
 
 class AggregationFn:
