@@ -32,6 +32,12 @@ extern "C" {
 #endif
 
 #define TFGNN_B200_ABI_VERSION 1
+/* The library is built with -fvisibility=hidden: only the entry points declared here are exported. */
+#if defined(__GNUC__)
+#define TFGNN_API __attribute__((visibility("default")))
+#else
+#define TFGNN_API
+#endif
 #define TFGNN_MAX_EDGE_TYPES 32
 
 typedef struct tfgnn_batch tfgnn_batch_t;
@@ -70,8 +76,8 @@ enum {
   TFGNN_PREPARE_TRANSPOSE = 1u << 1 /* key the CSR by SOURCE: the edge list of the backward pass (messages flow tgt->src) */
 };
 
-int tfgnn_b200_abi_version(void);
-const char* tfgnn_b200_last_error(void);
+TFGNN_API int tfgnn_b200_abi_version(void);
+TFGNN_API const char* tfgnn_b200_last_error(void);
 
 /* Per-batch preprocessing, reused by every layer of the stack (the adjacency is layer-invariant:
  * gnn.py:278,301).  Builds, per edge type, the edges sorted by target (CSR keyed by
@@ -81,7 +87,7 @@ const char* tfgnn_b200_last_error(void);
  *   num_edges  host array of L edge counts (may be 0: graph_dataset.py:244)
  * Edges whose src or tgt lies outside [0,V) are dropped; with TFGNN_PREPARE_VALIDATE the call
  * synchronises the stream and returns TFGNN_ERR_INDEX_OUT_OF_RANGE instead. */
-int tfgnn_b200_prepare(const int32_t* const* adj, const int64_t* num_edges, int32_t num_edge_types,
+TFGNN_API int tfgnn_b200_prepare(const int32_t* const* adj, const int64_t* num_edges, int32_t num_edge_types,
                        int64_t num_nodes, uint32_t prepare_flags, tfgnn_batch_t** out_batch,
                        void* stream);
 /* Target-range shard of ONE graph too large for a GPU: this batch owns the targets
@@ -89,25 +95,25 @@ int tfgnn_b200_prepare(const int32_t* const* adj, const int64_t* num_edges, int3
  * whole edge list (edges into other shards are skipped) or a pre-filtered one; ids stay GLOBAL.
  * Layer calls on such a batch take the full source table h[num_nodes_total, D] (all-gathered over the
  * ranks once per layer) and write out[target_count, H]; target-side reads use rows target_begin+v. */
-int tfgnn_b200_prepare_sharded(const int32_t* const* adj, const int64_t* num_edges,
+TFGNN_API int tfgnn_b200_prepare_sharded(const int32_t* const* adj, const int64_t* num_edges,
                                int32_t num_edge_types, int64_t num_nodes_total, int64_t target_begin,
                                int64_t target_count, uint32_t prepare_flags, tfgnn_batch_t** out_batch,
                                void* stream);
-int tfgnn_b200_free_batch(tfgnn_batch_t* batch);
+TFGNN_API int tfgnn_b200_free_batch(tfgnn_batch_t* batch);
 
 /* Introspection of the opaque batch (device pointers stay owned by the batch):
  * row_ptr int32[L*V+1], src_sorted int32[num_valid_edges]. */
-int tfgnn_b200_batch_info(const tfgnn_batch_t* batch, int64_t* num_nodes, int32_t* num_edge_types,
+TFGNN_API int tfgnn_b200_batch_info(const tfgnn_batch_t* batch, int64_t* num_nodes, int32_t* num_edge_types,
                           int64_t* num_edges_total, const int32_t** row_ptr,
                           const int32_t** src_sorted);
 
 /* Copy the CSR into caller-owned device buffers (row_ptr_out int32[L*V+1], src_sorted_out
  * int32[num_edges_total]); either may be NULL. */
-int tfgnn_b200_batch_export_csr(const tfgnn_batch_t* batch, int32_t* row_ptr_out,
+TFGNN_API int tfgnn_b200_batch_export_csr(const tfgnn_batch_t* batch, int32_t* row_ptr_out,
                                 int32_t* src_sorted_out, void* stream);
 
 /* calculate_type_to_num_incoming_edges (message_passing.py:230-263): out = float32[L, V]. */
-int tfgnn_b200_in_degree(const tfgnn_batch_t* batch, float* out, void* stream);
+TFGNN_API int tfgnn_b200_in_degree(const tfgnn_batch_t* batch, float* out, void* stream);
 
 /* GNN_Edge_MLP / RGCN forward (gnn_edge_mlp.py:84-107 + message_passing.py:95-218):
  *   out[v] = agg_{l, (u,v) in A_l} [ MLP_l(h_u [|| h_v]) / (c_{v,l}+1e-7) ]   with activation before
@@ -116,13 +122,13 @@ int tfgnn_b200_in_degree(const tfgnn_batch_t* batch, float* out, void* stream);
  *                [D_in, H] with D_in = D or 2D (rows [0,D) act on h_src, [D,2D) on h_tgt),
  *                further layers [H, H]; no biases (test_RGCN.py:35-39).
  *   h [V, D], out [V, H]. */
-int tfgnn_b200_edge_mlp_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
+TFGNN_API int tfgnn_b200_edge_mlp_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
                             const float* const* mlp_weights, int32_t num_hidden_layers, int32_t H,
                             uint32_t flags, int32_t aggregation, int32_t activation, int32_t path,
                             float* out, void* stream);
 
 /* RGCN convenience entry (rgcn.py:12-62): edge_mlp_fwd with 0 hidden layers, source state only. */
-int tfgnn_b200_rgcn_fwd(tfgnn_batch_t* batch, const float* h, int32_t D, const float* const* W,
+TFGNN_API int tfgnn_b200_rgcn_fwd(tfgnn_batch_t* batch, const float* h, int32_t D, const float* const* W,
                         int32_t H, uint32_t flags, int32_t aggregation, int32_t activation,
                         int32_t path, float* out, void* stream);
 
@@ -132,7 +138,7 @@ int tfgnn_b200_rgcn_fwd(tfgnn_batch_t* batch, const float* h, int32_t D, const f
  * Supported: sum/mean/sqrt_n aggregation, activation after aggregation, activations none/relu/tanh/leaky_relu/
  * elu/selu (derivative from the output) and gelu (pre-activation recomputed), source-only or source+target state input (W[l] = [D,H] or [2D,H],
  * TFGNN_FLAG_USE_TARGET_STATE); D and H multiples of 4. */
-int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* batch, tfgnn_batch_t* batch_t, const float* h, int32_t D,
+TFGNN_API int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* batch, tfgnn_batch_t* batch_t, const float* h, int32_t D,
                         const float* const* W, int32_t H, uint32_t flags, int32_t aggregation,
                         int32_t activation, const float* out, const float* grad_out, float* grad_h,
                         float* const* grad_W, void* stream);
@@ -141,7 +147,7 @@ int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* batch, tfgnn_batch_t* batch_t, const floa
  * normalised), aggregation, NO message activation, then Keras GRUCell(units=H, reset_after=True):
  * gru_kernel [H,3H] acts on the aggregated messages, gru_recurrent_kernel [H,3H] on the state h
  * (D == H required, ggnn.py:30), gru_bias [2,3H]; gate order z,r,h. */
-int tfgnn_b200_ggnn_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
+TFGNN_API int tfgnn_b200_ggnn_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
                         const float* const* mlp_weights, int32_t num_hidden_layers, int32_t H,
                         uint32_t flags, int32_t aggregation, const float* gru_kernel,
                         const float* gru_recurrent_kernel, const float* gru_bias, int32_t path,
@@ -152,7 +158,7 @@ int tfgnn_b200_ggnn_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
  * the TFGNN_PREPARE_TRANSPOSE batch of the same adjacency lists.  Writes grad_h [V,H], grad_W[l] [H,H],
  * grad_gru_kernel [H,3H], grad_gru_recurrent_kernel [H,3H], grad_gru_bias [2,3H].
  * Supported: 0 hidden layers in the message MLPs, source state only, sum / mean / sqrt_n aggregation, H % 4 == 0. */
-int tfgnn_b200_ggnn_bwd(tfgnn_batch_t* batch, tfgnn_batch_t* batch_t, const float* h, int32_t D,
+TFGNN_API int tfgnn_b200_ggnn_bwd(tfgnn_batch_t* batch, tfgnn_batch_t* batch_t, const float* h, int32_t D,
                         const float* const* W, int32_t H, uint32_t flags, int32_t aggregation,
                         const float* gru_kernel, const float* gru_recurrent_kernel, const float* gru_bias,
                         const float* grad_out, float* grad_h, float* const* grad_W, float* grad_gru_kernel,
@@ -160,7 +166,7 @@ int tfgnn_b200_ggnn_bwd(tfgnn_batch_t* batch, tfgnn_batch_t* batch_t, const floa
 
 /* RGIN (rgin.py:88-106): edge MLP messages, aggregation, optional aggregation MLP
  * (aggr_weights: host array of num_aggr_layers device pointers [H,H], may be NULL/0), activation. */
-int tfgnn_b200_rgin_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
+TFGNN_API int tfgnn_b200_rgin_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
                         const float* const* mlp_weights, int32_t num_hidden_layers, int32_t H,
                         uint32_t flags, int32_t aggregation, int32_t activation,
                         const float* const* aggr_weights, int32_t num_aggr_layers, int32_t path,
@@ -168,7 +174,7 @@ int tfgnn_b200_rgin_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
 
 /* GNN-FiLM (gnn_film.py:83-108): m = gamma_l(h_v) * EdgeMLP_l(...) + beta_l(h_v),
  * [gamma|beta] = h_v F_l, film_weights: host array of L device pointers [D, 2H] (no hidden layers). */
-int tfgnn_b200_film_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
+TFGNN_API int tfgnn_b200_film_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
                         const float* const* mlp_weights, int32_t num_hidden_layers,
                         const float* const* film_weights, int32_t H, uint32_t flags,
                         int32_t aggregation, int32_t activation, int32_t path, float* out,
@@ -176,14 +182,14 @@ int tfgnn_b200_film_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
 
 /* RGAT (rgat.py:91-163): per-type projection W_l [D,H], attention a_l [K, 2H/K]; softmax over all
  * incoming edges of all types jointly, per head; activation after. */
-int tfgnn_b200_rgat_fwd(tfgnn_batch_t* batch, const float* h, int32_t D, const float* const* W,
+TFGNN_API int tfgnn_b200_rgat_fwd(tfgnn_batch_t* batch, const float* h, int32_t D, const float* const* W,
                         const float* const* attention, int32_t H, int32_t num_heads,
                         int32_t activation, int32_t path, float* out, void* stream);
 
 /* Node-level dense layer out = act(x W), x [V,K], W [K,N], no bias — the op behind every
  * tf.keras.layers.Dense(use_bias=False) on the path (gnn.py:136-141,165-169) and the building
  * block of the fp32-accurate node-level contractions.  path: 0 auto, 2 SIMT fp32, 3 tcgen05 3xTF32. */
-int tfgnn_b200_dense_fwd(const float* x, const float* W, float* out, int64_t V, int32_t K, int32_t N,
+TFGNN_API int tfgnn_b200_dense_fwd(const float* x, const float* W, float* out, int64_t V, int32_t K, int32_t N,
                          int32_t activation, int32_t path, void* stream);
 
 /* The three stock ops of the reference's generic MessagePassing.call, for user-defined
@@ -192,20 +198,20 @@ int tfgnn_b200_dense_fwd(const float* x, const float* W, float* out, int64_t V, 
  *   unsorted_segment_reduce   tf.math.unsorted_segment_{sum,mean,max,sqrt_n}  :172-174
  *   activation                get_activation_function(...)      :169-177
  * ids / segment_ids are int32 with an element stride (2 addresses a column of an [E,2] list). */
-int tfgnn_b200_gather_rows(const float* table, int64_t num_rows, int32_t D, const int32_t* ids,
+TFGNN_API int tfgnn_b200_gather_rows(const float* table, int64_t num_rows, int32_t D, const int32_t* ids,
                            int64_t ids_stride, int64_t n, float* out, void* stream);
-int tfgnn_b200_unsorted_segment_reduce(const float* data, const int32_t* segment_ids,
+TFGNN_API int tfgnn_b200_unsorted_segment_reduce(const float* data, const int32_t* segment_ids,
                                        int64_t ids_stride, int64_t M, int32_t H,
                                        int64_t num_segments, int32_t aggregation, float* out,
                                        void* stream);
-int tfgnn_b200_activation(const float* x, int64_t n, int32_t activation, float* out, void* stream);
+TFGNN_API int tfgnn_b200_activation(const float* x, int64_t n, int32_t activation, float* out, void* stream);
 
 /* Node-level glue of GNN._internal_call around the message-passing layers (gnn.py:291-296,317-321):
  *   residual_average   out = (x + last) / 2                      gnn.py:294-295
  *   layer_norm         tf.keras.layers.LayerNormalization(axis=-1, epsilon) over each row  gnn.py:318-321
  * x, last, out: [V, H] contiguous; gamma, beta: [H]. */
-int tfgnn_b200_residual_average(const float* x, const float* last, float* out, int64_t n, void* stream);
-int tfgnn_b200_layer_norm(const float* x, const float* gamma, const float* beta, int64_t V, int32_t H,
+TFGNN_API int tfgnn_b200_residual_average(const float* x, const float* last, float* out, int64_t n, void* stream);
+TFGNN_API int tfgnn_b200_layer_norm(const float* x, const float* gamma, const float* beta, int64_t V, int32_t H,
                           float epsilon, float* out, void* stream);
 
 /* ---- On-device batch builder ------------------------------------------------------
@@ -222,11 +228,11 @@ int tfgnn_b200_layer_norm(const float* x, const float* gamma, const float* beta,
  *   adjacency_out        host array of num_types_out caller-allocated device lists, sizes as reported by _sizes
  *   type_to_num_incoming_edges  optional float32[num_types_out, V]: in-degree per processed type (:116-124; the
  *                        reference returns float64 of the same integer values) */
-int tfgnn_b200_process_adjacency_sizes(const int64_t* num_edges_fwd, int32_t num_fwd_types, int64_t num_nodes,
+TFGNN_API int tfgnn_b200_process_adjacency_sizes(const int64_t* num_edges_fwd, int32_t num_fwd_types, int64_t num_nodes,
                                        int32_t add_self_loop_edges, const int32_t* tied,
                                        int32_t self_loop_edge_type, int64_t* num_edges_out,
                                        int32_t* num_types_out);
-int tfgnn_b200_process_adjacency(const int32_t* const* adjacency_fwd, const int64_t* num_edges_fwd,
+TFGNN_API int tfgnn_b200_process_adjacency(const int32_t* const* adjacency_fwd, const int64_t* num_edges_fwd,
                                  int32_t num_fwd_types, int64_t num_nodes, int32_t add_self_loop_edges,
                                  const int32_t* tied, int32_t self_loop_edge_type,
                                  int32_t* const* adjacency_out, int32_t num_types_out,
@@ -244,16 +250,31 @@ int tfgnn_b200_process_adjacency(const int32_t* const* adjacency_fwd, const int6
  *   adjacency_lists      host array of T caller-allocated device lists [num_edges_in_batch[t], 2]: stored pairs plus
  *                        the running node count of their graph (:218-222)
  *   workspace            device, tfgnn_b200_assemble_batch_workspace_bytes(T, num_graphs_in_batch) bytes */
-size_t tfgnn_b200_assemble_batch_workspace_bytes(int32_t num_edge_types, int32_t num_graphs_in_batch);
-int tfgnn_b200_assemble_batch(const int64_t* node_offsets, const int64_t* const* edge_offsets,
+TFGNN_API size_t tfgnn_b200_assemble_batch_workspace_bytes(int32_t num_edge_types, int32_t num_graphs_in_batch);
+TFGNN_API int tfgnn_b200_assemble_batch(const int64_t* node_offsets, const int64_t* const* edge_offsets,
                               const int32_t* const* edges, int32_t num_edge_types, int64_t num_graphs_total,
                               const int32_t* graph_ids, int32_t num_graphs_in_batch,
                               int64_t num_nodes_in_batch, const int64_t* num_edges_in_batch,
                               int32_t* node_to_graph_map, int32_t* node_source_rows,
                               int32_t* const* adjacency_lists, void* workspace, void* stream);
 
+/* ---- Device-global state --------------------------------------------------------------------------------------
+ * Two things in this library outlive a call and are shared with the host framework's CUDA context:
+ *   (1) the fused RGCN kernel keeps its hand-off ring and the packed weights resident in L2 with evict_last hints,
+ *       which only bind inside a persisting-L2 carve-out.  The first fused launch on a device therefore saves the
+ *       current cudaLimitPersistingL2CacheSize and raises it to `megabytes` (default 72; never lowered if the host
+ *       already reserves more).  set_l2_persist_mb(0) opts out (results identical, ~4 GB more HBM traffic per cfg2
+ *       layer); -1 returns to the default / TFGNN_B200_L2_PERSIST_MB.
+ *   (2) a private stream-ordered memory pool (cudaMemPool) that caches the library's own buffers.
+ * tfgnn_b200_release_device_state() restores the saved L2 limit on every device and trims the pool; the Python
+ * shim registers it with atexit.
+ * Threading: entry points are re-entrant; ONE tfgnn_batch_t must not be used by two host threads or on two
+ * streams at the same time (it may move to another stream between calls: the library orders the streams). */
+TFGNN_API int tfgnn_b200_set_l2_persist_mb(int32_t megabytes);
+TFGNN_API int tfgnn_b200_release_device_state(void);
+
 /* Number of kernels this library has launched in the calling process (all threads). */
-int64_t tfgnn_b200_launch_count(void);
+TFGNN_API int64_t tfgnn_b200_launch_count(void);
 
 #ifdef __cplusplus
 }

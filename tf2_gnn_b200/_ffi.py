@@ -32,7 +32,7 @@ EXPORTED_SYMBOLS = (
     "tfgnn_b200_activation", "tfgnn_b200_residual_average", "tfgnn_b200_layer_norm",
     "tfgnn_b200_process_adjacency_sizes", "tfgnn_b200_process_adjacency",
     "tfgnn_b200_assemble_batch_workspace_bytes", "tfgnn_b200_assemble_batch",
-    "tfgnn_b200_launch_count",
+    "tfgnn_b200_launch_count", "tfgnn_b200_set_l2_persist_mb", "tfgnn_b200_release_device_state",
 )
 
 _PP = POINTER(c_void_p)
@@ -96,6 +96,8 @@ def lib() -> ctypes.CDLL:
     L.tfgnn_b200_assemble_batch_workspace_bytes.restype = ctypes.c_size_t
     L.tfgnn_b200_assemble_batch.argtypes = [c_void_p, _PP, _PP, c_int32, c_int64, c_void_p, c_int32, c_int64,
                                             POINTER(c_int64), c_void_p, c_void_p, _PP, c_void_p, c_void_p]
+    L.tfgnn_b200_set_l2_persist_mb.argtypes = [c_int32]
+    L.tfgnn_b200_release_device_state.argtypes = []
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is ctypes.c_int and name not in ("tfgnn_b200_abi_version",):
@@ -103,7 +105,19 @@ def lib() -> ctypes.CDLL:
     if L.tfgnn_b200_abi_version() != 1:
         raise RuntimeError("libtfgnn_b200.so ABI version mismatch; rebuild with python -m tf2_gnn_b200.build")
     _lib = L
+    import atexit
+    atexit.register(_release_device_state)
     return L
+
+
+def _release_device_state() -> None:
+    """Restore the persisting-L2 limit the fused kernel raised and trim the library's memory pool
+    (include/tfgnn_b200.h, "Device-global state")."""
+    try:
+        if _lib is not None:
+            _lib.tfgnn_b200_release_device_state()
+    except Exception:
+        pass
 
 
 def check(rc: int) -> None:

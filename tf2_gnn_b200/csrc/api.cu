@@ -160,6 +160,10 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
   const int V = (int)b->V, L = b->L;
   const int Vs = (int)b->V_src;                           // rows of the source table h
   if (V == 0) return 0;
+  {
+    const int rc_enter = batch_enter(b, st);
+    if (rc_enter) return rc_enter;
+  }
   TFGNN_REQUIRE(h != nullptr && out != nullptr, "h / out is NULL");
   TFGNN_REQUIRE(L == 0 || mlp_weights != nullptr, "mlp_weights is NULL");
   const float* h_tgt = h + (size_t)b->tgt_off * D;        // rows of the targets owned by this batch
@@ -348,6 +352,12 @@ using namespace tfgnn;
 extern "C" int tfgnn_b200_abi_version(void) { return TFGNN_B200_ABI_VERSION; }
 extern "C" const char* tfgnn_b200_last_error(void) { return t_last_error.c_str(); }
 extern "C" int64_t tfgnn_b200_launch_count(void) { return g_launch_count.load(); }
+extern "C" int tfgnn_b200_set_l2_persist_mb(int32_t megabytes) { return set_l2_persist_mb(megabytes); }
+extern "C" int tfgnn_b200_release_device_state(void) {
+  restore_l2_persist_carveout();
+  pool_trim_all();
+  return 0;
+}
 
 extern "C" int tfgnn_b200_edge_mlp_fwd(tfgnn_batch_t* batch, const float* h, int32_t D,
                                        const float* const* mlp_weights, int32_t num_hidden_layers, int32_t H,
@@ -376,10 +386,11 @@ extern "C" int tfgnn_b200_dense_fwd(const float* x, const float* W, float* out, 
   const bool want_tc = path == TFGNN_PATH_AUTO || path == TFGNN_PATH_SORTED_TC || path == TFGNN_PATH_FUSED_TC;
   if (want_tc && gemm_tc_supported(V, N, K, x, K, out, N)) {
     void* packed = nullptr;
-    TFGNN_CUDA(cudaMallocAsync(&packed, gemm_tc_packed_bytes(N, K), st));
-    int rc = launch_pack_weights_tc(W, N, K, N, (float*)packed, st);
+    int rc = pool_alloc(&packed, gemm_tc_packed_bytes(N, K), st);
+    if (rc) return rc;
+    rc = launch_pack_weights_tc(W, N, K, N, (float*)packed, st);
     if (!rc) rc = launch_gemm_tc(x, K, (const float*)packed, out, N, V, N, K, epi, st);
-    cudaFreeAsync(packed, st);
+    pool_free(packed, st);
     return rc;
   }
   if (path == TFGNN_PATH_SORTED_TC)

@@ -302,7 +302,22 @@ extern "C" int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* b, tfgnn_batch_t* bt, const fl
     gwt.p[l] = grad_W[l];
   }
   void *dz = nullptr, *A = nullptr, *WT = nullptr, *part = nullptr;
-  int rc = batch_scratch(b, 8, (size_t)V * H * sizeof(float), &dz);
+  int rc = batch_enter(b, st);
+  if (rc) return rc;
+  rc = batch_enter(bt, st);
+  if (rc) return rc;
+  // 1a. gelu: act'(pre-activation).  The pre-activation is recomputed by the forward kernel without activation
+  // BEFORE any other scratch pointer of this function is taken: the nested forward call may re-grow (= free and
+  // re-allocate) the slots it shares with this function (2, 3, 6), which would leave them dangling.
+  if (activation == TFGNN_ACT_GELU) {
+    void* z = nullptr;
+    rc = batch_scratch(b, 12, (size_t)V * H * sizeof(float), &z);
+    if (rc) return rc;
+    rc = edge_mlp_core(b, h, D, W, 0, H, flags, aggregation, TFGNN_ACT_NONE, TFGNN_PATH_AUTO, (float*)z, H, st);
+    if (rc) return rc;
+    out = (const float*)z;
+  }
+  rc = batch_scratch(b, 8, (size_t)V * H * sizeof(float), &dz);
   if (rc) return rc;
   rc = batch_scratch(b, 2, (size_t)V * K * sizeof(float), &A);     // A (forward operand), then dA
   if (rc) return rc;
@@ -312,15 +327,7 @@ extern "C" int tfgnn_b200_rgcn_bwd(tfgnn_batch_t* b, tfgnn_batch_t* bt, const fl
   rc = batch_scratch(b, 9, (size_t)chunks * K * H * sizeof(float), &part);
   if (rc) return rc;
 
-  // 1. dZ = dOut * act'(out) * rn(v)   (gelu: act'(pre-activation), recomputed by the forward kernel without activation)
-  if (activation == TFGNN_ACT_GELU) {
-    void* z = nullptr;
-    rc = batch_scratch(b, 12, (size_t)V * H * sizeof(float), &z);
-    if (rc) return rc;
-    rc = edge_mlp_core(b, h, D, W, 0, H, flags, aggregation, TFGNN_ACT_NONE, TFGNN_PATH_AUTO, (float*)z, H, st);
-    if (rc) return rc;
-    out = (const float*)z;
-  }
+  // 1b. dZ = dOut * act'(out) * rn(v)
   act_grad_kernel<<<grid_cap(V * H), 256, 0, st>>>(grad_out, out, V, H, activation, b->row_ptr, L,
                                                    agg_row_norm(aggregation), (float*)dz);
   TFGNN_LAUNCH_CHECK();
@@ -408,7 +415,11 @@ extern "C" int tfgnn_b200_ggnn_bwd(tfgnn_batch_t* b, tfgnn_batch_t* bt, const fl
   const int chunks = (int)((V + kTnChunk - 1) / kTnChunk);
   void *agg = nullptr, *gx = nullptr, *gh = nullptr, *dagg = nullptr, *wT = nullptr, *part = nullptr, *dhd = nullptr,
        *tmp = nullptr;
-  int rc = batch_scratch(b, 11, (size_t)V * H * sizeof(float), &agg);
+  int rc = batch_enter(b, st);
+  if (rc) return rc;
+  rc = batch_enter(bt, st);
+  if (rc) return rc;
+  rc = batch_scratch(b, 11, (size_t)V * H * sizeof(float), &agg);
   if (rc) return rc;
   rc = batch_scratch(b, 12, (size_t)V * N3 * sizeof(float), &gx);
   if (rc) return rc;

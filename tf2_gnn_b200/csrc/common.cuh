@@ -121,9 +121,15 @@ struct tfgnn_batch {
   // caller-owned adjacency (kept for the TFGNN_PATH_ATOMIC evidence path only)
   const int32_t* adj[TFGNN_MAX_EDGE_TYPES] = {};
   long long E[TFGNN_MAX_EDGE_TYPES] = {};
-  // grow-only scratch owned by the batch
+  // grow-only scratch owned by the batch (stream-ordered allocations from the library's private pool, mempool.cu)
   void* scratch[16] = {};
   size_t scratch_bytes[16] = {};
+  // the stream the batch was last used on: allocations / frees of its buffers are ordered on it.  A batch may move
+  // between streams from one call to the next (batch_enter orders the new stream after the old one), but it must
+  // not be used from two streams or two host threads at the same time.
+  cudaStream_t cur_stream = nullptr;
+  bool used = false;
+  cudaEvent_t ev_switch = nullptr;
   // internal fork/join streams of the gather || node-GEMM pipeline (created lazily)
   static constexpr int kPipeBufs = 3;
   bool pipe_ready = false;
@@ -133,6 +139,12 @@ struct tfgnn_batch {
 };
 
 namespace tfgnn {
-// Returns a device scratch buffer of at least `bytes` in slot `slot` of the batch.
+// Returns a device scratch buffer of at least `bytes` in slot `slot` of the batch (valid on b->cur_stream).
 int batch_scratch(tfgnn_batch* b, int slot, size_t bytes, void** out);
+// Every entry point that takes a batch calls this first: binds the batch to `st` for this call.
+int batch_enter(tfgnn_batch* b, cudaStream_t st);
+// Stream-ordered device memory from the library's PRIVATE cudaMemPool (release threshold = keep everything:
+// after the first batches no call on the per-batch path reaches cudaMalloc / cudaFree or synchronises).
+int pool_alloc(void** p, size_t bytes, cudaStream_t st);
+void pool_free(void* p, cudaStream_t st);
 }  // namespace tfgnn

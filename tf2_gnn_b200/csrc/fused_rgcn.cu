@@ -613,6 +613,67 @@ bool fused_rgcn_supported(long long V, int L, int D, int H, const float* h, cons
   return gemm_tc_supported(V, H, L * D, h, D, out, ldo) && fu_encode_fn() != nullptr;
 }
 
+// ---- device-global state: the persisting-L2 carve-out ---------------------------------------------------------
+// cudaLimitPersistingL2CacheSize is a property of the DEVICE CONTEXT the host framework shares with this library, so
+// it is handled explicitly (include/tfgnn_b200.h, "Device-global state"): the first fused launch on a device saves
+// the current limit and raises it to the configured size (default 72 MB: ring + packed weights);
+// tfgnn_b200_set_l2_persist_mb(0) / TFGNN_B200_L2_PERSIST_MB=0 opt out (the kernel stays correct, the ring then
+// spills ~4 GB per layer to HBM at cfg2); tfgnn_b200_release_device_state() restores the saved limit.
+static std::mutex g_l2_mu;
+static int g_l2_want_mb = -1;                 // -1: default / environment
+static bool g_l2_set[64] = {};
+static size_t g_l2_saved[64] = {};
+
+int set_l2_persist_mb(int mb) {
+  std::lock_guard<std::mutex> lock(g_l2_mu);
+  g_l2_want_mb = mb;
+  for (bool& b : g_l2_set) b = false;         // re-applied by the next fused launch
+  return 0;
+}
+
+static int ensure_l2_persist_carveout() {
+  int dev = 0;
+  TFGNN_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return 0;
+  std::lock_guard<std::mutex> lock(g_l2_mu);
+  if (g_l2_set[dev]) return 0;
+  g_l2_set[dev] = true;
+  long long want_mb = g_l2_want_mb;
+  if (want_mb < 0) {
+    const char* e = getenv("TFGNN_B200_L2_PERSIST_MB");
+    want_mb = e ? atoi(e) : 72;
+  }
+  if (want_mb <= 0) return 0;
+  int max_persist = 0;
+  if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess || max_persist <= 0) {
+    cudaGetLastError();
+    return 0;
+  }
+  size_t want = (size_t)want_mb << 20;
+  if (want > (size_t)max_persist) want = (size_t)max_persist;
+  size_t cur = 0;
+  if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cur >= want) return 0;                  // the host already reserves at least as much: leave it alone
+  g_l2_saved[dev] = cur + 1;                  // +1: "saved" marker (0 = nothing to restore)
+  cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
+  cudaGetLastError();
+  return 0;
+}
+
+void restore_l2_persist_carveout() {
+  std::lock_guard<std::mutex> lock(g_l2_mu);
+  int cur_dev = 0;
+  if (cudaGetDevice(&cur_dev) != cudaSuccess) { cudaGetLastError(); return; }
+  for (int d = 0; d < 64; ++d) {
+    if (!g_l2_saved[d]) continue;
+    if (cudaSetDevice(d) == cudaSuccess) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, g_l2_saved[d] - 1);
+    g_l2_saved[d] = 0;
+    g_l2_set[d] = false;
+  }
+  cudaSetDevice(cur_dev);
+  cudaGetLastError();
+}
+
 constexpr int kFuMaxGrid = 160;
 static int fused_num_slots(int L, int H) {
   static const int env_slots = [] { const char* e = getenv("TFGNN_B200_RING_SLOTS"); return e ? atoi(e) : 0; }();
@@ -724,19 +785,10 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   const int nv = (D + 127) / 128;
   // L2 set-aside for the evict_last (persisting) lines: the ring + the packed weights.  Without a carve-out
   // the evict_last hint is advisory only and the ring gets written back to HBM (measured: +4 GB/layer).
-  static std::once_flag l2_once;
-  std::call_once(l2_once, [&] {
-    int dev2 = 0, max_persist = 0;
-    if (cudaGetDevice(&dev2) == cudaSuccess &&
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev2) == cudaSuccess &&
-        max_persist > 0) {
-      size_t want = (size_t)72 << 20;
-      if (const char* e = getenv("TFGNN_B200_L2_PERSIST_MB")) want = (size_t)atoi(e) << 20;
-      if (want > (size_t)max_persist) want = (size_t)max_persist;
-      if (want > 0) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
-    }
-    cudaGetLastError();
-  });
+  {
+    const int rc_l2 = ensure_l2_persist_carveout();
+    if (rc_l2) return rc_l2;
+  }
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {

@@ -33,6 +33,10 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
                       const float* packedB, int H, float* ring, float* out, int ldo, const GemmEpilogue& epi,
                       cudaStream_t st);
 
+int set_l2_persist_mb(int mb);
+void restore_l2_persist_carveout();
+void pool_trim_all();
+
 // Weight packing helpers: gather per-type matrices into one node-level operand.
 //  vertical:   dst[(blk*rows + r), :] = src_blk[row0 + r, :]          (aggregate-then-transform)
 //  horizontal: dst[r, blk*cols + c]  = src_blk[row0 + r, c]           (transform-then-aggregate)

@@ -30,8 +30,10 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, long long nu
 }
 
 __device__ __forceinline__ void atomic_max_float(float* addr, float val) {
-  // total order trick: positive floats compare like ints, negative floats reversed as uints
-  if (val >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(val));
+  // total order trick: positive floats compare like ints, negative floats reversed as uints.  The branch is on
+  // the SIGN BIT, not on val >= 0: -0.0f has the bit pattern 0x80000000 = INT_MIN, which atomicMax(int) would
+  // never store over the -FLT_MAX identity (a segment holding only -0.0 must return -0.0, not -3.4e38).
+  if (__float_as_int(val) >= 0) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(val));
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(val));
 }
 
@@ -137,7 +139,8 @@ extern "C" int tfgnn_b200_unsorted_segment_reduce(const float* data, const int32
   TFGNN_LAUNCH_CHECK();
   int* counts = nullptr;
   if (need_counts) {
-    TFGNN_CUDA(cudaMallocAsync(&counts, (size_t)num_segments * sizeof(int), st));
+    int rc = pool_alloc((void**)&counts, (size_t)num_segments * sizeof(int), st);
+    if (rc) return rc;
     TFGNN_CUDA(cudaMemsetAsync(counts, 0, (size_t)num_segments * sizeof(int), st));
   }
   if (M > 0) {
@@ -150,7 +153,7 @@ extern "C" int tfgnn_b200_unsorted_segment_reduce(const float* data, const int32
     segment_norm_kernel<<<grid_for(num_segments * H), 256, 0, st>>>(out, counts, num_segments, H,
                                                                    aggregation == TFGNN_AGG_MEAN ? 1 : 2);
     TFGNN_LAUNCH_CHECK();
-    TFGNN_CUDA(cudaFreeAsync(counts, st));
+    pool_free(counts, st);
   }
   return 0;
 }

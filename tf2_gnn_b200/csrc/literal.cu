@@ -127,7 +127,9 @@ int edge_mlp_literal(tfgnn_batch* b, const float* h, int D, const float* const* 
   for (int l = 0; l < L; ++l) maxE = b->E[l] > maxE ? b->E[l] : maxE;
   const int wide = D_in > H ? D_in : H;
   void *X0 = nullptr, *X1 = nullptr, *tgt_of = nullptr;
-  int rc = batch_scratch(b, 2, (size_t)maxE * wide * sizeof(float), &X0);
+  int rc = batch_enter(b, st);
+  if (rc) return rc;
+  rc = batch_scratch(b, 2, (size_t)maxE * wide * sizeof(float), &X0);
   if (rc) return rc;
   rc = batch_scratch(b, 5, (size_t)maxE * wide * sizeof(float), &X1);
   if (rc) return rc;

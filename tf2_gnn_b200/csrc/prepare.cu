@@ -227,18 +227,6 @@ __global__ void in_degree_kernel(const int* __restrict__ row_ptr, long long num_
     out[s] = (float)(row_ptr[s + 1] - row_ptr[s]);
 }
 
-int batch_scratch(tfgnn_batch* b, int slot, size_t bytes, void** out) {
-  if (b->scratch_bytes[slot] < bytes) {
-    if (b->scratch[slot]) TFGNN_CUDA(cudaFree(b->scratch[slot]));
-    b->scratch[slot] = nullptr;
-    b->scratch_bytes[slot] = 0;
-    TFGNN_CUDA(cudaMalloc(&b->scratch[slot], bytes));
-    b->scratch_bytes[slot] = bytes;
-  }
-  *out = b->scratch[slot];
-  return 0;
-}
-
 int exclusive_scan_inplace(int* data, long long n, int* block_sums_scratch, cudaStream_t st) {
   const int nb = ceil_div(n, kScanTile);
   scan_reduce_kernel<<<nb, kScanThreads, 0, st>>>(data, n, block_sums_scratch);
@@ -295,9 +283,10 @@ static int prepare_impl(const int32_t* const* adj, const int64_t* num_edges, int
 #define TRY_CUDA(expr) TRY(check_cuda((expr), #expr, __FILE__, __LINE__))
 
   TRY_CUDA(cudaGetDevice(&b->device));
-  TRY_CUDA(cudaMalloc(&b->row_ptr, (size_t)(S + 1) * sizeof(int)));
-  TRY_CUDA(cudaMalloc(&b->src_sorted, (size_t)(M > 0 ? M : 1) * sizeof(int)));
-  TRY_CUDA(cudaMalloc(&b->invalid_count, sizeof(int)));
+  TRY(batch_enter(b, st));
+  TRY(pool_alloc((void**)&b->row_ptr, (size_t)(S + 1) * sizeof(int), st));
+  TRY(pool_alloc((void**)&b->src_sorted, (size_t)(M > 0 ? M : 1) * sizeof(int), st));
+  TRY(pool_alloc((void**)&b->invalid_count, sizeof(int), st));
   TRY_CUDA(cudaMemsetAsync(b->row_ptr, 0, (size_t)(S + 1) * sizeof(int), st));
   TRY_CUDA(cudaMemsetAsync(b->invalid_count, 0, sizeof(int), st));
 
@@ -384,10 +373,12 @@ extern "C" int tfgnn_b200_prepare_sharded(const int32_t* const* adj, const int64
 
 extern "C" int tfgnn_b200_free_batch(tfgnn_batch_t* b) {
   if (!b) return 0;
-  cudaFree(b->row_ptr);
-  cudaFree(b->src_sorted);
-  cudaFree(b->invalid_count);
-  for (int i = 0; i < 16; ++i) cudaFree(b->scratch[i]);
+  // stream-ordered frees behind the last work enqueued for this batch: no device synchronisation
+  pool_free(b->row_ptr, b->cur_stream);
+  pool_free(b->src_sorted, b->cur_stream);
+  pool_free(b->invalid_count, b->cur_stream);
+  for (int i = 0; i < 16; ++i) pool_free(b->scratch[i], b->cur_stream);
+  if (b->ev_switch) cudaEventDestroy(b->ev_switch);
   if (b->pipe_ready) {
     cudaStreamDestroy(b->pipe_gather);
     cudaStreamDestroy(b->pipe_gemm);

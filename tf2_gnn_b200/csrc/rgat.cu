@@ -21,7 +21,7 @@ constexpr int kHubChunk = 1024;
 __device__ __forceinline__ float rgat_leaky(float x) { return x > 0.f ? x : kLeakyReluAlpha * x; }
 
 __device__ __forceinline__ void rgat_atomic_max(float* addr, float val) {
-  if (val >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(val));
+  if (__float_as_int(val) >= 0) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(val));   // sign bit: -0.0f goes to the atomicMin branch
   else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(val));
 }
 

@@ -38,7 +38,9 @@ extern "C" int tfgnn_b200_ggnn_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   TFGNN_REQUIRE(gru_kernel && gru_recurrent_kernel && gru_bias, "GRU weight pointer is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   void *agg = nullptr, *gx = nullptr, *gh = nullptr;
-  int rc = batch_scratch(b, 8, (size_t)V * H * sizeof(float), &agg);
+  int rc = batch_enter(b, st);
+  if (rc) return rc;
+  rc = batch_scratch(b, 8, (size_t)V * H * sizeof(float), &agg);
   if (rc) return rc;
   rc = batch_scratch(b, 9, (size_t)V * 3 * H * sizeof(float), &gx);
   if (rc) return rc;
@@ -80,7 +82,9 @@ extern "C" int tfgnn_b200_rgin_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   TFGNN_REQUIRE(aggr_weights != nullptr, "aggr_weights is NULL");
   if (V == 0) return 0;
   void *t0 = nullptr, *t1 = nullptr;
-  int rc = batch_scratch(b, 8, (size_t)V * H * sizeof(float), &t0);
+  int rc = batch_enter(b, st);
+  if (rc) return rc;
+  rc = batch_scratch(b, 8, (size_t)V * H * sizeof(float), &t0);
   if (rc) return rc;
   rc = batch_scratch(b, 9, (size_t)V * H * sizeof(float), &t1);
   if (rc) return rc;
@@ -132,7 +136,9 @@ extern "C" int tfgnn_b200_film_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   const int Vs = (int)b->V_src;
   const float* h_tgt = h + (size_t)b->tgt_off * D;
   void *P = nullptr, *Tt = nullptr, *Wcat = nullptr, *FB = nullptr, *Fcat = nullptr;
-  int rc = batch_scratch(b, 2, (size_t)Vs * LH * sizeof(float), &P);
+  int rc = batch_enter(b, st);
+  if (rc) return rc;
+  rc = batch_scratch(b, 2, (size_t)Vs * LH * sizeof(float), &P);
   if (rc) return rc;
   rc = batch_scratch(b, 3, (size_t)D * LH * sizeof(float), &Wcat);
   if (rc) return rc;
@@ -287,7 +293,8 @@ extern "C" int tfgnn_b200_rgat_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
     at.p[l] = attention[l];
   }
   void *P = nullptr, *Wcat = nullptr, *ss = nullptr, *stt = nullptr;
-  int rc;
+  int rc = batch_enter(b, st);
+  if (rc) return rc;
   if (L > 0) {
     rc = batch_scratch(b, 2, (size_t)Vs * LH * sizeof(float), &P);
     if (rc) return rc;
