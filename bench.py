@@ -46,6 +46,9 @@ WORKLOADS = {
                  desc="GGNN QM9-shaped 500k nodes / 1.5M edges / 5 edge types, hidden_dim=128 (BASELINE.json configs[3])"),
     "cfg5_shard": dict(V=2_000_000, E=[5_333_333] * 6, H=320, kind="gnn_film", graph="er",
                        desc="GNN-FiLM 1/8 shard of BASELINE.json configs[4]: 2M nodes / 32M edges / 6 edge types, hidden_dim=320"),
+    "cfg5": dict(V=16_000_000, E=[42_666_666] * 6, H=320, kind="gnn_film", graph="er",
+                 desc="GNN-FiLM synthetic 16M nodes / 256M edges / 6 edge types, hidden_dim=320, target-range sharded over "
+                      "8 GPUs with one all-gather per layer (BASELINE.json configs[4]; sharded leg only)"),
     "h320": dict(V=1_000_000, E=[6_666_667] * 3, H=320, kind="rgcn", graph="er",
                  desc="RGCN synthetic Erdos-Renyi 1M nodes / 20M edges / 3 edge types, hidden_dim=320 "
                       "(north_star hidden size on a graph that exceeds L2)"),
@@ -94,14 +97,20 @@ def make_inputs(wl, seed):
 
 
 def load_traffic(workload, path):
-    """Measured DRAM bytes per launch of the dominant kernel (one ncu --set full capture, profiles/traffic_r1.json)."""
-    p = os.path.join(ROOT, "profiles", "traffic_r1.json")
-    try:
-        with open(p) as f:
-            e = json.load(f).get(f"{workload}:{path}")
-        return None if e is None else int(e["dram_bytes_read"]) + int(e["dram_bytes_write"])
-    except Exception:
-        return None
+    """DRAM bytes per launch of the dominant kernel.  NOT measured in this run (ncu replays kernels; a number printed
+    under a profiler is never a bench value): a STATIC figure from the committed ncu --set full capture of the same
+    command, labelled with the file and the commit it was taken at.  (None, reason) when no capture exists."""
+    for fname in ("traffic_r2.json", "traffic_r1.json"):
+        p = os.path.join(ROOT, "profiles", fname)
+        try:
+            with open(p) as f:
+                e = json.load(f).get(f"{workload}:{path}")
+        except Exception:
+            continue
+        if e is not None:
+            src = f"static, from {e.get('source', 'profiles/' + fname)} @ {e.get('commit', 'round-1 kernel')}"
+            return int(e["dram_bytes_read"]) + int(e["dram_bytes_write"]), src
+    return None, "no ncu --set full capture committed for this workload/path"
 
 
 def load_peaks():
@@ -337,6 +346,271 @@ def reference_arm(args, wl, rank, world):
 
 
 # -------------------------------------------------------------------------------------------
+KERNEL_OF = {
+    "rgcn": "fused_rgcn_kernel (gather ring -> TMA -> 3xTF32 tcgen05.mma cta_group::2 -> epilogue) + 2 weight-pack kernels",
+    "ggnn": "fused_rgcn_kernel (messages) + gemm_tc_kernel x2 (GRU gates) + gru_gate_kernel",
+    "rgat": "gemm_tc_kernel (P = h W) + rgat_scores_kernel + rgat_warp_kernel / hub kernels (segment softmax + weighted sum)",
+    "gnn_film": "edge_reduce_kernel (A_l) + gemm_tc_kernel (FiLM parameters, messages) with the modulation in the GEMM epilogue",
+}
+
+
+def build_layer(wl, rank, path="auto"):
+    import torch
+    from tf2_gnn_b200.layers import MessagePassingInput, get_message_passing_class
+    kind, H, L = wl["kind"], wl["H"], len(wl["E"])
+    layer_cls = get_message_passing_class(kind)
+    params = layer_cls.get_default_hyperparameters()
+    params.update(wl.get("params", {}))
+    params.update(hidden_dim=H, b200_path=path)
+    layer = layer_cls(params)
+    torch.manual_seed(1234 + rank)
+    layer.build(MessagePassingInput((None, H), tuple((None, 2) for _ in range(L))))  # Glorot-uniform weights
+    return layer, params
+
+
+class L2Flusher:
+    """Writes a buffer larger than the 126 MB L2 between timed iterations (workloads whose inputs fit L2)."""
+
+    def __init__(self, dev, nbytes=256 << 20):
+        import torch
+        self.buf = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+
+    def __call__(self):
+        self.buf.fill_(1.0)
+
+
+def time_device_resident(layer, inp, prepared, steps, warmup, flush=None):
+    """ms per layer call with inputs resident in HBM: CUDA events on the launching stream.  With `flush`, every
+    iteration is timed on its own (the flush runs outside the event pair) and the times are summed."""
+    import torch
+    for _ in range(warmup):
+        out = layer(inp, prepared=prepared)
+    torch.cuda.synchronize()
+    if flush is None:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record()
+        for i in range(steps):
+            out = layer(inp, prepared=prepared)
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+        return ev[0].elapsed_time(ev[-1]), per_step, out
+    per_step = []
+    for i in range(steps):
+        flush()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = layer(inp, prepared=prepared)
+        e1.record()
+        torch.cuda.synchronize()
+        per_step.append(e0.elapsed_time(e1))
+    return float(sum(per_step)), per_step, out
+
+
+def time_e2e(layer, h_host, adj_host, out_host, steps, world, depth=2):
+    """The public call with HOST buffers: every step copies its node states + adjacency lists from pinned host memory,
+    builds the per-batch CSR, runs the layer and copies the new node states back to pinned host memory.  Steps are
+    software-pipelined `depth` deep on CUDA streams (runtime.HostPipeline): D2H of step i overlaps H2D of step i+1."""
+    import torch
+    from tf2_gnn_b200.layers import MessagePassingInput
+    from tf2_gnn_b200.runtime import HostPipeline
+    host_inp = MessagePassingInput(h_host, tuple(adj_host))
+    outs = [out_host] + [torch.empty_like(out_host).pin_memory() for _ in range(depth - 1)]
+    pipe = HostPipeline(lambda b: layer(b), depth=depth)
+    for i in range(2 * depth):
+        pipe.submit(host_inp, outs[i % depth])
+    pipe.drain()
+    torch.cuda.synchronize()
+    barrier(world)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        pipe.submit(host_inp, outs[i % depth])
+    pipe.drain()
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0, world)
+    return dt
+
+
+def measure_workload(name, args, rank, world, local, dev, headline):
+    """One workload: device-resident layer time (+ roofline), optional e2e.  Returns a dict."""
+    import torch
+    from tf2_gnn_b200 import _ffi
+    from tf2_gnn_b200.layers import MessagePassingInput
+    from tf2_gnn_b200.runtime import PreparedBatch
+    wl = WORKLOADS[name]
+    V, H, L = wl["V"], wl["H"], len(wl["E"])
+    M = sum(wl["E"])
+    kind = wl["kind"]
+    h_np, adjs_np, w_np = make_inputs(wl, seed=rank)
+    h_host = torch.from_numpy(h_np).pin_memory()
+    adj_host = [torch.from_numpy(a).pin_memory() for a in adjs_np]
+    layer, params = build_layer(wl, rank, args.path)
+    if kind == "rgcn":
+        layer.set_weights_from_oracle_dict({"edge_mlps": [[w] for w in w_np]})
+    h_dev = h_host.to(dev)
+    adj_dev = tuple(a.to(dev) for a in adj_host)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    prepared = PreparedBatch(adj_dev, V)
+    torch.cuda.synchronize()
+    prepare_first_ms = (time.perf_counter() - t0) * 1e3
+    # steady-state prepare (pool warm): CUDA events around a second build of the same CSR
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    prepared2 = PreparedBatch(adj_dev, V)
+    e1.record()
+    torch.cuda.synchronize()
+    prepare_wall_ms = (time.perf_counter() - t0) * 1e3
+    prepare_dev_ms = e0.elapsed_time(e1)
+    del prepared2
+    inp = MessagePassingInput(h_dev, adj_dev)
+    fits_l2 = V * H * 4 <= 126e6
+    flush = L2Flusher(dev) if fits_l2 else None
+    sampler = ClockSampler(local)
+    if headline and rank == 0 and not args.no_clock_sampler:
+        sampler.start()          # before the warm-up, so the poller is running when the timed region starts
+    time_device_resident(layer, inp, prepared, 0, args.warmup, None)
+    barrier(world)
+    launches0 = _ffi.launch_count()
+    sampler.begin()
+    total_ms, per_step, out = time_device_resident(layer, inp, prepared, args.steps, 0, flush)
+    sampler.end()
+    barrier(world)
+    launches = _ffi.launch_count() - launches0
+    total_ms = max_over_ranks(total_ms, world)
+    clocks = sampler.stop() if (headline and rank == 0) else None
+    ms_per_step = total_ms / args.steps
+    res = {"workload": wl["desc"], "nodes": V, "edges": M, "edge_types": L, "hidden_dim": H, "kind": kind,
+           "ms_per_layer": ms_per_step, "edges_per_s": world * M / (ms_per_step * 1e-3),
+           "step_ms_min_max": [min(per_step), max(per_step)], "gpu_launches": int(launches),
+           "prepare_ms": prepare_dev_ms, "prepare_wall_ms": prepare_wall_ms, "prepare_first_call_ms": prepare_first_ms,
+           "l2": ("flushed between timed iterations (256 MB write): node table fits the 126 MB L2" if fits_l2
+                  else "no flush needed: node table exceeds the 126 MB L2"),
+           "clocks": clocks}
+    peak, peak_src = load_peaks()
+    alg = algorithmic_bytes(kind, V, wl["E"], H, H, params)
+    achieved = alg / (ms_per_step * 1e-3) / 1e9
+    traffic, traffic_src = load_traffic(name, args.path)
+    res["roofline"] = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                       "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                       "algorithmic_bytes_per_step": alg, "frac_of_nominal_8TBs": achieved / 8000.0,
+                       "kernel": KERNEL_OF.get(kind, kind)}
+    if not args.skip_e2e:
+        out_host = torch.empty((V, H), dtype=torch.float32).pin_memory()
+        e2e_steps = max(4, min(args.steps, 10))
+        dt = time_e2e(layer, h_host, adj_host, out_host, e2e_steps, world, depth=2)
+        res["e2e"] = {"value": world * M * e2e_steps / dt, "unit": "edges/s",
+                      "h2d_bytes_per_step": int(h_host.numel() * 4 + sum(a.numel() * 4 for a in adj_host)),
+                      "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps,
+                      "ms_per_step": dt / e2e_steps * 1e3, "pipeline_depth": 2,
+                      "what": "public layer call on pinned HOST buffers: H2D(node states + adjacency) -> CSR prepare -> "
+                              "layer -> D2H(new node states) every step; steps software-pipelined 2 deep on CUDA streams "
+                              "(runtime.HostPipeline), wall clock over all steps"}
+    res["_inputs"] = (h_np, adjs_np, w_np)
+    return res
+
+
+def measure_sharded(args, rank, world, local, dev):
+    """SURVEY.md §8e case 2 under the bench clock: ONE graph (cfg2) strong-scaled over the N ranks by target range, one
+    all-gather of the node-state shards per layer (NCCL over NVLink), checked against the unsharded layer on rank 0's rows."""
+    import torch
+    import torch.distributed as dist
+    from tf2_gnn_b200.layers import MessagePassingInput
+    from tf2_gnn_b200.runtime import PreparedBatch
+    results = {}
+    jobs = [("cfg2_strong", "cfg2")]
+    if world == 8:
+        jobs.append(("cfg5_full", "cfg5"))
+    for key, name in jobs:
+      try:
+          wl = WORKLOADS[name]
+          V, H, L = wl["V"], wl["H"], len(wl["E"])
+          M = sum(wl["E"])
+          if V % (world * 128) != 0:
+              V = V // (world * 128) * (world * 128)   # equal shards on 128-row tile boundaries
+          rows = V // world
+          lo, hi = rank * rows, (rank + 1) * rows
+          layer, params = build_layer(wl, 0, args.path)            # same weights on every rank
+          gen = torch.Generator(device=dev)
+          gen.manual_seed(99)
+          if name == "cfg5":
+              # each rank generates ITS shard of the ER graph directly: targets uniform in its range, sources uniform in
+              # [0, V) (the full 256M-edge list never exists in one place); node states generated on the device
+              g2 = torch.Generator(device=dev)
+              g2.manual_seed(1000 + rank)
+              adj_dev = []
+              for E in wl["E"]:
+                  e_loc = E // world
+                  src = torch.randint(0, V, (e_loc,), generator=g2, device=dev, dtype=torch.int32)
+                  tgt = torch.randint(lo, hi, (e_loc,), generator=g2, device=dev, dtype=torch.int32)
+                  adj_dev.append(torch.stack([src, tgt], dim=1).contiguous())
+              adj_dev = tuple(adj_dev)
+              h_local = torch.rand((rows, H), generator=g2, device=dev) * 2 - 1
+              m_total = sum(int(a.shape[0]) for a in adj_dev) * world
+              full_check = None
+          else:
+              h_np, adjs_np, w_np = make_inputs(dict(wl, V=V), seed=0)   # the SAME graph on every rank
+              if wl["kind"] == "rgcn":
+                  layer.set_weights_from_oracle_dict({"edge_mlps": [[w] for w in w_np]})
+              adj_dev = tuple(torch.from_numpy(a).to(dev) for a in adjs_np)
+              h_local = torch.from_numpy(h_np[lo:hi]).to(dev)
+              m_total = M
+              full_check = (h_np, adjs_np)
+          shard = PreparedBatch(adj_dev, V, target_range=(lo, hi))
+          h_full = torch.empty((V, H), dtype=torch.float32, device=dev)
+
+          def step():
+              dist.all_gather_into_tensor(h_full, h_local)          # the one collective of the layer
+              return layer(MessagePassingInput(h_full, adj_dev), prepared=shard)
+
+          for _ in range(max(3, args.warmup)):
+              out_local = step()
+          torch.cuda.synchronize()
+          barrier(world)
+          n_it = args.steps
+          ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+          # all-gather alone, layer alone, both (device time, max over ranks)
+          ev[0].record()
+          for _ in range(n_it):
+              dist.all_gather_into_tensor(h_full, h_local)
+          ev[1].record()
+          torch.cuda.synchronize()
+          ag_ms = max_over_ranks(ev[0].elapsed_time(ev[1]) / n_it, world)
+          barrier(world)
+          ev[0].record()
+          for _ in range(n_it):
+              out_local = step()
+          ev[1].record()
+          torch.cuda.synchronize()
+          tot_ms = max_over_ranks(ev[0].elapsed_time(ev[1]) / n_it, world)
+          ag_bytes = (world - 1) * rows * H * 4
+          rec = {"workload": wl["desc"], "nodes": V, "edges": m_total, "target_rows_per_rank": rows,
+                 "ms_per_layer": tot_ms, "edges_per_s": m_total / (tot_ms * 1e-3), "allgather_ms": ag_ms,
+                 "allgather_bytes_received_per_rank": ag_bytes,
+                 "allgather_GBps_per_rank": ag_bytes / (ag_ms * 1e-3) / 1e9 if ag_ms > 0 else None,
+                 "overlap": "none: all_gather_into_tensor of the [V/N, H] shards, then the layer on the rank's target range",
+                 "scaling": "strong"}
+          if full_check is not None and rank == 0:
+              h_np, adjs_np = full_check
+              full = PreparedBatch(adj_dev, V)
+              ref = layer(MessagePassingInput(torch.from_numpy(h_np).to(dev), adj_dev), prepared=full)
+              mine = out_local
+              diff = (ref[lo:hi] - mine).abs().max().item()
+              rec["check"] = {"what": "rank 0's target rows of the sharded layer vs the unsharded layer on the same GPU",
+                              "bitwise_equal": bool(torch.equal(ref[lo:hi], mine)), "max_abs_diff": diff,
+                              "max_abs_ref": ref.abs().max().item()}
+              del full, ref
+          results[key] = rec
+          del shard, h_full, adj_dev, h_local, out_local
+          torch.cuda.empty_cache()
+          barrier(world)
+      except Exception as e:   # same shapes on every rank: a failure (e.g. out of memory) is collective
+        results[key] = {"workload": WORKLOADS[name]["desc"], "error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+    return results
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -347,6 +621,8 @@ def main():
     ap.add_argument("--path", default="auto")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-secondary", action="store_true", help="headline workload only")
+    ap.add_argument("--skip-sharded", action="store_true", help="N > 1: no target-range sharded leg")
     ap.add_argument("--no-clock-sampler", action="store_true", help="do not poll nvidia-smi during the run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -362,97 +638,32 @@ def main():
     rank, world, local = dist_setup(args.gpus)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback exists)")
-    from tf2_gnn_b200 import _ffi
     from tf2_gnn_b200.build import build_library
-    from tf2_gnn_b200.layers import MessagePassingInput, get_message_passing_class
-    from tf2_gnn_b200.runtime import PreparedBatch
     build_library()
     dev = torch.device("cuda", torch.cuda.current_device())
 
-    V, H, L = wl["V"], wl["H"], len(wl["E"])
-    M = sum(wl["E"])
-    h_np, adjs_np, w_np = make_inputs(wl, seed=rank)
-    # pinned host buffers (the e2e leg copies from / to these every step)
-    h_host = torch.from_numpy(h_np).pin_memory()
-    adj_host = [torch.from_numpy(a).pin_memory() for a in adjs_np]
-    out_host = torch.empty((V, H), dtype=torch.float32).pin_memory()
+    head = measure_workload(args.workload, args, rank, world, local, dev, headline=True)
+    h_np, adjs_np, w_np = head.pop("_inputs")
+    V, H, L, M, kind = head["nodes"], head["hidden_dim"], head["edge_types"], head["edges"], head["kind"]
 
-    kind = wl["kind"]
-    layer_cls = get_message_passing_class(kind)
-    params = layer_cls.get_default_hyperparameters()
-    params.update(wl.get("params", {}))
-    params.update(hidden_dim=H, b200_path=args.path)
-    layer = layer_cls(params)
-    torch.manual_seed(1234 + rank)
-    layer.build(MessagePassingInput((None, H), tuple((None, 2) for _ in range(L))))  # Glorot-uniform weights
-    if kind == "rgcn":
-        layer.set_weights_from_oracle_dict({"edge_mlps": [[w] for w in w_np]})
+    # ---- secondary workloads in the same run (north_star: hidden_dim 320; PPI-shaped batch) ----
+    secondary = {}
+    if not args.skip_secondary and args.workload == "cfg2" and world == 1:
+        for name in ("h320", "cfg1"):
+            torch.cuda.empty_cache()
+            r = measure_workload(name, args, rank, world, local, dev, headline=False)
+            r.pop("_inputs")
+            r.pop("clocks")
+            secondary[name] = r
 
-    # ---- device-resident leg -------------------------------------------------------------
-    h_dev = h_host.to(dev)
-    adj_dev = tuple(a.to(dev) for a in adj_host)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    prepared = PreparedBatch(adj_dev, V)
-    torch.cuda.synchronize()
-    prepare_ms = (time.perf_counter() - t0) * 1e3
-    inp = MessagePassingInput(h_dev, adj_dev)
-    sampler = ClockSampler(local)
-    if rank == 0 and not args.no_clock_sampler:
-        sampler.start()          # before the warm-up, so the poller is running when the timed region starts
-    for _ in range(args.warmup):
-        out = layer(inp, prepared=prepared)
-    torch.cuda.synchronize()
-    barrier(world)
-    launches0 = _ffi.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    torch.cuda.synchronize()
-    sampler.begin()
-    ev[0].record()
-    for i in range(args.steps):
-        out = layer(inp, prepared=prepared)
-        ev[i + 1].record()
-    torch.cuda.synchronize()
-    sampler.end()
-    barrier(world)
-    launches = _ffi.launch_count() - launches0
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    total_ms = max_over_ranks(total_ms, world)
-    clocks = sampler.stop() if rank == 0 else None
-    ms_per_step = total_ms / args.steps
-    value = world * M * args.steps / (total_ms * 1e-3)
-
-    # ---- end-to-end leg: public API with host buffers ------------------------------------
-    e2e = None
-    if not args.skip_e2e:
-        host_inp = MessagePassingInput(h_host, tuple(adj_host))
-        e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(2):
-            o = layer(host_inp)
-            out_host.copy_(o, non_blocking=True)
-        torch.cuda.synchronize()
-        barrier(world)
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            o = layer(host_inp)               # H2D of h + adjacency, prepare (CSR), layer
-            out_host.copy_(o, non_blocking=True)  # D2H of the new node states
-            torch.cuda.synchronize()
-        dt = max_over_ranks(time.perf_counter() - t0, world)
-        e2e = {"value": world * M * e2e_steps / dt, "unit": "edges/s",
-               "h2d_bytes_per_step": int(h_host.numel() * 4 + sum(a.numel() * 4 for a in adj_host)),
-               "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps,
-               "ms_per_step": dt / e2e_steps * 1e3}
+    # ---- target-range sharded leg (N > 1) --------------------------------------------------
+    sharded = None
+    if world > 1 and not args.skip_sharded and args.workload == "cfg2":
+        torch.cuda.empty_cache()
+        sharded = measure_sharded(args, rank, world, local, dev)
 
     if rank != 0:
         return
-    # ---- roofline: algorithmic bytes of the layer over its device time ---------------------
-    peak, peak_src = load_peaks()
-    alg = algorithmic_bytes(kind, V, wl["E"], H, H, params)
-    achieved = alg / (ms_per_step * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": load_traffic(args.workload, args.path), "peak_source": peak_src, "algorithmic_bytes_per_step": alg,
-                "kernel": "whole layer call (for RGCN at H<=256: fused_rgcn_kernel + 2 weight-pack kernels); see profiles/"}
     cpu = None
     if not args.skip_cpu_baseline and kind == "rgcn":
         threads, _, host_cores = best_cpu_threads(wl, h_np, adjs_np, w_np)
@@ -462,15 +673,19 @@ def main():
                          f"torch-CPU restatement of the reference op order (TensorFlow absent); fastest thread "
                          f"count on a {host_cores}-core host"}
     line = {
-        "metric": METRIC, "value": value, "unit": "edges/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": head["edges_per_s"], "unit": "edges/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": head["ms_per_layer"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "nodes": V, "edges": M, "edge_types": L, "hidden_dim": H,
+        "config": {"workload": head["workload"], "nodes": V, "edges": M, "edge_types": L, "hidden_dim": H,
                    "layers_per_step": 1, "path": args.path, "inputs_exceed_l2": V * H * 4 > 126e6,
-                   "l2_flush": "not needed: 1 GB node table >> 126 MB L2" if V * H * 4 > 126e6 else "none (fits L2)",
-                   "parallelism": f"dp{world} (independent batches, no collective)", "prepare_ms": prepare_ms},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "step_ms_min_max": [min(per_step), max(per_step)],
+                   "l2_flush": head["l2"],
+                   "parallelism": f"dp{world} (independent batches of disjoint graphs, no collective; the target-range "
+                                  f"sharded path is reported under 'sharded')",
+                   "prepare_ms": head["prepare_ms"], "prepare_wall_ms": head["prepare_wall_ms"],
+                   "prepare_first_call_ms": head["prepare_first_call_ms"]},
+        "roofline": head["roofline"], "cpu_baseline": cpu, "e2e": head.get("e2e"),
+        "gpu_launches": head["gpu_launches"], "clocks": head["clocks"], "step_ms_min_max": head["step_ms_min_max"],
+        "secondary": secondary or None, "sharded": sharded,
     }
     print(json.dumps(line), flush=True)
 

@@ -55,7 +55,9 @@ enum { TFGNN_AGG_SUM = 0, TFGNN_AGG_MEAN = 1, TFGNN_AGG_MAX = 2, TFGNN_AGG_SQRT_
 /* tf2_gnn/utils/param_helpers.py:22-42 ; activation.py:7-14 */
 enum {
   TFGNN_ACT_NONE = 0, TFGNN_ACT_RELU = 1, TFGNN_ACT_TANH = 2, TFGNN_ACT_LEAKY_RELU = 3,
-  TFGNN_ACT_ELU = 4, TFGNN_ACT_SELU = 5, TFGNN_ACT_GELU = 6
+  TFGNN_ACT_ELU = 4, TFGNN_ACT_SELU = 5, TFGNN_ACT_GELU = 6,
+  TFGNN_ACT_SIGMOID = 7 /* not in the reference's name table: tf.nn.sigmoid of the readout weights,
+                           nodes_to_graph_representation.py:174-175 */
 };
 /* layer flags */
 enum {
@@ -213,6 +215,56 @@ TFGNN_API int tfgnn_b200_activation(const float* x, int64_t n, int32_t activatio
 TFGNN_API int tfgnn_b200_residual_average(const float* x, const float* last, float* out, int64_t n, void* stream);
 TFGNN_API int tfgnn_b200_layer_norm(const float* x, const float* gamma, const float* beta, int64_t V, int32_t H,
                           float epsilon, float* out, void* stream);
+
+/* ---- Training-time node-level glue (the reference differentiates gnn.py:279-327 with
+ * tf.GradientTape, models/graph_task_model.py:338-365) -------------------------------------------------------------
+ *   dense_bwd        backward of out = act(x W + bias): grad_x [V,K] (or NULL), grad_W [K,N] (or NULL), grad_bias [N] (or
+ *                    NULL); `out` is the saved forward output (gelu recomputes the pre-activation)
+ *   layer_norm_bwd   backward of tfgnn_b200_layer_norm: grad_x (or NULL), grad_gamma, grad_beta (fixed-order column sums)
+ *   dropout          tf.nn.dropout(x, rate): out = x * mask / (1 - rate), mask ~ Bernoulli(1 - rate) from Philox4x32-10
+ *                    keyed by (seed, offset + element index / 4).  Deterministic per (seed, offset); the backward pass is
+ *                    the same call on the incoming gradient.  (TensorFlow's own stream cannot be reproduced: parity of
+ *                    training-time dropout is distributional.)
+ *   axpby            out = alpha * a + beta * b (b NULL: alpha * a): residual average and its backward */
+TFGNN_API int tfgnn_b200_dense_bwd(const float* x, const float* W, const float* bias, const float* out, const float* grad_out,
+                                   int64_t V, int32_t K, int32_t N, int32_t activation, float* grad_x, float* grad_W,
+                                   float* grad_bias, void* stream);
+TFGNN_API int tfgnn_b200_layer_norm_bwd(const float* x, const float* gamma, const float* grad_out, int64_t V, int32_t H,
+                                        float epsilon, float* grad_x, float* grad_gamma, float* grad_beta, void* stream);
+TFGNN_API int tfgnn_b200_dropout(const float* x, int64_t n, float rate, uint64_t seed, uint64_t offset, float* out,
+                                 void* stream);
+TFGNN_API int tfgnn_b200_axpby(const float* a, float alpha, const float* b, float beta, int64_t n, float* out, void* stream);
+
+/* ---- Graph-level readout and global exchange ---------------------------------------------
+ * Segment primitives keyed by node_to_graph_map, which is non-decreasing (graph_dataset.py:211-217; the reference's own
+ * tf.math.segment_sum requires it), so a graph is the contiguous row range graph_ptr[g] .. graph_ptr[g+1].
+ *   graph_offsets          node_to_graph_map int32[V] -> graph_ptr int32[G+1]; validate != 0 synchronises the stream and
+ *                          returns TFGNN_ERR_INVALID_ARGUMENT for ids that decrease or fall outside [0, G)
+ *   segment_softmax        scores [V,K] -> weights [V,K]: per (graph, head) exp((s - max) - log(sum exp(s - max)))
+ *                          = dpu_utils unsorted_segment_softmax          nodes_to_graph_representation.py:176-186
+ *   weighted_segment_sum   out[g, k*d+c] = sum_{v in g} weights[v,k] * node_reprs[v, k*d+c], d = repr_dim/num_heads
+ *                          (weights NULL: plain tf.math.segment_sum; mean != 0: segment_mean)      :204-227
+ *   gathered_add           out[v,:] = act((a[v,:] + b[index[v],:]) * scale); index NULL = identity
+ *                          (mean exchange (x + g[n2g]) / 2, graph_global_exchange.py:124; hidden layer of the MLP exchange)
+ *   gru_gate_fwd           Keras GRUCell(reset_after=True) gate math on precomputed gx = inputs K + b0 (rows picked by
+ *                          gx_row_index, NULL = identity) and gh = h U + b1        graph_global_exchange.py:147-152
+ *   clamp                  in-place transformation_mlp_result_{lower,upper}_bound   nodes_to_graph_representation.py:194-197
+ *   dense_bias_fwd         out = act(x W + bias) (bias [N] or NULL)                 MLPs with use_biases, GRU halves */
+TFGNN_API int tfgnn_b200_graph_offsets(const int32_t* node_to_graph_map, int64_t num_nodes, int32_t num_graphs,
+                                       int32_t* graph_ptr, int32_t validate, void* stream);
+TFGNN_API int tfgnn_b200_segment_softmax(const float* scores, const int32_t* graph_ptr, int32_t num_graphs,
+                                         int32_t num_heads, float* out, void* stream);
+TFGNN_API int tfgnn_b200_weighted_segment_sum(const float* node_reprs, const float* weights, const int32_t* graph_ptr,
+                                              int32_t num_graphs, int32_t repr_dim, int32_t num_heads, int32_t mean,
+                                              float* out, void* stream);
+TFGNN_API int tfgnn_b200_gathered_add(const float* a, const float* b, const int32_t* index, int64_t num_rows, int32_t H,
+                                      float scale, int32_t activation, float* out, void* stream);
+TFGNN_API int tfgnn_b200_gru_gate_fwd(const float* gx, const int32_t* gx_row_index, const float* gh, const float* h,
+                                      int64_t num_rows, int32_t H, float* out, void* stream);
+TFGNN_API int tfgnn_b200_clamp(float* x, int64_t n, float lower, float upper, int32_t has_lower, int32_t has_upper,
+                               void* stream);
+TFGNN_API int tfgnn_b200_dense_bias_fwd(const float* x, const float* W, const float* bias, float* out, int64_t V, int32_t K,
+                                        int32_t N, int32_t activation, int32_t path, void* stream);
 
 /* ---- On-device batch builder ------------------------------------------------------
  * Bit-exact int32 bookkeeping of the data layer, so that a training loop never leaves the device between the

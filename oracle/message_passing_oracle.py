@@ -374,8 +374,115 @@ def make_weights(kind: str, params: Dict[str, Any], D: int, L: int, rng: np.rand
 
 
 # --------------------------------------------------------------------------------------
-# GNN stack, inference mode (gnn.py:276-329).  Global exchange layers are not restated
-# (disabled by every PPI config: global_exchange_every_num_layers = 10000).
+# Graph readout and global exchange (nodes_to_graph_representation.py:170-229,
+# graph_global_exchange.py:83-183).  PARITY UNPINNED (no reference test holds a value; dpu_utils.MLP and
+# unsorted_segment_softmax are external) until tests/golden/tf_layers_golden.json exists (tools/gen_tf_golden.py).
+# --------------------------------------------------------------------------------------
+def dense_mlp_forward(x: np.ndarray, kernels: Sequence[np.ndarray], biases: Optional[Sequence[np.ndarray]] = None,
+                      activation=None) -> np.ndarray:
+    """dpu_utils.tf2utils.MLP with an arbitrary hidden activation and optional biases (the readout MLPs:
+    nodes_to_graph_representation.py:128-148): hidden Dense layers with `activation`, linear output layer."""
+    act = activation or (lambda v: np.maximum(v, v.dtype.type(0)))
+    cur = x
+    n = len(kernels)
+    for i, w in enumerate(kernels):
+        cur = cur @ w
+        if biases is not None and biases[i] is not None:
+            cur = cur + biases[i]
+        if i < n - 1:
+            cur = act(cur)
+    return cur
+
+
+def unsorted_segment_softmax(logits, segment_ids, num_segments):
+    """dpu_utils.tf2utils.unsorted_segment_softmax = exp(unsorted_segment_log_softmax) [external]."""
+    return np.exp(unsorted_segment_log_softmax(logits, segment_ids, num_segments))
+
+
+def weighted_sum_graph_representation(node_embeddings, node_to_graph_map, num_graphs, weights: Dict[str, Any],
+                                      graph_representation_size: int, num_heads: int, weighting_fun: str = "softmax",
+                                      scoring_activation: str = "relu", transformation_activation: str = "relu",
+                                      lower_bound: Optional[float] = None, upper_bound: Optional[float] = None,
+                                      dtype=np.float32) -> np.ndarray:
+    """WeightedSumGraphRepresentation.call, inference mode (nodes_to_graph_representation.py:170-229).
+    weights: {"scoring_mlp": [kernels], "transformation_mlp": [kernels], optional "scoring_biases",
+    "transformation_biases"}.  Returns [num_graphs, GD] (the reference's tf.math.segment_sum returns
+    max(id)+1 rows: identical whenever the last graph of the batch has a node, which graph_dataset.py guarantees)."""
+    x = np.asarray(node_embeddings, dtype=dtype)
+    ids = np.asarray(node_to_graph_map).astype(np.int64)
+    G, GD, K = int(num_graphs), int(graph_representation_size), int(num_heads)
+    weighting_fun = weighting_fun.lower()
+
+    def cast(ws):
+        return None if ws is None else [None if w is None else np.asarray(w, dtype=dtype) for w in ws]
+
+    w = None
+    if weighting_fun not in ("none", "average"):                                   # :172-188
+        scores = dense_mlp_forward(x, cast(weights["scoring_mlp"]), cast(weights.get("scoring_biases")),
+                                   get_activation_function(scoring_activation))   # [V, K]
+        if weighting_fun == "sigmoid":
+            w = _sigmoid(scores).astype(dtype)
+        elif weighting_fun == "softmax":
+            w = np.stack([unsorted_segment_softmax(scores[:, k], ids, G) for k in range(K)], axis=1).astype(dtype)
+        else:
+            raise ValueError()
+    t_act = get_activation_function(transformation_activation)
+    reprs = t_act(dense_mlp_forward(x, cast(weights["transformation_mlp"]),
+                                    cast(weights.get("transformation_biases")), t_act))  # :191-193
+    if lower_bound is not None:
+        reprs = np.maximum(reprs, dtype(lower_bound))
+    if upper_bound is not None:
+        reprs = np.minimum(reprs, dtype(upper_bound))
+    if weighting_fun == "none":                                                     # :204-210
+        return unsorted_segment_sum(reprs, ids, G)
+    if weighting_fun == "average":                                                  # :211-217
+        cnt = np.maximum(np.bincount(ids, minlength=G), 1).astype(dtype)
+        return unsorted_segment_sum(reprs, ids, G) / cnt[:, None]
+    reprs = reprs.reshape(-1, K, GD // K) * w[:, :, None]                           # :219-220
+    return unsorted_segment_sum(reprs.reshape(-1, GD), ids, G)                      # :222-227
+
+
+def graph_global_exchange(mode: str, node_embeddings, node_to_graph_map, num_graphs, weights: Dict[str, Any],
+                          hidden_dim: int, num_heads: int, weighting_fun: str = "softmax", dtype=np.float32):
+    """GraphGlobal{Mean,GRU,MLP}Exchange.call, inference mode (graph_global_exchange.py:83-183).
+    weights: the readout's {"scoring_mlp", "transformation_mlp"} + gru: "gru_kernel", "gru_recurrent_kernel",
+    "gru_bias"; mlp: "mlp" (kernels of MLP(out_size=H) on [graph repr || node state])."""
+    x = np.asarray(node_embeddings, dtype=dtype)
+    ids = np.asarray(node_to_graph_map).astype(np.int64)
+    g = weighted_sum_graph_representation(x, ids, num_graphs, weights, hidden_dim, num_heads, weighting_fun,
+                                          dtype=dtype)                              # :84-92
+    per_node = g[ids]                                                               # :94-96 gather_dense_gradient
+    mode = mode.lower()
+    if mode == "mean":
+        return (x + per_node) / dtype(2)                                            # :124
+    if mode == "gru":                                                               # :147-152
+        return gru_cell_forward(per_node, x, np.asarray(weights["gru_kernel"], dtype=dtype),
+                                np.asarray(weights["gru_recurrent_kernel"], dtype=dtype),
+                                np.asarray(weights["gru_bias"], dtype=dtype)).astype(dtype)
+    if mode == "mlp":                                                               # :176-181
+        return mlp_forward(np.concatenate([per_node, x], axis=-1), [np.asarray(w, dtype=dtype) for w in weights["mlp"]])
+    raise ValueError(f"Unknown global_exchange_mode mode {mode}")
+
+
+def make_exchange_weights(mode: str, hidden_dim: int, num_heads: int, rng: np.random.Generator,
+                          weighting_fun: str = "softmax", dtype=np.float32) -> Dict[str, Any]:
+    """Shapes as GraphGlobalExchange.build creates them (graph_global_exchange.py:46-58,138-140,167-169):
+    scoring MLP [H -> H -> num_heads], transformation MLP [H -> 128 -> H] (the class default layer list), no biases."""
+    H = hidden_dim
+    w: Dict[str, Any] = {"transformation_mlp": [glorot_uniform(rng, (H, 128), dtype), glorot_uniform(rng, (128, H), dtype)]}
+    if weighting_fun.lower() in ("softmax", "sigmoid"):
+        w["scoring_mlp"] = [glorot_uniform(rng, (H, H), dtype), glorot_uniform(rng, (H, num_heads), dtype)]
+    if mode.lower() == "gru":
+        w["gru_kernel"] = glorot_uniform(rng, (H, 3 * H), dtype)
+        w["gru_recurrent_kernel"] = glorot_uniform(rng, (H, 3 * H), dtype)
+        w["gru_bias"] = rng.uniform(-0.1, 0.1, size=(2, 3 * H)).astype(dtype)
+    if mode.lower() == "mlp":
+        w["mlp"] = [glorot_uniform(rng, (2 * H, H), dtype), glorot_uniform(rng, (H, H), dtype)]
+    return w
+
+
+# --------------------------------------------------------------------------------------
+# GNN stack, inference mode (gnn.py:276-329), including the global exchange layers.
 # --------------------------------------------------------------------------------------
 def layer_norm(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, epsilon: float = 1e-3) -> np.ndarray:
     """tf.keras.layers.LayerNormalization() defaults (axis=-1, epsilon=1e-3) [external Keras]."""
@@ -385,9 +492,10 @@ def layer_norm(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, epsilon: floa
 
 
 def gnn_forward(params: Dict[str, Any], weights: Dict[str, Any], node_features: np.ndarray,
-                adjacency_lists: Sequence[np.ndarray], dtype=np.float32):
+                adjacency_lists: Sequence[np.ndarray], dtype=np.float32,
+                node_to_graph_map: Optional[np.ndarray] = None, num_graphs: Optional[int] = None):
     """weights: {"initial_projection": [F,H], "mp": [per-layer message-passing weight dicts],
-    "dense": {layer_idx: [H,H]}, "layernorm": [(gamma, beta) per layer]}.
+    "dense": {layer_idx: [H,H]}, "layernorm": [(gamma, beta) per layer], "exchange": {layer_idx: exchange weights}}.
     Returns (final representations, tuple of all representations) like GNN._internal_call."""
     kind = params["message_calculation_class"].lower()
     act_init = get_activation_function(params["initial_node_representation_activation"])
@@ -404,12 +512,16 @@ def gnn_forward(params: Dict[str, Any], weights: Dict[str, Any], node_features: 
             last = tmp
         cur = message_passing_forward(kind, params, weights["mp"][i], cur, adjacency_lists, dtype=dtype)
         all_reps.append(cur)                                              # gnn.py:305
-        if i and i % int(params["global_exchange_every_num_layers"]) == 0:
-            raise NotImplementedError("global exchange is outside the restated path")
+        if i and i % int(params["global_exchange_every_num_layers"]) == 0:   # gnn.py:307-315
+            ex = weights["exchange"][i] if i in weights["exchange"] else weights["exchange"][str(i)]
+            cur = graph_global_exchange(params["global_exchange_mode"], cur, node_to_graph_map, int(num_graphs), ex,
+                                        int(params["hidden_dim"]), int(params["global_exchange_num_heads"]),
+                                        params["global_exchange_weighting_fun"], dtype=dtype).astype(dtype)
         if params["use_inter_layer_layernorm"]:                           # gnn.py:317-321
             g, b = weights["layernorm"][i]
             cur = layer_norm(cur, np.asarray(g, dtype=dtype), np.asarray(b, dtype=dtype)).astype(dtype)
         if i % int(params["dense_every_num_layers"]) == 0:                # gnn.py:324-327
-            y = cur @ np.asarray(weights["dense"][i], dtype=dtype)
+            d = weights["dense"][i] if i in weights["dense"] else weights["dense"][str(i)]
+            y = cur @ np.asarray(d, dtype=dtype)
             cur = act_dense(y) if act_dense is not None else y
     return cur, tuple(all_reps)

@@ -18,6 +18,7 @@ _lib: Optional[ctypes.CDLL] = None
 OK, ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_UNSUPPORTED, ERR_INDEX_OUT_OF_RANGE = 0, 1, 2, 3, 4
 AGG = {"sum": 0, "mean": 1, "max": 2, "sqrt_n": 3}
 ACT = {None: 0, "relu": 1, "tanh": 2, "leaky_relu": 3, "elu": 4, "selu": 5, "gelu": 6}
+ACT_SIGMOID = 7  # library-internal (readout weights); deliberately NOT in the name table: the reference raises on "sigmoid"
 FLAG_NORMALIZE, FLAG_ACT_BEFORE_AGG, FLAG_USE_TARGET = 1, 2, 4
 PATH = {"auto": 0, "atomic": 1, "sorted": 2, "sorted_tc": 3, "fused_tc": 4}
 PREPARE_VALIDATE = 1
@@ -33,6 +34,9 @@ EXPORTED_SYMBOLS = (
     "tfgnn_b200_process_adjacency_sizes", "tfgnn_b200_process_adjacency",
     "tfgnn_b200_assemble_batch_workspace_bytes", "tfgnn_b200_assemble_batch",
     "tfgnn_b200_launch_count", "tfgnn_b200_set_l2_persist_mb", "tfgnn_b200_release_device_state",
+    "tfgnn_b200_graph_offsets", "tfgnn_b200_segment_softmax", "tfgnn_b200_weighted_segment_sum",
+    "tfgnn_b200_gathered_add", "tfgnn_b200_gru_gate_fwd", "tfgnn_b200_clamp", "tfgnn_b200_dense_bias_fwd",
+    "tfgnn_b200_dense_bwd", "tfgnn_b200_layer_norm_bwd", "tfgnn_b200_dropout", "tfgnn_b200_axpby",
 )
 
 _PP = POINTER(c_void_p)
@@ -96,6 +100,22 @@ def lib() -> ctypes.CDLL:
     L.tfgnn_b200_assemble_batch_workspace_bytes.restype = ctypes.c_size_t
     L.tfgnn_b200_assemble_batch.argtypes = [c_void_p, _PP, _PP, c_int32, c_int64, c_void_p, c_int32, c_int64,
                                             POINTER(c_int64), c_void_p, c_void_p, _PP, c_void_p, c_void_p]
+    L.tfgnn_b200_graph_offsets.argtypes = [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_void_p]
+    L.tfgnn_b200_segment_softmax.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]
+    L.tfgnn_b200_weighted_segment_sum.argtypes = [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                                  c_void_p, c_void_p]
+    L.tfgnn_b200_gathered_add.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_int32, c_void_p,
+                                          c_void_p]
+    L.tfgnn_b200_gru_gate_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    L.tfgnn_b200_clamp.argtypes = [c_void_p, c_int64, c_float, c_float, c_int32, c_int32, c_void_p]
+    L.tfgnn_b200_dense_bias_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
+                                            c_int32, c_void_p]
+    L.tfgnn_b200_dense_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32,
+                                       c_void_p, c_void_p, c_void_p, c_void_p]
+    L.tfgnn_b200_layer_norm_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_void_p, c_void_p,
+                                            c_void_p, c_void_p]
+    L.tfgnn_b200_dropout.argtypes = [c_void_p, c_int64, c_float, ctypes.c_uint64, ctypes.c_uint64, c_void_p, c_void_p]
+    L.tfgnn_b200_axpby.argtypes = [c_void_p, c_float, c_void_p, c_float, c_int64, c_void_p, c_void_p]
     L.tfgnn_b200_set_l2_persist_mb.argtypes = [c_int32]
     L.tfgnn_b200_release_device_state.argtypes = []
     for name in EXPORTED_SYMBOLS:

@@ -39,7 +39,7 @@ int unsupported(const std::string& msg) {
   return TFGNN_ERR_UNSUPPORTED;
 }
 
-bool valid_act(int a) { return a >= TFGNN_ACT_NONE && a <= TFGNN_ACT_GELU; }
+bool valid_act(int a) { return a >= TFGNN_ACT_NONE && a <= TFGNN_ACT_SIGMOID; }
 bool valid_agg(int a) { return a >= TFGNN_AGG_SUM && a <= TFGNN_AGG_SQRT_N; }
 
 // Node-level contraction C = epi(A B) with B [K,N] row-major in device memory.

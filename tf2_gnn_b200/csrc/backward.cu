@@ -20,6 +20,7 @@ __device__ __forceinline__ float act_grad_from_output(float y, int act) {
     case TFGNN_ACT_LEAKY_RELU: return y > 0.f ? 1.f : kLeakyReluAlpha;
     case TFGNN_ACT_ELU: return y > 0.f ? 1.f : y + 1.f;                               // d/dx (e^x - 1) = y + 1
     case TFGNN_ACT_SELU: return y > 0.f ? kSeluScale : y + kSeluScale * kSeluAlpha;   // scale*alpha*e^x = y + scale*alpha
+    case TFGNN_ACT_SIGMOID: return y * (1.f - y);
     default: return 1.f;
   }
 }
@@ -485,6 +486,232 @@ extern "C" int tfgnn_b200_ggnn_bwd(tfgnn_batch_t* b, tfgnn_batch_t* bt, const fl
   if (rc) return rc;
   // 7. grad_h += dh_direct + dh_rec
   add3_kernel<<<grid_cap(V * H), 256, 0, st>>>(grad_h, (const float*)dhd, (const float*)tmp, V * H);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================================================
+// Node-level glue of GNN._internal_call under training (gnn.py:279-327): backward of the bias-free / biased Dense layers,
+// LayerNormalization, and the Philox dropout shared by forward and backward.  The reference gets all of these from
+// tf.GradientTape (models/graph_task_model.py:338-365).
+// =====================================================================================================================
+namespace tfgnn {
+
+// dZ = dY * act'(.) for a Dense layer: derivative from the OUTPUT (every activation but gelu) or from the recomputed
+// pre-activation (gelu).
+__global__ void dense_act_grad_kernel(const float* __restrict__ g, const float* __restrict__ y, long long n, int act,
+                                      float* __restrict__ dz) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dz[i] = g[i] * (act == TFGNN_ACT_GELU ? gelu_grad_from_input(y[i]) : act_grad_from_output(y[i], act));
+}
+
+// LayerNormalization backward, one warp per row:
+//   xhat = (x - mean) * rstd;  dxhat = g * gamma;
+//   dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat));   t[v,c] = g * xhat  (column-summed into dgamma)
+__global__ void layer_norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                      const float* __restrict__ g, long long V, int H, float eps,
+                                      float* __restrict__ dx, float* __restrict__ t) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= V) return;
+  const float* xr = x + row * H;
+  const float* gr = g + row * H;
+  float s = 0.f;
+  for (int c = lane; c < H; c += 32) s += xr[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)H;
+  float q = 0.f;
+  for (int c = lane; c < H; c += 32) {
+    const float d = xr[c] - mean;
+    q += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)H + eps);
+  float a = 0.f, b = 0.f;   // sum dxhat, sum dxhat * xhat
+  for (int c = lane; c < H; c += 32) {
+    const float xhat = (xr[c] - mean) * rstd;
+    const float dxh = gr[c] * gamma[c];
+    a += dxh;
+    b += dxh * xhat;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  a /= (float)H;
+  b /= (float)H;
+  for (int c = lane; c < H; c += 32) {
+    const float xhat = (xr[c] - mean) * rstd;
+    const float dxh = gr[c] * gamma[c];
+    if (dx) dx[row * H + c] = rstd * (dxh - a - xhat * b);
+    t[row * H + c] = gr[c] * xhat;
+  }
+}
+
+// Philox4x32-10 (Salmon et al. 2011), the counter-based generator TensorFlow's stateless random ops use as well.
+// One counter value yields 4 uniform 32-bit words: element i takes word i & 3 of counter i >> 2, so the mask of an
+// element depends only on (seed, offset, i): the backward pass regenerates it instead of storing it.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+// tf.nn.dropout(x, rate): keep with probability 1 - rate, scale kept values by 1 / (1 - rate)   (gnn.py:285-289)
+__global__ void dropout_kernel(const float* __restrict__ x, long long n, float rate, unsigned long long seed,
+                               unsigned long long offset, float* __restrict__ out) {
+  const float scale = 1.0f / (1.0f - rate);
+  const long long groups = (n + 3) >> 2;
+  for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < groups;
+       gi += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long c = (unsigned long long)gi + offset;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = gi * 4 + j;
+      if (i < n) {
+        const float u = (float)(w[j] >> 8) * (1.0f / 16777216.0f);   // uniform in [0, 1)
+        out[i] = u >= rate ? x[i] * scale : 0.0f;
+      }
+    }
+  }
+}
+
+__global__ void axpby_kernel(const float* __restrict__ a, float alpha, const float* __restrict__ b, float beta,
+                             long long n, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = b ? alpha * a[i] + beta * b[i] : alpha * a[i];
+}
+
+// column sums of X [V, N] in fixed-order chunks -> out [N]   (bias / gamma / beta gradients)
+static int column_sums(const float* X, long long V, int N, float* out, cudaStream_t st) {
+  const int chunks = (int)((V + kTnChunk - 1) / kTnChunk);
+  void* part = nullptr;
+  int rc = pool_alloc(&part, (size_t)chunks * N * sizeof(float), st);
+  if (rc) return rc;
+  dim3 grid((N + 127) / 128, chunks);
+  colsum_partial_kernel<<<grid, 128, 0, st>>>(X, V, N, (float*)part);
+  TFGNN_LAUNCH_CHECK();
+  colsum_reduce_kernel<<<(N + 127) / 128, 128, 0, st>>>((const float*)part, chunks, N, out);
+  TFGNN_LAUNCH_CHECK();
+  pool_free(part, st);
+  return 0;
+}
+
+}  // namespace tfgnn
+
+// Backward of out = act(x W + bias): grad_x = dZ W^T (tensor-core GEMM), grad_W = x^T dZ (TN GEMM, fixed-order partials),
+// grad_bias = column sums of dZ, dZ = grad_out * act'.  `out` is the saved forward output.
+extern "C" int tfgnn_b200_dense_bwd(const float* x, const float* W, const float* bias, const float* out,
+                                    const float* grad_out, int64_t V, int32_t K, int32_t N, int32_t activation,
+                                    float* grad_x, float* grad_W, float* grad_bias, void* stream) {
+  TFGNN_REQUIRE(V >= 0 && K > 0 && N > 0, "bad dense shape");
+  TFGNN_REQUIRE(valid_act(activation), "unknown activation code");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (V == 0) {
+    if (grad_W) TFGNN_CUDA(cudaMemsetAsync(grad_W, 0, (size_t)K * N * sizeof(float), st));
+    if (grad_bias) TFGNN_CUDA(cudaMemsetAsync(grad_bias, 0, (size_t)N * sizeof(float), st));
+    return 0;
+  }
+  TFGNN_REQUIRE(x && W && out && grad_out, "NULL pointer");
+  void *dz = nullptr, *pre = nullptr, *wT = nullptr, *part = nullptr;
+  int rc = pool_alloc(&dz, (size_t)V * N * sizeof(float), st);
+  if (rc) return rc;
+  const float* y = out;
+  if (activation == TFGNN_ACT_GELU) {   // derivative needs the pre-activation: recompute x W + bias
+    rc = pool_alloc(&pre, (size_t)V * N * sizeof(float), st);
+    if (!rc) rc = tfgnn_b200_dense_bias_fwd(x, W, bias, (float*)pre, V, K, N, TFGNN_ACT_NONE, TFGNN_PATH_AUTO, stream);
+    if (rc) { pool_free(dz, st); pool_free(pre, st); return rc; }
+    y = (const float*)pre;
+  }
+  dense_act_grad_kernel<<<grid_cap(V * N), 256, 0, st>>>(grad_out, y, V * N, activation, (float*)dz);
+  g_launch_count.fetch_add(1);
+  if (grad_W) {
+    const int chunks = (int)((V + kTnChunk - 1) / kTnChunk);
+    rc = pool_alloc(&part, (size_t)chunks * K * N * sizeof(float), st);
+    if (!rc) {
+      PtrTable gt{};
+      gt.p[0] = grad_W;
+      dim3 grid((K + kTnTile - 1) / kTnTile, (N + kTnTile - 1) / kTnTile, chunks);
+      gemm_tn_partial_kernel<<<grid, 256, 0, st>>>(x, K, (const float*)dz, N, V, K, N, (float*)part);
+      g_launch_count.fetch_add(1);
+      reduce_partials_kernel<<<grid_cap((long long)K * N), 256, 0, st>>>((const float*)part, chunks, 1, K, N, gt);
+      g_launch_count.fetch_add(1);
+    }
+  }
+  if (!rc && grad_bias) rc = column_sums((const float*)dz, V, N, grad_bias, st);
+  if (!rc && grad_x) {
+    rc = pool_alloc(&wT, (size_t)N * K * sizeof(float), st);
+    if (!rc) {
+      PtrTable wt{};
+      wt.p[0] = W;
+      pack_transposed_kernel<<<grid_cap((long long)K * N), 256, 0, st>>>(wt, 1, K, N, (float*)wT);   // [N, K]
+      g_launch_count.fetch_add(1);
+      rc = tfgnn_b200_dense_fwd((const float*)dz, (const float*)wT, grad_x, V, N, K, TFGNN_ACT_NONE, TFGNN_PATH_AUTO,
+                                stream);
+    }
+  }
+  if (!rc) rc = check_cuda(cudaGetLastError(), "dense_bwd kernels", __FILE__, __LINE__);
+  pool_free(dz, st);
+  pool_free(pre, st);
+  pool_free(wT, st);
+  pool_free(part, st);
+  return rc;
+}
+
+extern "C" int tfgnn_b200_layer_norm_bwd(const float* x, const float* gamma, const float* grad_out, int64_t V, int32_t H,
+                                         float epsilon, float* grad_x, float* grad_gamma, float* grad_beta,
+                                         void* stream) {
+  TFGNN_REQUIRE(V >= 0 && H > 0, "bad layer_norm shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (V == 0) {
+    if (grad_gamma) TFGNN_CUDA(cudaMemsetAsync(grad_gamma, 0, (size_t)H * sizeof(float), st));
+    if (grad_beta) TFGNN_CUDA(cudaMemsetAsync(grad_beta, 0, (size_t)H * sizeof(float), st));
+    return 0;
+  }
+  TFGNN_REQUIRE(x && gamma && grad_out, "NULL pointer");
+  void* t = nullptr;
+  int rc = pool_alloc(&t, (size_t)V * H * sizeof(float), st);
+  if (rc) return rc;
+  layer_norm_bwd_kernel<<<ceil_div(V * 32, 256), 256, 0, st>>>(x, gamma, grad_out, V, H, epsilon, grad_x, (float*)t);
+  g_launch_count.fetch_add(1);
+  rc = check_cuda(cudaGetLastError(), "layer_norm_bwd_kernel", __FILE__, __LINE__);
+  if (!rc && grad_gamma) rc = column_sums((const float*)t, V, H, grad_gamma, st);
+  if (!rc && grad_beta) rc = column_sums(grad_out, V, H, grad_beta, st);
+  pool_free(t, st);
+  return rc;
+}
+
+// tf.nn.dropout (gnn.py:285-289, graph_global_exchange.py:98-101).  The mask is a pure function of (seed, offset, element
+// index), so the backward pass calls the same entry on the incoming gradient.
+extern "C" int tfgnn_b200_dropout(const float* x, int64_t n, float rate, uint64_t seed, uint64_t offset, float* out,
+                                  void* stream) {
+  TFGNN_REQUIRE(n >= 0 && rate >= 0.0f && rate < 1.0f, "dropout rate must lie in [0, 1)");
+  if (n == 0) return 0;
+  TFGNN_REQUIRE(x && out, "NULL pointer");
+  dropout_kernel<<<grid_cap((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, n, rate, seed, offset, out);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tfgnn_b200_axpby(const float* a, float alpha, const float* b, float beta, int64_t n, float* out,
+                                void* stream) {
+  TFGNN_REQUIRE(n >= 0, "negative size");
+  if (n == 0) return 0;
+  TFGNN_REQUIRE(a && out, "NULL pointer");
+  axpby_kernel<<<grid_cap(n), 256, 0, (cudaStream_t)stream>>>(a, alpha, b, beta, n, out);
   TFGNN_LAUNCH_CHECK();
   return 0;
 }

@@ -54,6 +54,7 @@ __device__ __forceinline__ float apply_act(float x, int act) {
       float cdf = 0.5f * (1.0f + tanhf(c * (x + 0.044715f * x * x * x)));
       return x * cdf;
     }
+    case TFGNN_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
     default: return x;
   }
 }
@@ -87,6 +88,7 @@ __device__ __forceinline__ void apply_act_vec(float* v, int act) {
     case TFGNN_ACT_ELU: apply_act_vec_t<TFGNN_ACT_ELU, N>(v); break;
     case TFGNN_ACT_SELU: apply_act_vec_t<TFGNN_ACT_SELU, N>(v); break;
     case TFGNN_ACT_GELU: apply_act_vec_t<TFGNN_ACT_GELU, N>(v); break;
+    case TFGNN_ACT_SIGMOID: apply_act_vec_t<TFGNN_ACT_SIGMOID, N>(v); break;
     default: break;
   }
 }

@@ -159,7 +159,7 @@ extern "C" int tfgnn_b200_unsorted_segment_reduce(const float* data, const int32
 }
 
 extern "C" int tfgnn_b200_activation(const float* x, int64_t n, int32_t activation, float* out, void* stream) {
-  TFGNN_REQUIRE(n >= 0 && activation >= TFGNN_ACT_NONE && activation <= TFGNN_ACT_GELU, "bad activation arguments");
+  TFGNN_REQUIRE(n >= 0 && activation >= TFGNN_ACT_NONE && activation <= TFGNN_ACT_SIGMOID, "bad activation arguments");
   if (n == 0) return 0;
   TFGNN_REQUIRE(x && out, "NULL pointer");
   activation_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, n, activation, out);

@@ -4,9 +4,9 @@ Same GNNInput namedtuple, hyper-parameter dict, layer loop and return convention
 lists are prepared ONCE per call (CSR sorted by type,target) and shared by all message-passing layers;
 the reference rebuilds the in-degree table in every layer (message_passing.py:190).
 
-Node-level glue implemented on the library's kernels: initial projection / inter-layer Dense
-(tfgnn_b200_dense_fwd), residual average, LayerNormalization.  Not built yet (raise, never fall
-back): training-time dropout with rate > 0 and the graph global exchange layers.
+Node-level glue on the library's kernels (layers/node_ops.py): initial projection / inter-layer Dense, residual
+average, LayerNormalization, training-time dropout (Philox) — each differentiable through its own backward
+kernel — and the graph global exchange layers (layers/graph_global_exchange.py).
 """
 from __future__ import annotations
 
@@ -14,9 +14,11 @@ from typing import Any, Dict, List, NamedTuple, Optional, Tuple
 
 import torch
 
-from .. import _ffi
-from ..runtime import PreparedBatch, prepared_batch_for, stream_ptr, to_device_adj, to_device_f32
+from ..runtime import PreparedBatch, prepared_batch_for, to_device_adj, to_device_f32
 from ..utils.param_helpers import get_activation_function
+from . import node_ops
+from .graph_global_exchange import (GraphGlobalExchange, GraphGlobalExchangeInput, GraphGlobalGRUExchange,
+                                    GraphGlobalMeanExchange, GraphGlobalMLPExchange)
 from .message_passing import MessagePassing, MessagePassingInput, get_message_passing_class
 from .message_passing.message_passing import Variable, glorot_uniform
 
@@ -38,13 +40,7 @@ class _Dense:
         self.activation = activation
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
-        V, K = int(x.shape[0]), int(x.shape[1])
-        N = int(self.kernel.value.shape[1])
-        out = torch.empty((V, N), dtype=torch.float32, device=x.device)
-        _ffi.check(_ffi.lib().tfgnn_b200_dense_fwd(
-            x.data_ptr(), self.kernel.value.data_ptr(), out.data_ptr(), V, K, N,
-            self.activation.code if self.activation is not None else 0, 0, stream_ptr()))
-        return out
+        return node_ops.dense(x, self.kernel.value, None, self.activation)
 
 
 class _LayerNorm:
@@ -57,11 +53,7 @@ class _LayerNorm:
         self.epsilon = epsilon
 
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
-        out = torch.empty_like(x)
-        _ffi.check(_ffi.lib().tfgnn_b200_layer_norm(
-            x.data_ptr(), self.gamma.value.data_ptr(), self.beta.value.data_ptr(), int(x.shape[0]),
-            int(x.shape[1]), self.epsilon, out.data_ptr(), stream_ptr()))
-        return out
+        return node_ops.layer_norm(x, self.gamma.value, self.beta.value, self.epsilon)
 
 
 class GNN:
@@ -111,10 +103,16 @@ class GNN:
                 f"Unknown global_exchange_mode mode {params['global_exchange_mode']} - has to be one of 'mean', 'mlp', 'gru'!")
         self._global_exchange_mode = params["global_exchange_mode"]
         self._global_exchange_every_num_layers = params["global_exchange_every_num_layers"]
+        self._global_exchange_weighting_fun = params["global_exchange_weighting_fun"]
+        self._global_exchange_num_heads = params["global_exchange_num_heads"]
+        self._global_exchange_dropout_rate = params["global_exchange_dropout_rate"]
         self._initial_projection_layer: Optional[_Dense] = None
         self._mp_layers: List[MessagePassing] = []
         self._inter_layer_layernorms: List[_LayerNorm] = []
         self._dense_layers: Dict[str, _Dense] = {}
+        self._global_exchange_layers: Dict[str, GraphGlobalExchange] = {}
+        # Philox stream of the training-time dropout (b200_dropout_seed is not a reference hyper-parameter)
+        self.dropout_state = node_ops.DropoutState(int(params.get("b200_dropout_seed", 0x5EED)))
         self.built = False
 
     def _exchange_layers(self) -> List[int]:
@@ -140,6 +138,16 @@ class GNN:
                 self._dense_layers[str(layer_idx)] = _Dense(
                     f"{scope}/Layer_{layer_idx}/Dense/dense", self._hidden_dim, self._hidden_dim,
                     self._dense_intermediate_layer_activation_fn)
+            if layer_idx and layer_idx % self._global_exchange_every_num_layers == 0:       # gnn.py:172-200
+                exchange_layer_class = {"mean": GraphGlobalMeanExchange, "gru": GraphGlobalGRUExchange,
+                                        "mlp": GraphGlobalMLPExchange}[self._global_exchange_mode.lower()]
+                exchange_layer = exchange_layer_class(
+                    hidden_dim=self._hidden_dim, weighting_fun=self._global_exchange_weighting_fun,
+                    num_heads=self._global_exchange_num_heads, dropout_rate=self._global_exchange_dropout_rate)
+                exchange_layer.build(GraphGlobalExchangeInput((None, self._hidden_dim), (None,), ()),
+                                     name=f"{scope}/Layer_{layer_idx}/Global_Exchange/{exchange_layer_class.__name__}")
+                exchange_layer.dropout_state = self.dropout_state
+                self._global_exchange_layers[str(layer_idx)] = exchange_layer
         self.built = True
 
     @property
@@ -151,6 +159,8 @@ class GNN:
                 out.extend([self._inter_layer_layernorms[i].gamma, self._inter_layer_layernorms[i].beta])
             if str(i) in self._dense_layers:
                 out.append(self._dense_layers[str(i)].kernel)
+            if str(i) in self._global_exchange_layers:
+                out.extend(self._global_exchange_layers[str(i)].variables)
         return out
 
     trainable_variables = variables
@@ -171,12 +181,6 @@ class GNN:
 
     def _internal_call(self, inputs: GNNInput, training: bool = False):
         """gnn.py:276-329."""
-        if self._exchange_layers():
-            raise NotImplementedError(
-                "graph global exchange layers are not built yet (set global_exchange_every_num_layers > "
-                "num_layers, as every PPI config of the reference does)")
-        if training and float(self._params.get("layer_input_dropout_rate", 0.0)) > 0.0:
-            raise NotImplementedError("training-time dropout is not built yet (forward/inference path only)")
         feats = to_device_f32(inputs.node_features)
         adjs = tuple(to_device_adj(a, feats.device) for a in inputs.adjacency_lists)
         if all(a is b for a, b in zip(adjs, inputs.adjacency_lists)):
@@ -186,17 +190,26 @@ class GNN:
         cur = self._initial_projection_layer(feats)
         last = cur
         all_reps = [cur]
+        n2g = None
+        if self._global_exchange_layers:
+            n2g = inputs.node_to_graph_map
+            if not isinstance(n2g, torch.Tensor):
+                n2g = torch.as_tensor(n2g)
+            n2g = n2g.to(device=feats.device, dtype=torch.int32).contiguous()
+        dropout_rate = float(self._params.get("layer_input_dropout_rate", 0.0))
         for layer_idx, mp_layer in enumerate(self._mp_layers):
-            if layer_idx % self._residual_every_num_layers == 0:
+            if training:                                                             # gnn.py:285-289
+                cur = node_ops.dropout(cur, dropout_rate, self.dropout_state)
+            if layer_idx % self._residual_every_num_layers == 0:                     # gnn.py:291-296
                 tmp = cur
                 if layer_idx > 0:
-                    avg = torch.empty_like(cur)
-                    _ffi.check(_ffi.lib().tfgnn_b200_residual_average(cur.data_ptr(), last.data_ptr(),
-                                                                      avg.data_ptr(), cur.numel(), stream_ptr()))
-                    cur = avg
+                    cur = node_ops.residual_average(cur, last)
                 last = tmp
             cur = mp_layer(MessagePassingInput(cur, adjs), training=training, prepared=prepared)
             all_reps.append(cur)
+            if layer_idx and layer_idx % self._global_exchange_every_num_layers == 0:   # gnn.py:307-315
+                cur = self._global_exchange_layers[str(layer_idx)](
+                    GraphGlobalExchangeInput(cur, n2g, int(inputs.num_graphs)), training=training)
             if self._use_inter_layer_layernorm:
                 cur = self._inter_layer_layernorms[layer_idx](cur)
             if layer_idx % self._dense_every_num_layers == 0:

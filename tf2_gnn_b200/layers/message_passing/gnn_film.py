@@ -8,6 +8,7 @@ import torch
 from ... import _ffi
 from ...runtime import PreparedBatch, stream_ptr
 from .gnn_edge_mlp import EdgeMLP, GNN_Edge_MLP
+from ..node_ops import require_no_grad
 from .message_passing import MessagePassingInput, _last_dim, register_message_passing_implementation
 
 
@@ -44,6 +45,7 @@ class GNN_FiLM(GNN_Edge_MLP):
     def call(self, inputs: MessagePassingInput, training: bool = False,
              prepared: Optional[PreparedBatch] = None):
         h, prepared = self._device_inputs(inputs, prepared)
+        require_no_grad(type(self).__name__, h, *[v.value for v in self.variables])
         self._check_types(prepared)
         if any(m.num_hidden_layers for m in self._edge_type_film_layer_computations):
             raise NotImplementedError("film_parameter_MLP_hidden_layers != [] is not built yet")

@@ -179,6 +179,8 @@ class MessagePassing:
              prepared: Optional[PreparedBatch] = None):
         """Generic path for user plugins (message_passing.py:95-133)."""
         h, prepared = self._device_inputs(inputs, prepared)
+        from ..node_ops import require_no_grad
+        require_no_grad("the generic MessagePassing.call plugin path", h, *[v.value for v in self.variables])
         num_nodes = int(h.shape[0])
         messages_per_type = self._calculate_messages_per_type(prepared, h, training)
         edge_type_to_message_targets = [a[:, 1] for a in prepared.adjacency_lists]

@@ -8,6 +8,7 @@ import torch
 from ... import _ffi
 from ...runtime import PreparedBatch, stream_ptr
 from .gnn_edge_mlp import GNN_Edge_MLP
+from ..node_ops import require_no_grad
 from .message_passing import MessagePassingInput, Variable, register_message_passing_implementation
 
 
@@ -44,6 +45,7 @@ class RGIN(GNN_Edge_MLP):
     def call(self, inputs: MessagePassingInput, training: bool = False,
              prepared: Optional[PreparedBatch] = None):
         h, prepared = self._device_inputs(inputs, prepared)
+        require_no_grad(type(self).__name__, h, *[v.value for v in self.variables])
         self._check_types(prepared)
         out = torch.empty((prepared.num_nodes, self._hidden_dim), dtype=torch.float32, device=h.device)
         ptrs, _keep = self._mlp_weight_ptrs()

@@ -130,8 +130,52 @@ class PreparedBatch:
         return row_ptr, src
 
 
+class HostPipeline:
+    """Software pipeline for callers whose batches live in (pinned) HOST memory.
+
+    One step = H2D of the step's inputs, per-batch prepare, the layer call(s) and the D2H of the result.  Steps are
+    issued round-robin on `depth` CUDA streams, so the D2H of step i overlaps the H2D of step i+1 (PCIe is full
+    duplex) and both overlap the kernels; every step still performs all of its own copies.  The reference overlaps
+    host batch construction with the step in the same spirit (DoubleBufferedIterator, graph_dataset.py:292-295).
+
+        pipe = HostPipeline(lambda batch: layer(batch), depth=2)
+        for batch, out_host in work:            # out_host: pinned torch tensor the result is copied into
+            pipe.submit(batch, out_host)        # returns immediately; at most `depth` steps are in flight
+        pipe.drain()                            # all results have landed in their out_host buffers
+    """
+
+    def __init__(self, step_fn, depth: int = 2):
+        require_cuda()
+        self.step_fn = step_fn
+        self.depth = max(1, int(depth))
+        self.streams = [torch.cuda.Stream() for _ in range(self.depth)]
+        self.done: List[Optional[torch.cuda.Event]] = [None] * self.depth
+        self._keep: List[Optional[object]] = [None] * self.depth
+        self._i = 0
+
+    def submit(self, batch, out_host: torch.Tensor) -> None:
+        slot = self._i % self.depth
+        self._i += 1
+        if self.done[slot] is not None:
+            self.done[slot].synchronize()       # the slot's previous result has landed: its buffers may be reused
+        s = self.streams[slot]
+        with torch.cuda.stream(s):
+            out = self.step_fn(batch)
+            out_host.copy_(out, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s)
+        self.done[slot] = ev
+        self._keep[slot] = out                  # keeps the device result alive until its D2H copy has completed
+
+    def drain(self) -> None:
+        for ev in self.done:
+            if ev is not None:
+                ev.synchronize()
+        self._keep = [None] * self.depth
+
+
 _cache: List[Tuple[tuple, "weakref.ref", PreparedBatch]] = []
-_CACHE_SIZE = 4
+_CACHE_SIZE = 2
 
 
 def prepared_batch_for(adjacency_lists: Sequence[torch.Tensor], num_nodes: int) -> PreparedBatch:
