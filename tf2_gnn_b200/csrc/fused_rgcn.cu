@@ -51,6 +51,7 @@ struct FusedParams {
   long long M;          // entries of src (bound for the 32-wide index block loads)
   int discard_ring;     // discard.global.L2 on consumed ring slots
   int gather_q;         // bulk row copies each gather warp keeps in flight (= its shared-memory row slots)
+  int corr_bf16;        // 1: corrections as one bf16-pair MMA (sm100_ptx.cuh), 0: two tf32 MMAs
   int debug_skip;       // timing experiments only (results invalid), bit mask: 1 = no edge gathers, 2 = one K block per slot, 4 = no epilogue work, 8 = no weight-tile loads, 16 = no ring stores, 32 = raw fp32 tile as the hi operand (valid iff the MMA truncates)
   // ring
   float* ring;  // [grid * num_slots * 128, D]
@@ -399,6 +400,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else if (warp == 1) {
     // ================= MMA issuer (the leader CTA of a pair issues for both) =================
     const uint32_t idesc = ptx::umma_idesc_tf32(128u * CTAS, (uint32_t)p.block_n);
+    const uint32_t idesc_bf = ptx::umma_idesc_bf16(128u * CTAS, (uint32_t)p.block_n);
     uint32_t it = 0, tile_count = 0;
     for (long long tp = unit0 * n_pass; rank == 0 && tp < total_units * n_pass;
          tp = (tp % n_pass == n_pass - 1) ? tp + (unit_step - 1) * n_pass + 1 : tp + 1, ++tile_count) {
@@ -423,12 +425,20 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           for (int k = 0; k < kFuBK / 8; ++k) {
             const uint64_t adv = (uint64_t)(k * 32 >> 4);
             if (CTAS == 2) {
-              ptx::mma_tf32_ss_pair(c_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-              ptx::mma_tf32_ss_pair(c_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+              if (p.corr_bf16) {
+                ptx::mma_bf16_ss_pair(c_tmem, a_lo + adv, b_lo + adv, idesc_bf, (kb | k) != 0);   // a lo(b) + lo(a) b
+              } else {
+                ptx::mma_tf32_ss_pair(c_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+                ptx::mma_tf32_ss_pair(c_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+              }
               ptx::mma_tf32_ss_pair(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
             } else {
-              ptx::mma_tf32_ss(c_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-              ptx::mma_tf32_ss(c_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+              if (p.corr_bf16) {
+                ptx::mma_bf16_ss(c_tmem, a_lo + adv, b_lo + adv, idesc_bf, (kb | k) != 0);
+              } else {
+                ptx::mma_tf32_ss(c_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+                ptx::mma_tf32_ss(c_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+              }
               ptx::mma_tf32_ss(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
             }
           }
@@ -446,7 +456,8 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else if (warp >= 4 && warp < 8) {
     // ================= A splitters =================
     const int tid = threadIdx.x - 128;
-    const bool raw_hi = p.debug_skip & 32;   // experiment: leave the fp32 tile in place as the hi operand
+    const bool raw_hi = (p.debug_skip & 32) || p.corr_bf16;   // the fp32 tile stays in place as the hi operand
+    const bool pair = p.corr_bf16;
     uint32_t it = 0, slot_base_it = 0;
     for (long long unit = unit0; unit < total_units; unit += unit_step, slot_base_it += p.L) {
      for (int pass = 0; pass < n_pass; ++pass) {
@@ -474,10 +485,17 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             const float4 x = a[idx];
             float4 hh, ll;
             hh.x = ptx::tf32_hi(x.x); hh.y = ptx::tf32_hi(x.y); hh.z = ptx::tf32_hi(x.z); hh.w = ptx::tf32_hi(x.w);
-            ll.x = ptx::tf32_hi(x.x - hh.x); ll.y = ptx::tf32_hi(x.y - hh.y);
-            ll.z = ptx::tf32_hi(x.z - hh.z); ll.w = ptx::tf32_hi(x.w - hh.w);
-            if (!raw_hi) a[idx] = hh;   // raw_hi: the tensor core itself drops the low 13 mantissa bits of the operand
-            lo[idx] = ll;
+            if (pair) {   // one tile of bf16 pairs (a | a - tf32(a)) in the bytes of the lo tile
+              uint4 w;
+              w.x = ptx::pack_bf16x2(x.x - hh.x, x.x); w.y = ptx::pack_bf16x2(x.y - hh.y, x.y);
+              w.z = ptx::pack_bf16x2(x.z - hh.z, x.z); w.w = ptx::pack_bf16x2(x.w - hh.w, x.w);
+              reinterpret_cast<uint4*>(lo)[idx] = w;
+            } else {
+              ll.x = ptx::tf32_hi(x.x - hh.x); ll.y = ptx::tf32_hi(x.y - hh.y);
+              ll.z = ptx::tf32_hi(x.z - hh.z); ll.w = ptx::tf32_hi(x.w - hh.w);
+              if (!raw_hi) a[idx] = hh;   // raw_hi: the tensor core itself drops the low 13 mantissa bits of the operand
+              lo[idx] = ll;
+            }
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
@@ -703,6 +721,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   p.discard_ring = discard_env;
   static const int dbg_env = [] { const char* e = getenv("TFGNN_B200_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
   p.debug_skip = dbg_env;
+  p.corr_bf16 = tc_corr_bf16();
   p.N = H;
   p.n_tiles = H > 256 ? 2 : 1;            // N passes
   p.block_n = H / p.n_tiles;

@@ -33,6 +33,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
                       const float* packedB, int H, float* ring, float* out, int ldo, const GemmEpilogue& epi,
                       cudaStream_t st);
 
+int tc_corr_bf16();   // correction scheme of the 3xTF32 contractions (gemm_tc.cu)
 int set_l2_persist_mb(int mb);
 void restore_l2_persist_carveout();
 void pool_trim_all();

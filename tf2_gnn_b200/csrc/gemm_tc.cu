@@ -17,6 +17,7 @@
 //   warps 6-9   epilogue: tcgen05.ld -> row normalisation / bias / activation -> global
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 
 #include "gemm.cuh"
@@ -40,6 +41,7 @@ struct TcParams {
   int block_n, n_tiles;
   long long m_tiles, total_tiles;
   int num_k_blocks, num_stages;
+  int corr_bf16;   // 1: corrections as one bf16-pair MMA (sm100_ptx.cuh), 0: two tf32 MMAs (round-1 scheme)
   float* C;
   int ldc;
   GemmEpilogue epi;
@@ -120,6 +122,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else if (warp == 1) {
     // ================= MMA issuer =================
     const uint32_t idesc = ptx::umma_idesc_tf32_m128((uint32_t)p.block_n);
+    const uint32_t idesc_bf = ptx::umma_idesc_bf16(128u, (uint32_t)p.block_n);
     uint32_t it = 0, tile_count = 0;
     const uint32_t n_acc = p.block_n <= 128 ? 2 : 1;       // accumulator stages that fit 512 TMEM columns
     const uint32_t corr_off = p.block_n <= 128 ? 128 : 256;
@@ -143,9 +146,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint64_t b_lo = ptx::umma_desc_k_sw128(st + 2 * kTcATileBytes + b_tile_bytes);
 #pragma unroll
           for (int k = 0; k < kTcBK / 8; ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 8 tf32 = 32 B along K inside the swizzle row
-            ptx::mma_tf32_ss(c_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
-            ptx::mma_tf32_ss(c_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 8 tf32 (or 16 bf16) = 32 B along K inside the swizzle row
+            if (p.corr_bf16) {
+              ptx::mma_bf16_ss(c_tmem, a_lo + adv, b_lo + adv, idesc_bf, (kb | k) != 0);   // pair tiles: a lo(b) + lo(a) b
+            } else {
+              ptx::mma_tf32_ss(c_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+              ptx::mma_tf32_ss(c_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+            }
             ptx::mma_tf32_ss(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
           }
           ptx::mma_commit(&empty[s]);
@@ -171,10 +178,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const float4 x = a[idx];
           float4 h, l;
           h.x = ptx::tf32_hi(x.x); h.y = ptx::tf32_hi(x.y); h.z = ptx::tf32_hi(x.z); h.w = ptx::tf32_hi(x.w);
-          l.x = ptx::tf32_hi(x.x - h.x); l.y = ptx::tf32_hi(x.y - h.y);
-          l.z = ptx::tf32_hi(x.z - h.z); l.w = ptx::tf32_hi(x.w - h.w);
-          a[idx] = h;
-          lo[idx] = l;
+          if (p.corr_bf16) {
+            // the raw fp32 tile stays in place as the main operand (kind::tf32 ignores the low 13 mantissa bits:
+            // tools/exp_rawhi.py); one tile of bf16 pairs (a | a - tf32(a)) feeds the correction MMA
+            uint4 w;
+            w.x = ptx::pack_bf16x2(x.x - h.x, x.x); w.y = ptx::pack_bf16x2(x.y - h.y, x.y);
+            w.z = ptx::pack_bf16x2(x.z - h.z, x.z); w.w = ptx::pack_bf16x2(x.w - h.w, x.w);
+            reinterpret_cast<uint4*>(lo)[idx] = w;
+          } else {
+            l.x = ptx::tf32_hi(x.x - h.x); l.y = ptx::tf32_hi(x.y - h.y);
+            l.z = ptx::tf32_hi(x.z - h.z); l.w = ptx::tf32_hi(x.w - h.w);
+            a[idx] = h;
+            lo[idx] = l;
+          }
         }
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&split[s]);
@@ -268,8 +284,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
-// B [K,N] row-major -> packed [2N, Kp] K-major: rows [0,N) = tf32 hi of B^T, rows [N,2N) = lo.
-__global__ void pack_weights_tc_kernel(const float* __restrict__ B, int ldb, int K, int N, int Kp,
+// Correction scheme of the 3xTF32 contractions (gemm_tc_kernel and fused_rgcn_kernel share the packed weights):
+// 1 = one bf16-pair MMA (default), 0 = two tf32 MMAs (round 1).  TFGNN_B200_CORR_BF16 is read once per process.
+int tc_corr_bf16() {
+  static const int v = [] { const char* e = getenv("TFGNN_B200_CORR_BF16"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
+  return v;
+}
+
+// B [K,N] row-major -> packed [2N, Kp] K-major: rows [0,N) = tf32 hi of B^T, rows [N,2N) = the correction operand:
+// tf32 lo (two-MMA scheme) or the bf16 pair (b - tf32(b) | b) (pair scheme, sm100_ptx.cuh).
+__global__ void pack_weights_tc_kernel(const float* __restrict__ B, int ldb, int K, int N, int Kp, int corr_bf16,
                                        float* __restrict__ out) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)N * Kp;
@@ -279,7 +303,8 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ B, int ldb, int
   const float x = k < K ? __ldg(B + (long long)k * ldb + n) : 0.f;
   const float h = ptx::tf32_hi(x);
   out[idx] = h;
-  out[total + idx] = ptx::tf32_hi(x - h);
+  if (corr_bf16) reinterpret_cast<uint32_t*>(out)[total + idx] = ptx::pack_bf16x2(x, x - h);   // low half: lo(b), high half: b
+  else out[total + idx] = ptx::tf32_hi(x - h);
 }
 
 // ---- host side -------------------------------------------------------------------------------
@@ -339,7 +364,7 @@ size_t gemm_tc_packed_bytes(int N, int K) { return (size_t)2 * N * round_up(K, k
 int launch_pack_weights_tc(const float* B, int ldb, int K, int N, float* packed, cudaStream_t st) {
   const int Kp = round_up(K, kTcBK);
   const long long total = (long long)N * Kp;
-  pack_weights_tc_kernel<<<ceil_div(total, 256), 256, 0, st>>>(B, ldb, K, N, Kp, packed);
+  pack_weights_tc_kernel<<<ceil_div(total, 256), 256, 0, st>>>(B, ldb, K, N, Kp, tc_corr_bf16(), packed);
   TFGNN_LAUNCH_CHECK();
   return 0;
 }
@@ -364,6 +389,7 @@ int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int 
   if (stages > 4) stages = 4;
   TFGNN_REQUIRE(stages >= 2, "tcgen05 GEMM: tile does not fit shared memory");
   p.num_stages = stages;
+  p.corr_bf16 = tc_corr_bf16();
   p.C = C; p.ldc = ldc; p.epi = epi;
 
   CUtensorMap map_a, map_b;

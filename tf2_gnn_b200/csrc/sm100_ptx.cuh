@@ -248,6 +248,41 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_tf32(uint32_t m, uint32_
   return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// ---- bf16-pair correction operands (round 2) -----------------------------------------------------------------
+// 3xTF32 needs A_hi B_hi + (A_lo B_hi + A_hi B_lo).  The two small products only need ~8 bits each, so they run as ONE
+// kind::f16 (bf16) MMA over a K-interleaved operand: the 32-bit word at the position of fp32 element k holds the bf16
+// pair (A: bf16(a_k) | bf16(a_k - tf32(a_k)),  B: bf16(b_k - tf32(b_k)) | bf16(b_k)), low half first.  A row of 32 fp32
+// words is then a row of 64 bf16 K-elements in the SAME bytes, swizzle and descriptors as the fp32 tile, and
+//   sum_j A'_j B'_j = sum_k a_k lo(b_k) + lo(a_k) b_k.
+// Tensor work per K block: 4 tf32 + 4 bf16 instructions instead of 12 tf32 (-33 %); the splitter writes one tile, not two.
+__device__ __forceinline__ uint32_t pack_bf16x2(float upper, float lower) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(upper), "f"(lower));
+  return d;
+}
+// Instruction descriptor kind::f16 with bf16 operands, fp32 accumulate, A and B K-major
+__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // tf32 split of an fp32 value: hi keeps sign/exponent/10 mantissa bits (exact truncation, so the
 // tensor core sees the same bits whether it truncates or rounds), lo = x - hi (exact in fp32).
 __host__ __device__ __forceinline__ float tf32_hi(float x) {
