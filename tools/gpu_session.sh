@@ -12,7 +12,7 @@ has() { [[ " $SECTIONS " == *" $1 "* ]]; }
 
 if has tests; then
   for f in test_gpu_parity test_gpu_batch_builder test_gpu_graph_ops test_gpu_scale test_tf_golden; do
-    timeout 900 python -m pytest tests/$f.py -m gpu -q -x --durations=8 -s > $OUT/pytest_$f.log 2>&1
+    timeout 900 python -m pytest tests/$f.py -m gpu -q --maxfail=8 --durations=8 -s > $OUT/pytest_$f.log 2>&1
     echo "== $f: rc=$? $(tail -1 $OUT/pytest_$f.log)"
     grep -E "^(FAILED|ERROR)|rel err|ms per batch" $OUT/pytest_$f.log | head -20
   done
