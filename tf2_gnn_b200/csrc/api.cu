@@ -48,7 +48,8 @@ int node_gemm(const float* A, int lda, const float* B, int ldb, float* C, int ld
                      int K, const GemmEpilogue& epi, int path, tfgnn_batch* batch, int tc_slot,
                      cudaStream_t st) {
   bool want_tc = (path == TFGNN_PATH_AUTO || path == TFGNN_PATH_SORTED_TC || path == TFGNN_PATH_FUSED_TC);
-  if (want_tc && ldb == N && gemm_tc_supported(M, N, K, A, lda, C, ldc)) {
+  const bool mul_ok = epi.mul == nullptr || (epi.ldm % 4 == 0 && (reinterpret_cast<uintptr_t>(epi.mul) & 15) == 0);
+  if (want_tc && mul_ok && gemm_tc_supported(M, N, K, A, lda, C, ldc)) {   // the packing kernel takes any ldb
     void* packed = nullptr;
     int rc = batch_scratch(batch, tc_slot, gemm_tc_packed_bytes(N, K), &packed);
     if (rc) return rc;
@@ -209,13 +210,11 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
     static const bool fused_auto = [] { const char* e = getenv("TFGNN_B200_FUSED"); return !e || atoi(e) != 0; }();
     if (fused_ok && (path == TFGNN_PATH_FUSED_TC || (path == TFGNN_PATH_AUTO && fused_auto))) {
       void *packed = nullptr, *ring = nullptr;
-      rc = launch_pack_vertical(first, L, 0, D, H, H, (float*)Wcat, H, 0, st);
-      if (rc) return rc;
       rc = batch_scratch(b, 6, gemm_tc_packed_bytes(H, K), &packed);
       if (rc) return rc;
       rc = batch_scratch(b, 15, fused_rgcn_ring_bytes(D, L, H), &ring);
       if (rc) return rc;
-      rc = launch_pack_weights_tc((const float*)Wcat, H, K, H, (float*)packed, st);
+      rc = launch_pack_weights_tc_table(first, L, D, H, (float*)packed, st);   // [W_0;..;W_{L-1}] -> K-major hi / correction
       if (rc) return rc;
       GemmEpilogue epi;
       epi.act = activation;

@@ -12,6 +12,12 @@ struct GemmEpilogue {
   int V = 0, L = 0;
   long long row0 = 0;  // global node id of output row 0 (chunked launches)
   int row_norm = 0;  // 0 none, 1 mean (/max(cnt,1)), 2 sqrt_n (/sqrt(max(cnt,1)))
+  // FiLM-style chained contractions (variants.cu): val = (accumulate ? C_old : 0) + (mul ? mul[row, n] * acc : acc);
+  // row-norm / bias / activation are applied only when `finalize` (the last contraction of the chain).
+  const float* mul = nullptr;   // [M, ldm] elementwise multiplier (gamma), rows/cols aligned with C
+  int ldm = 0;
+  int accumulate = 0;
+  int finalize = 1;
 };
 
 // fp32 SIMT GEMM, any shape / alignment (universal fallback).  C[M,N] = epi(A[M,K] B[K,N]).
@@ -23,6 +29,7 @@ int launch_gemm_simt(const float* A, int lda, const float* B, int ldb, float* C,
 bool gemm_tc_supported(long long M, int N, int K, const float* A, int lda, const float* C, int ldc);
 size_t gemm_tc_packed_bytes(int N, int K);
 int launch_pack_weights_tc(const float* B, int ldb, int K, int N, float* packed, cudaStream_t st);
+int launch_pack_weights_tc_table(const PtrTable& W, int L, int D, int H, float* packed, cudaStream_t st);
 int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int ldc, long long M, int N,
                    int K, const GemmEpilogue& epi, cudaStream_t st);
 

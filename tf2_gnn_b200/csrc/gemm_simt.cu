@@ -129,9 +129,16 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float v = acc[i][jh * 4 + j];
-        if (epi.row_norm) v = v / rn;
-        if (epi.bias && n + j < N) v += __ldg(epi.bias + n + j);
-        o[j] = apply_act(v, epi.act);
+        if (n + j < N) {
+          if (epi.mul) v *= __ldg(epi.mul + r * epi.ldm + n + j);
+          if (epi.accumulate) v += C[r * ldc + n + j];
+        }
+        if (epi.finalize) {
+          if (epi.row_norm) v = v / rn;
+          if (epi.bias && n + j < N) v += __ldg(epi.bias + n + j);
+          v = apply_act(v, epi.act);
+        }
+        o[j] = v;
       }
       float* cp = C + r * ldc + n;
       if (vecC && n + 3 < N) {

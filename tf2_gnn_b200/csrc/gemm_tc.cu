@@ -211,6 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const long long row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
       const float inv_rn = row_ok ? 1.0f / tc_row_norm(p.epi, row) : 1.0f;
+      const bool chained = p.epi.mul != nullptr || p.epi.accumulate || !p.epi.finalize;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTcAccStride;
       float* stage = epi_stage + (size_t)(warp - 6) * 32 * kTcEpiPitch;
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
@@ -236,19 +237,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(mv[half][j]) + __uint_as_float(cv[half][j]);
               // uniform branches hoisted out of the element loops (predicated-off code still costs issue slots
               // and instruction-cache space: the epilogue was ~48 us per 128x256 tile before)
-              if (p.epi.row_norm) {
+              if (!chained) {
+                if (p.epi.row_norm) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] *= inv_rn;
-              }
-              if (p.epi.bias) {
-                const float4* bp = reinterpret_cast<const float4*>(p.epi.bias + n0 + c0 + half * 16);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float4 bb = __ldg(bp + j);
-                  v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+                  for (int j = 0; j < 16; ++j) v[j] *= inv_rn;
                 }
+                if (p.epi.bias) {
+                  const float4* bp = reinterpret_cast<const float4*>(p.epi.bias + n0 + c0 + half * 16);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float4 bb = __ldg(bp + j);
+                    v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+                  }
+                }
+                apply_act_vec<16>(v, p.epi.act);
               }
-              apply_act_vec<16>(v, p.epi.act);
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
                 *reinterpret_cast<float4*>(stage + lane * kTcEpiPitch + half * 16 + j) =
@@ -264,9 +267,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int r0 = 0; r0 < 32; r0 += rows_per_it) {
           const int r = r0 + rr;
           const long long grow = m0 + q * 32 + r;
+          // chained contractions: the row-norm factor of row r lives in lane r (shuffle before the row guard)
+          const float rn_r = chained ? __shfl_sync(0xffffffffu, inv_rn, r) : 1.0f;
           if (grow < p.M) {
-            const float4 val = *reinterpret_cast<const float4*>(stage + r * kTcEpiPitch + cc);
-            *reinterpret_cast<float4*>(p.C + grow * p.ldc + n0 + c0 + cc) = val;
+            float4 val = *reinterpret_cast<const float4*>(stage + r * kTcEpiPitch + cc);
+            float* cptr = p.C + grow * p.ldc + n0 + c0 + cc;
+            if (chained) {
+              float o[4] = {val.x, val.y, val.z, val.w};
+              if (p.epi.mul) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(p.epi.mul + grow * p.epi.ldm + n0 + c0 + cc));
+                o[0] *= m.x; o[1] *= m.y; o[2] *= m.z; o[3] *= m.w;
+              }
+              if (p.epi.accumulate) {
+                const float4 c = *reinterpret_cast<const float4*>(cptr);
+                o[0] += c.x; o[1] += c.y; o[2] += c.z; o[3] += c.w;
+              }
+              if (p.epi.finalize) {
+                if (p.epi.row_norm) { o[0] *= rn_r; o[1] *= rn_r; o[2] *= rn_r; o[3] *= rn_r; }
+                if (p.epi.bias) {
+                  const float4 bb = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n0 + c0 + cc));
+                  o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
+                }
+                apply_act_vec<4>(o, p.epi.act);
+              }
+              val = make_float4(o[0], o[1], o[2], o[3]);
+            }
+            *reinterpret_cast<float4*>(cptr) = val;
           }
         }
         __syncwarp();
@@ -304,6 +330,26 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ B, int ldb, int
   const float h = ptx::tf32_hi(x);
   out[idx] = h;
   if (corr_bf16) reinterpret_cast<uint32_t*>(out)[total + idx] = ptx::pack_bf16x2(x, x - h);   // low half: lo(b), high half: b
+  else out[total + idx] = ptx::tf32_hi(x - h);
+}
+
+// The same packing straight from the L per-type matrices W_l [D, H] stacked vertically (K = L*D): one launch instead
+// of pack_vertical + pack_weights_tc on the per-layer path of the fused kernel.
+__global__ void pack_weights_tc_table_kernel(PtrTable W, int L, int D, int H, int Kp, int corr_bf16,
+                                             float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)H * Kp;
+  if (idx >= total) return;
+  const int k = (int)(idx % Kp);
+  const int n = (int)(idx / Kp);
+  float x = 0.f;
+  if (k < L * D) {
+    const int l = k / D, d = k - l * D;
+    x = __ldg(reinterpret_cast<const float*>(W.p[l]) + (long long)d * H + n);
+  }
+  const float h = ptx::tf32_hi(x);
+  out[idx] = h;
+  if (corr_bf16) reinterpret_cast<uint32_t*>(out)[total + idx] = ptx::pack_bf16x2(x, x - h);
   else out[total + idx] = ptx::tf32_hi(x - h);
 }
 
@@ -360,6 +406,14 @@ bool gemm_tc_supported(long long M, int N, int K, const float* A, int lda, const
 }
 
 size_t gemm_tc_packed_bytes(int N, int K) { return (size_t)2 * N * round_up(K, kTcBK) * sizeof(float); }
+
+int launch_pack_weights_tc_table(const PtrTable& W, int L, int D, int H, float* packed, cudaStream_t st) {
+  const int Kp = round_up(L * D, kTcBK);
+  const long long total = (long long)H * Kp;
+  pack_weights_tc_table_kernel<<<ceil_div(total, 256), 256, 0, st>>>(W, L, D, H, Kp, tc_corr_bf16(), packed);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}
 
 int launch_pack_weights_tc(const float* B, int ldb, int K, int N, float* packed, cudaStream_t st) {
   const int Kp = round_up(K, kTcBK);

@@ -136,8 +136,85 @@ extern "C" int tfgnn_b200_film_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   const int Vs = (int)b->V_src;
   const float* h_tgt = h + (size_t)b->tgt_off * D;
   void *P = nullptr, *Tt = nullptr, *Wcat = nullptr, *FB = nullptr, *Fcat = nullptr;
+  GemmEpilogue none;
   int rc = batch_enter(b, st);
   if (rc) return rc;
+  static const bool film_att = [] { const char* e = getenv("TFGNN_B200_FILM_ATT"); return !e || atoi(e) != 0; }();
+  if (film_att && num_hidden_layers == 0 && aggregation != TFGNN_AGG_MAX && !act_before && D % 4 == 0 && H % 4 == 0 &&
+      (reinterpret_cast<uintptr_t>(h) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    // ---- aggregate-then-transform (round 2) ------------------------------------------------------------------
+    // Every per-edge quantity of gnn_film.py:83-108 but h_u depends on (target, type) only, so
+    //   sum_{e in A_l -> v} gamma_l(v) * (s W_l h_u [+ s W^t_l h_v]) + beta_l(v)
+    //     = gamma_l(v) * (A_l[v] W_l [+ coeff_l(v) h_v W^t_l]) + c_{v,l} beta_l(v),        A_l[v] = s sum_e h_u,
+    // with s = 1/(c+eps) or 1, coeff = c s.  The per-edge work is the plain row gather (edge_reduce, HBM-bound, exactly
+    // the RGCN traffic); everything else is node-level contractions chained through the GEMM epilogue
+    // (C += gamma * acc): no [V, L*H] projected table, no [V, 2*L*H] FiLM table, and on a target-range shard only
+    // the OWNED rows are ever multiplied (the transform-then-aggregate form projects all num_nodes_total sources on
+    // every rank: 123 GB per rank at BASELINE config 5).
+    const int K = L * D;
+    void *A = nullptr, *T = nullptr, *G = nullptr, *Fb = nullptr;
+    rc = batch_scratch(b, 2, (size_t)V * K * sizeof(float), &A);
+    if (rc) return rc;
+    rc = batch_scratch(b, 4, (size_t)V * K * sizeof(float), &T);
+    if (rc) return rc;
+    rc = batch_scratch(b, 11, (size_t)V * H * sizeof(float), &G);
+    if (rc) return rc;
+    rc = batch_scratch(b, 3, (size_t)K * H * sizeof(float), &Fb);
+    if (rc) return rc;
+    {
+      EdgeReduceParams p;
+      p.X = h; p.ldx = D; p.x_type_stride = 0;
+      p.row_ptr = b->row_ptr; p.src = b->src_sorted;
+      p.out = (float*)A; p.ldo = K; p.out_type_stride = D;
+      p.V = V; p.L = L; p.C = D; p.normalize = normalize;
+      rc = launch_edge_reduce(p, /*merged=*/false, st);
+      if (rc) return rc;
+    }
+    // beta part: out = [c_0 h_v | .. | c_{L-1} h_v] [Fbeta_0; ..; Fbeta_{L-1}]   (one K = L*D contraction, not finalised)
+    rc = launch_target_term(h_tgt, D, b->row_ptr, V, L, D, /*normalize=*/0, (float*)T, K, 0, st);
+    if (rc) return rc;
+    PtrTable fbeta{};
+    for (int l = 0; l < L; ++l) fbeta.p[l] = reinterpret_cast<const float*>(film.p[l]) + H;
+    rc = launch_pack_vertical(fbeta, L, 0, D, H, 2 * H, (float*)Fb, H, 0, st);
+    if (rc) return rc;
+    GemmEpilogue raw;
+    raw.finalize = 0;
+    rc = node_gemm((const float*)T, K, (const float*)Fb, H, out, H, V, H, K, raw, path, b, 6, st);
+    if (rc) return rc;
+    if (use_target && normalize) {   // coeff(v,l) h_v with the normalised coefficient (the beta operand used the raw count)
+      rc = launch_target_term(h_tgt, D, b->row_ptr, V, L, D, 1, (float*)T, K, 0, st);
+      if (rc) return rc;
+    }
+    for (int l = 0; l < L; ++l) {
+      // gamma_l = h_v Fgamma_l  (first H columns of F_l [D, 2H])
+      rc = node_gemm(h_tgt, D, reinterpret_cast<const float*>(film.p[l]), 2 * H, (float*)G, H, V, H, D, none, path, b, 6, st);
+      if (rc) return rc;
+      GemmEpilogue chain;
+      chain.mul = (const float*)G; chain.ldm = H;
+      chain.accumulate = 1;
+      chain.finalize = 0;
+      const bool last_src = !use_target && l == L - 1;
+      if (last_src) {
+        chain.finalize = 1;
+        chain.act = activation;
+        chain.row_norm = agg_row_norm(aggregation); chain.row_ptr = b->row_ptr; chain.V = V; chain.L = L;
+      }
+      rc = node_gemm((const float*)A + (size_t)l * D, K, reinterpret_cast<const float*>(first.p[l]), H, out, H, V, H, D,
+                     chain, path, b, 6, st);
+      if (rc) return rc;
+      if (use_target) {
+        if (l == L - 1) {
+          chain.finalize = 1;
+          chain.act = activation;
+          chain.row_norm = agg_row_norm(aggregation); chain.row_ptr = b->row_ptr; chain.V = V; chain.L = L;
+        }
+        rc = node_gemm((const float*)T + (size_t)l * D, K, reinterpret_cast<const float*>(first.p[l]) + (size_t)D * H, H,
+                       out, H, V, H, D, chain, path, b, 6, st);
+        if (rc) return rc;
+      }
+    }
+    return 0;
+  }
   rc = batch_scratch(b, 2, (size_t)Vs * LH * sizeof(float), &P);
   if (rc) return rc;
   rc = batch_scratch(b, 3, (size_t)D * LH * sizeof(float), &Wcat);
@@ -146,7 +223,6 @@ extern "C" int tfgnn_b200_film_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   if (rc) return rc;
   rc = batch_scratch(b, 12, (size_t)D * 2 * LH * sizeof(float), &Fcat);
   if (rc) return rc;
-  GemmEpilogue none;
   if (num_hidden_layers > 0) {
     // hidden layers in the edge MLP: FiLM parameters at node level, messages on the literal per-edge path
     rc = launch_pack_horizontal(film, L, 0, D, 2 * H, 2 * H, (float*)Fcat, 2 * LH, st);
