@@ -125,10 +125,13 @@ def _load_exchange(ex, w):
 
 
 @pytest.mark.parametrize("mode", ["mean", "gru", "mlp"])
-@pytest.mark.parametrize("weighting", ["softmax", "sigmoid"])
-@pytest.mark.parametrize("V,G,H", [(900, 50, 32), (6000, 4, 128)])
+@pytest.mark.parametrize("weighting,V,G,H", [("softmax", 900, 50, 32), ("softmax", 6000, 4, 128),
+                                             ("sigmoid", 900, 50, 32), ("sigmoid", 6000, 400, 128)])
 def test_graph_global_exchange(mode, weighting, V, G, H):
-    """graph_global_exchange.py:106-183, inference mode."""
+    """graph_global_exchange.py:106-183, inference mode.  Softmax weights sum to 1 per graph, so PPI-sized graphs (1500
+    nodes) stay O(1); sigmoid weights sum ~0.5 per NODE (the reference uses them on molecule-sized graphs: with 1500-node
+    graphs the graph representation reaches ~1e2 and saturates the GRU / MLP that follow, where 1e-5 of the OUTPUT scale is
+    below what float32 itself delivers), hence QM9-sized graphs (15 nodes) for that weighting."""
     _need_gpu()
     from tf2_gnn_b200.layers import (GraphGlobalExchangeInput, GraphGlobalGRUExchange, GraphGlobalMeanExchange,
                                      GraphGlobalMLPExchange)

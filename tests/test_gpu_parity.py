@@ -264,6 +264,32 @@ def test_rgcn_fused_kernel_cta_pairs(monkeypatch, pair, V, D, H, L, E, agg):
     assert np.array_equal(a.cpu().numpy(), a2.cpu().numpy())
 
 
+@pytest.mark.parametrize("V,D,H,L,E,agg,act", [
+    (129, 64, 64, 3, 1000, "sum", "relu"),          # 2 tiles, the second with a single row
+    (8000, 320, 320, 3, 120000, "sum", "relu"),      # BASELINE cfg1 shape (63 tiles): H/2 = 160 columns per CTA
+    (5000, 128, 128, 4, 30000, "mean", "tanh"),      # tanh -> two-tf32-MMA corrections in the split kernel
+    (9000, 256, 256, 4, 40000, "sqrt_n", "gelu"),    # 71 tiles: just under SMs / 2
+    (2500, 128, 512, 2, 9000, "sum", "relu"),        # H/2 = 256: full-width accumulators per CTA
+    (700, 96, 64, 5, 6000, "sum", "leaky_relu"),     # D = 96: three 32-float K blocks per type
+])
+def test_rgcn_fused_kernel_split_tiles(monkeypatch, V, D, H, L, E, agg, act):
+    """Split-tile mode of the fused kernel (batches with fewer tiles than SMs / 2: two CTAs of a cluster share a tile, half
+    of the gathered rows and half of the output columns each) against the oracle, against the one-CTA-per-tile kernel
+    (same bits: the K order of every output element is unchanged) and run to run."""
+    _need_gpu()
+    rng = np.random.default_rng(V + H)
+    adjs = random_graph(rng, V, L, E, hub=True, self_loops=True, dups=True)
+    p = mo.default_hyperparameters("rgcn")
+    p.update(hidden_dim=H, aggregation_function=agg, message_activation_function=act)
+    monkeypatch.setenv("TFGNN_B200_FUSED_SPLIT", "1")
+    a = run_case("rgcn", p, V, D, L, adjs, seed=V, path="fused_tc")
+    a2 = run_case("rgcn", p, V, D, L, adjs, seed=V, path="fused_tc")
+    assert np.array_equal(a.cpu().numpy(), a2.cpu().numpy())
+    monkeypatch.setenv("TFGNN_B200_FUSED_SPLIT", "0")
+    b = run_case("rgcn", p, V, D, L, adjs, seed=V, path="fused_tc")
+    assert np.array_equal(a.cpu().numpy(), b.cpu().numpy())
+
+
 @pytest.mark.parametrize("q", ["1", "2", "3", "8"])
 def test_rgcn_fused_kernel_gather_ring_depths(monkeypatch, q):
     """The rolling cp.async gather ring with Q = 1..8 row slots per warp: long segments (hubs > 32 edges cross the

@@ -214,12 +214,13 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
       if (rc) return rc;
       rc = batch_scratch(b, 15, fused_rgcn_ring_bytes(D, L, H), &ring);
       if (rc) return rc;
-      rc = launch_pack_weights_tc_table(first, L, D, H, (float*)packed, st);   // [W_0;..;W_{L-1}] -> K-major hi / correction
+      const int corr = fused_corr_bf16(activation);
+      rc = launch_pack_weights_tc_table(first, L, D, H, corr, (float*)packed, st);   // [W_0;..;W_{L-1}] -> K-major hi / correction
       if (rc) return rc;
       GemmEpilogue epi;
       epi.act = activation;
       epi.row_norm = row_norm; epi.row_ptr = b->row_ptr; epi.V = V; epi.L = L;
-      return launch_fused_rgcn(h, D, b->row_ptr, b->src_sorted, b->M_in, V, L, normalize, (const float*)packed, H,
+      return launch_fused_rgcn(h, D, b->row_ptr, b->src_sorted, b->M_in, V, L, normalize, (const float*)packed, corr, H,
                                (float*)ring, out, ldo, epi, st);
     }
     if (pipelined) {

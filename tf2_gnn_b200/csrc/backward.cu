@@ -108,6 +108,10 @@ constexpr int kTnTile = 128, kTnMB = 16, kTnChunk = 8192;
 __global__ void __launch_bounds__(256, 2)
 gemm_tn_partial_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, long long M,
                        int Kd, int N, float* __restrict__ Cpart) {
+  // 16-byte row loads need 4-float leading dimensions and aligned bases (rgcn_bwd guarantees them; the Dense backward
+  // of e.g. a 50-feature input layer does not)
+  const bool vecA = (lda & 3) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0;
+  const bool vecB = (ldb & 3) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0;
   __shared__ __align__(16) float As[2][kTnMB][kTnTile];
   __shared__ __align__(16) float Bs[2][kTnMB][kTnTile];
   const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -124,17 +128,19 @@ gemm_tn_partial_kernel(const float* __restrict__ A, int lda, const float* __rest
       if (m < m_end) {
         const float* pa = A + m * lda + k0 + lc;
         const float* pb = B + m * ldb + n0 + lc;
-        if (k0 + lc + 3 < Kd) va = __ldg(reinterpret_cast<const float4*>(pa));
+        if (vecA && k0 + lc + 3 < Kd) va = __ldg(reinterpret_cast<const float4*>(pa));
         else {
           if (k0 + lc < Kd) va.x = pa[0];
           if (k0 + lc + 1 < Kd) va.y = pa[1];
           if (k0 + lc + 2 < Kd) va.z = pa[2];
+          if (k0 + lc + 3 < Kd) va.w = pa[3];
         }
-        if (n0 + lc + 3 < N) vb = __ldg(reinterpret_cast<const float4*>(pb));
+        if (vecB && n0 + lc + 3 < N) vb = __ldg(reinterpret_cast<const float4*>(pb));
         else {
           if (n0 + lc < N) vb.x = pb[0];
           if (n0 + lc + 1 < N) vb.y = pb[1];
           if (n0 + lc + 2 < N) vb.z = pb[2];
+          if (n0 + lc + 3 < N) vb.w = pb[3];
         }
       }
       ra[i] = va;

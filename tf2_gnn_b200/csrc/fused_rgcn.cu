@@ -96,6 +96,7 @@ struct GatherIssue {
   int lane, gw, Q, ncalls;
   long long unit0, unit_step;
   int ctas, rank;
+  int rpw, row_off;      // rows of the tile owned by this warp, first row of this CTA's share of the tile
   uint32_t buf_s;        // shared-window address of this warp's slot 0, + 16 * lane
   uint32_t row_bytes;
   int ic;                // call being issued
@@ -109,9 +110,9 @@ struct GatherIssue {
     const int u = n / L;
     l = n - u * L;
     const long long tile = (unit0 + (long long)u * unit_step) * ctas + rank;
-    v0 = (int)(tile * kFuBM) + gw * (kFuBM / kFuGatherWarps);
+    v0 = (int)(tile * kFuBM) + row_off + gw * rpw;
     nr = V - v0;
-    nr = nr < 0 ? 0 : (nr > kFuBM / kFuGatherWarps ? kFuBM / kFuGatherWarps : nr);
+    nr = nr < 0 ? 0 : (nr > rpw ? rpw : nr);
   }
   __device__ __forceinline__ int rp_of(int n) const {   // row_ptr of the call's rows, lane r -> first edge of row r
     if (n >= ncalls) return 0;
@@ -186,12 +187,16 @@ __device__ __forceinline__ void cp_async_wait_oldest(int Q) {   // at most Q-1 g
   }
 }
 
+// split != 0 (split-tile mode): this CTA gathers only rows [split_rank*64, split_rank*64 + 64) of every tile; the slot
+// is shared with the peer CTA of the cluster, whose slot_ready barrier gets a (cluster-scope release) arrival as well.
 template <int NV>
 __device__ __forceinline__ void gather_warp_main(const FusedParams& p, int lane, int gw, int Q, uint8_t* bufs,
                                                  long long unit0, long long unit_step, long long total_units,
                                                  int ctas, int rank, int ring_row0, uint64_t* slot_ready,
-                                                 uint64_t* slot_free) {
-  constexpr int kRowsPerWarp = kFuBM / kFuGatherWarps;
+                                                 uint64_t* slot_free, int split, int split_rank,
+                                                 uint32_t peer_slot_ready0) {
+  const int kRowsPerWarp = split ? kFuBM / 2 / kFuGatherWarps : kFuBM / kFuGatherWarps;
+  const int row_off = split ? split_rank * (kFuBM / 2) : 0;
   const int D = p.D, C4 = p.D >> 2, normalize = p.normalize;
   const bool no_store = p.debug_skip & 16;   // timing experiment: gathered rows are not written to the ring
   const int kFuSlots = p.num_slots;
@@ -203,6 +208,7 @@ __device__ __forceinline__ void gather_warp_main(const FusedParams& p, int lane,
   g.skip = p.debug_skip & 1; g.C4 = C4;
   g.lane = lane; g.gw = gw; g.Q = Q; g.ncalls = (int)(my_units * p.L);
   g.unit0 = unit0; g.unit_step = unit_step; g.ctas = ctas; g.rank = rank;
+  g.rpw = kRowsPerWarp; g.row_off = row_off;
   g.buf_s = ptx::smem_u32(bufs) + (uint32_t)lane * 16u;
   g.row_bytes = (uint32_t)p.D * 4;
   g.ic = 0; g.islot = 0; g.in_blk = 0; g.ibuf = g.buf_s;
@@ -230,8 +236,9 @@ __device__ __forceinline__ void gather_warp_main(const FusedParams& p, int lane,
     crp = crp_next;
     crp_next = g.rp_of(cc + 2);
     const int slot = cc % kFuSlots;
-    ptx::mbar_wait(&slot_free[slot], ((cc / kFuSlots) & 1) ^ 1);
-    float* dst = ring + ((size_t)ring_row0 + (size_t)slot * kFuBM + (size_t)gw * kRowsPerWarp) * D + 4 * lane;
+    if (split) ptx::mbar_wait_cluster(&slot_free[slot], ((cc / kFuSlots) & 1) ^ 1);   // the peer's reads are done too
+    else ptx::mbar_wait(&slot_free[slot], ((cc / kFuSlots) & 1) ^ 1);
+    float* dst = ring + ((size_t)ring_row0 + (size_t)slot * kFuBM + (size_t)row_off + (size_t)gw * kRowsPerWarp) * D + 4 * lane;
     int row = 0;
     int seg_begin = __shfl_sync(0xffffffffu, rp, 0);
     int seg_end = __shfl_sync(0xffffffffu, rp, 1);
@@ -273,7 +280,14 @@ __device__ __forceinline__ void gather_warp_main(const FusedParams& p, int lane,
     // generic-proxy global writes -> visible to the TMA (async proxy) reads of this CTA
     asm volatile("fence.proxy.async.global;" ::: "memory");
     __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(&slot_ready[slot]);
+    if (lane == 0) {
+      if (split) {   // both CTAs of the cluster read the whole slot: tell the peer's TMA producer too
+        ptx::mbar_arrive_cluster_release(ptx::mapa_shared(ptx::smem_u32(&slot_ready[slot]), (uint32_t)split_rank));
+        ptx::mbar_arrive_cluster_release(peer_slot_ready0 + (uint32_t)slot * 8u);
+      } else {
+        ptx::mbar_arrive(&slot_ready[slot]);
+      }
+    }
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
@@ -285,10 +299,15 @@ __device__ __forceinline__ void gather_warp_main(const FusedParams& p, int lane,
 // targets exactly as before, but the MMA is one cta_group::2 instruction of M = 256 issued by the leader (rank 0):
 // every CTA stages only HALF of the weight tile's N rows, so the weight stream from L2 (the largest on-chip
 // traffic of the kernel: 2 MB per 128 targets at H = 256) and its shared-memory footprint are halved.
-template <int NV, int BK, int CTAS>
+// SPLIT (small batches, fewer than SMs/2 tiles): the two CTAs of a cluster share ONE 128-target tile.  Each gathers half of
+// its rows into the common ring slot and contracts the whole tile with its HALF of the output columns (cta_group::1 MMAs,
+// N = H/2 per CTA): the gather (bound by one SM's L2 bandwidth when a tile is all an SM has) and the K loop are both
+// spread over twice as many SMs.  Ring slots are released only when both CTAs have read them.
+template <int NV, int BK, int CTAS, bool SPLIT = false>
 __global__ void __launch_bounds__(kFuThreads, 1)
 fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                   const FusedParams p) {
+  static_assert(!(SPLIT && CTAS != 1), "split-tile mode uses single-CTA MMAs");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kFuBK = BK;
@@ -313,9 +332,11 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CTAS == 2 ? ptx::cluster_ctarank() : 0u;
+  const uint32_t srank = SPLIT ? ptx::cluster_ctarank() : 0u;      // split-tile mode: which half (rows to gather, columns to produce)
+  constexpr int kClu = (CTAS == 2 || SPLIT) ? 2 : 1;               // CTAs per cluster
   // one unit = CTAS consecutive 128-target tiles (one per CTA of the pair); the N dimension is covered in n_pass passes
   const long long total_units = (p.m_tiles + CTAS - 1) / CTAS;
-  const long long unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;
+  const long long unit0 = blockIdx.x / kClu, unit_step = gridDim.x / kClu;
   const int n_pass = p.n_tiles;
   const int kFuSlots = p.num_slots;
   const int kb_per_tile = p.L * p.kb_per_type;
@@ -333,12 +354,12 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       ptx::mbar_init(&tmem_empty[a], 4 * CTAS);  // one arrival per epilogue warp
     }
     for (int r = 0; r < kFuMaxSlots; ++r) {
-      ptx::mbar_init(&slot_ready[r], kFuGatherWarps);
-      ptx::mbar_init(&slot_free[r], 128);
+      ptx::mbar_init(&slot_ready[r], kFuGatherWarps * (SPLIT ? 2 : 1));   // split: the peer's gather warps arrive too
+      ptx::mbar_init(&slot_free[r], 4 * (SPLIT ? 2 : 1));                  // one arrival per splitter warp (of both CTAs)
     }
     ptx::fence_barrier_init();
   }
-  if (CTAS == 2) {
+  if (kClu == 2) {
     // both CTAs' barriers must exist before any remote arrive / multicast commit can land on them
     __syncthreads();
     ptx::cluster_sync_all();
@@ -354,7 +375,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (CTAS == 2) ptx::cluster_sync_all();   // both halves of the pair's TMEM are allocated before the first MMA
+  if (kClu == 2) ptx::cluster_sync_all();   // both halves of the pair's TMEM are allocated before the first MMA
   ptx::tc_fence_after_sync();
   // the leader's barriers that collect arrivals from both CTAs (split[], tmem_empty[])
   const uint32_t split_remote0 = CTAS == 2 ? ptx::mapa_shared(ptx::smem_u32(&split[0]), 0) : 0u;
@@ -362,7 +383,10 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t n_acc = p.block_n <= 128 ? 2 : 1;
   const uint32_t corr_off = p.block_n <= 128 ? 128 : 256;
-  const int ring_row0 = blockIdx.x * kFuSlots * kFuBM;  // first ring row of this CTA
+  // first ring row of this CTA (split-tile mode: of this CLUSTER, both CTAs fill and read the same slots)
+  const int ring_row0 = (SPLIT ? blockIdx.x / 2 : blockIdx.x) * kFuSlots * kFuBM;
+  const uint32_t peer_slot_ready0 = SPLIT ? ptx::mapa_shared(ptx::smem_u32(&slot_ready[0]), srank ^ 1u) : 0u;
+  const uint32_t peer_slot_free0 = SPLIT ? ptx::mapa_shared(ptx::smem_u32(&slot_free[0]), srank ^ 1u) : 0u;
 
   // N passes: main + correction accumulators need 2*block_n <= 512 TMEM columns, so H in (256, 512] is covered
   // in two passes of block_n = H/2 columns over the SAME gathered ring slots (the ring then holds all L types of
@@ -374,11 +398,12 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const uint64_t pol_keep = ptx::policy_evict_last();   // ring slots and the 2 MB of weights stay in L2
       for (long long unit = unit0; unit < total_units; unit += unit_step, slot_it += p.L) {
        for (int pass = 0; pass < n_pass; ++pass) {
-        const int n0 = pass * p.block_n + (int)rank * b_rows;
+        const int n0 = pass * p.block_n + (int)rank * b_rows + (int)srank * p.block_n;
         for (int l = 0; l < p.L; ++l) {
           const uint32_t sq = slot_it + l;
           const int slot = sq % kFuSlots;
-          ptx::mbar_wait(&slot_ready[slot], (sq / kFuSlots) & 1);
+          if (SPLIT) ptx::mbar_wait_cluster(&slot_ready[slot], (sq / kFuSlots) & 1);   // half of the rows come from the peer SM
+          else ptx::mbar_wait(&slot_ready[slot], (sq / kFuSlots) & 1);
           for (int kb = 0; kb < p.kb_per_type; ++kb, ++it) {
             const int s = it % S;
             const uint32_t ph = (it / S) & 1;
@@ -470,12 +495,16 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (kb == p.kb_per_type - 1 && pass == n_pass - 1) {
             // all TMA reads of the slot have landed: its lines are dead.  Discard them from L2 so that they are
             // never written back to HBM (the ring is pure on-chip hand-off), then hand the slot back.
-            if (p.discard_ring) {
+            if (p.discard_ring && !SPLIT) {   // split-tile mode: the peer may still be reading the slot
               const char* sb = reinterpret_cast<const char*>(p.ring + ((size_t)ring_row0 + (size_t)(slot_it % kFuSlots) * kFuBM) * p.D);
               const int lines = kFuBM * p.D * 4 / 128;
               for (int i = tid; i < lines; i += 128) ptx::discard_l2_128(sb + (size_t)i * 128);
             }
-            ptx::mbar_arrive(&slot_free[slot_it % kFuSlots]);
+            __syncwarp();
+            if (lane == 0) {
+              ptx::mbar_arrive(&slot_free[slot_it % kFuSlots]);
+              if (SPLIT) ptx::mbar_arrive_cluster_release(peer_slot_free0 + (uint32_t)(slot_it % kFuSlots) * 8u);
+            }
           }
           float4* a = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
           float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + kFuATileBytes);
@@ -515,7 +544,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (long long tp = unit0 * n_pass; tp < total_units * n_pass;
          tp = (tp % n_pass == n_pass - 1) ? tp + (unit_step - 1) * n_pass + 1 : tp + 1, ++tile_count) {
       const long long m0 = ((tp / n_pass) * CTAS + rank) * kFuBM;
-      const int n0 = (int)(tp % n_pass) * p.block_n;
+      const int n0 = (int)(tp % n_pass) * p.block_n + (int)srank * p.block_n;
       const uint32_t acc = tile_count % n_acc, acc_ph = (tile_count / n_acc) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_ph);
       ptx::tc_fence_after_sync();
@@ -591,12 +620,13 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // ================= gather warps =================
     const int gw = warp - kFuFirstGatherWarp;
     gather_warp_main<NV>(p, lane, gw, p.gather_q, gbuf + (size_t)gw * p.gather_q * ((size_t)p.D * 4), unit0,
-                         unit_step, total_units, CTAS, (int)rank, ring_row0, slot_ready, slot_free);
+                         unit_step, total_units, CTAS, (int)rank, ring_row0, slot_ready, slot_free, SPLIT ? 1 : 0,
+                         (int)srank, peer_slot_ready0);
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (CTAS == 2) ptx::cluster_sync_all();   // the leader's MMAs read the peer's shared memory: leave together
+  if (kClu == 2) ptx::cluster_sync_all();   // the leader's MMAs read the peer's shared memory / remote arrivals: leave together
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     if (CTAS == 2) ptx::tmem_dealloc_pair(tmem_base, kFuTmemCols);
@@ -693,18 +723,19 @@ void restore_l2_persist_carveout() {
 }
 
 constexpr int kFuMaxGrid = 160;
-static int fused_num_slots(int L, int H) {
+static int fused_num_slots(int L, int H, bool split = false) {
   static const int env_slots = [] { const char* e = getenv("TFGNN_B200_RING_SLOTS"); return e ? atoi(e) : 0; }();
-  if (H > 256) return L + 1;
+  if (H > 256 && !split) return L + 1;
   return (env_slots >= 2 && env_slots <= kFuMaxSlots) ? env_slots : 4;   // cfg2: 4 slots 4.61 ms, 3: 4.63-4.88, 5: 4.70, 2: 5.05
 }
 size_t fused_rgcn_ring_bytes(int D, int L, int H) {
-  return (size_t)kFuMaxGrid * fused_num_slots(L, H) * kFuBM * D * sizeof(float);
+  const int slots = fused_num_slots(L, H) > 4 ? fused_num_slots(L, H) : 4;   // covers the split-tile mode (4 slots) as well
+  return (size_t)kFuMaxGrid * slots * kFuBM * D * sizeof(float);
 }
 
 int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src, long long M, int V, int L,
-                      int normalize, const float* packedB, int H, float* ring, float* out, int ldo, const GemmEpilogue& epi,
-                      cudaStream_t st) {
+                      int normalize, const float* packedB, int corr_bf16, int H, float* ring, float* out, int ldo,
+                      const GemmEpilogue& epi, cudaStream_t st) {
   EncodeTiledFn encode = fu_encode_fn();
   if (!encode) {
     set_error(TFGNN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -721,24 +752,29 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   p.discard_ring = discard_env;
   static const int dbg_env = [] { const char* e = getenv("TFGNN_B200_DEBUG_SKIP"); return e ? atoi(e) : 0; }();
   p.debug_skip = dbg_env;
-  p.corr_bf16 = tc_corr_bf16();
+  p.corr_bf16 = corr_bf16;
   p.N = H;
-  p.n_tiles = H > 256 ? 2 : 1;            // N passes
-  p.block_n = H / p.n_tiles;
-  p.num_slots = fused_num_slots(L, H);
   p.m_tiles = ((long long)V + kFuBM - 1) / kFuBM;
+  if (sms > kFuMaxGrid) sms = kFuMaxGrid;
+  // Split-tile mode (small batches): fewer tiles than half the SMs -> two CTAs share each tile (rows of the gather,
+  // columns of the contraction).  TFGNN_B200_FUSED_SPLIT: 0 = never, 1 = default rule (read per call: the tests sweep it)
+  const char* split_str = getenv("TFGNN_B200_FUSED_SPLIT");
+  const int split_env = split_str ? atoi(split_str) : 1;
+  const char* pair_str = getenv("TFGNN_B200_FUSED_PAIR");
+  const int pair_env = pair_str ? atoi(pair_str) : 1;
+  const bool split = split_env != 0 && pair_env != 2 && 2 * p.m_tiles <= sms && H % 32 == 0 && H / 2 >= 16 && H / 2 <= 256;
+  p.n_tiles = split ? 1 : (H > 256 ? 2 : 1);            // N passes (per CTA)
+  p.block_n = split ? H / 2 : H / p.n_tiles;
+  p.num_slots = fused_num_slots(L, H, split);
   // K block: 32 floats (128 B rows, SWIZZLE_128B) since the CTA-pair kernel; measured on cfg2 4.63 ms vs 4.88 ms with
   // 16 floats, H=320 6.47 vs 6.61 ms (half as many barrier round trips per byte; 2 stages of 64 KB still fit)
   static const int bk_env = [] { const char* e = getenv("TFGNN_B200_FUSED_BK"); return e ? atoi(e) : 32; }();
   p.C = out; p.ldc = ldo; p.epi = epi;
-  if (sms > kFuMaxGrid) sms = kFuMaxGrid;
   // CTA pairs (cta_group::2) when there is at least one 128-target tile per SM; tiny batches keep single CTAs
   // TFGNN_B200_FUSED_PAIR: 0 = never, 1 = default rule, 2 = whenever there are two tiles (tests); read per call
-  const char* pair_str = getenv("TFGNN_B200_FUSED_PAIR");
-  const int pair_env = pair_str ? atoi(pair_str) : 1;
-  const bool pair_ok = (p.block_n / 2) % 8 == 0 && sms >= 2;
+  const bool pair_ok = !split && (p.block_n / 2) % 8 == 0 && sms >= 2;
   const int ctas = (pair_ok && ((pair_env == 1 && p.m_tiles >= sms) || (pair_env == 2 && p.m_tiles >= 2))) ? 2 : 1;
-  int grid = (int)(p.m_tiles < sms ? p.m_tiles : sms);
+  int grid = split ? (int)(2 * p.m_tiles) : (int)(p.m_tiles < sms ? p.m_tiles : sms);
   if (ctas == 2) grid &= ~1;
   // shared memory: S pipeline stages + epilogue staging + Q row slots for each of the 16 gather warps.
   // Q = 4 rolling copies per warp saturate HBM in isolation (tools/gather_ceiling.cu); the pipeline gets what is left.
@@ -817,7 +853,8 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
     };
 #define TFGNN_FU_SET(NV) \
     set((const void*)fused_rgcn_kernel<NV, 16, 1>); set((const void*)fused_rgcn_kernel<NV, 32, 1>); \
-    set((const void*)fused_rgcn_kernel<NV, 16, 2>); set((const void*)fused_rgcn_kernel<NV, 32, 2>);
+    set((const void*)fused_rgcn_kernel<NV, 16, 2>); set((const void*)fused_rgcn_kernel<NV, 32, 2>); \
+    set((const void*)fused_rgcn_kernel<NV, 16, 1, true>); set((const void*)fused_rgcn_kernel<NV, 32, 1, true>);
     TFGNN_FU_SET(1) TFGNN_FU_SET(2) TFGNN_FU_SET(3) TFGNN_FU_SET(4)
 #undef TFGNN_FU_SET
   });
@@ -829,14 +866,15 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = (unsigned)ctas;
+  attr[0].val.clusterDim.x = (unsigned)(split ? 2 : ctas);
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
 #define TFGNN_FU_LAUNCH(NV, BK)                                                                             \
-  TFGNN_CUDA(ctas == 2 ? cudaLaunchKernelEx(&cfg, fused_rgcn_kernel<NV, BK, 2>, map_a, map_b, p)            \
-                       : cudaLaunchKernelEx(&cfg, fused_rgcn_kernel<NV, BK, 1>, map_a, map_b, p))
+  TFGNN_CUDA(split ? cudaLaunchKernelEx(&cfg, fused_rgcn_kernel<NV, BK, 1, true>, map_a, map_b, p)          \
+             : ctas == 2 ? cudaLaunchKernelEx(&cfg, fused_rgcn_kernel<NV, BK, 2>, map_a, map_b, p)          \
+                         : cudaLaunchKernelEx(&cfg, fused_rgcn_kernel<NV, BK, 1>, map_a, map_b, p))
   if (kFuBK == 32) {
     switch (nv) {
       case 1: TFGNN_FU_LAUNCH(1, 32); break;

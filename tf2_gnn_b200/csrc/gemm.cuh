@@ -29,7 +29,7 @@ int launch_gemm_simt(const float* A, int lda, const float* B, int ldb, float* C,
 bool gemm_tc_supported(long long M, int N, int K, const float* A, int lda, const float* C, int ldc);
 size_t gemm_tc_packed_bytes(int N, int K);
 int launch_pack_weights_tc(const float* B, int ldb, int K, int N, float* packed, cudaStream_t st);
-int launch_pack_weights_tc_table(const PtrTable& W, int L, int D, int H, float* packed, cudaStream_t st);
+int launch_pack_weights_tc_table(const PtrTable& W, int L, int D, int H, int corr_bf16, float* packed, cudaStream_t st);
 int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int ldc, long long M, int N,
                    int K, const GemmEpilogue& epi, cudaStream_t st);
 
@@ -37,10 +37,11 @@ int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int 
 bool fused_rgcn_supported(long long V, int L, int D, int H, const float* h, const float* out, int ldo);
 size_t fused_rgcn_ring_bytes(int D, int L, int H);
 int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src, long long M, int V, int L, int normalize,
-                      const float* packedB, int H, float* ring, float* out, int ldo, const GemmEpilogue& epi,
+                      const float* packedB, int corr_bf16, int H, float* ring, float* out, int ldo, const GemmEpilogue& epi,
                       cudaStream_t st);
 
-int tc_corr_bf16();   // correction scheme of the 3xTF32 contractions (gemm_tc.cu)
+int gemm_corr_bf16();                 // correction scheme of the 3xTF32 contractions (gemm_tc.cu)
+int fused_corr_bf16(int activation);
 int set_l2_persist_mb(int mb);
 void restore_l2_persist_carveout();
 void pool_trim_all();

@@ -310,11 +310,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
 }
 
-// Correction scheme of the 3xTF32 contractions (gemm_tc_kernel and fused_rgcn_kernel share the packed weights):
-// 1 = one bf16-pair MMA (default), 0 = two tf32 MMAs (round 1).  TFGNN_B200_CORR_BF16 is read once per process.
-int tc_corr_bf16() {
-  static const int v = [] { const char* e = getenv("TFGNN_B200_CORR_BF16"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
+// Correction scheme of the 3xTF32 contractions (rows [N, 2N) of the packed weights differ between the two):
+//   0 = two tf32 MMAs  A_lo B_hi + A_hi B_lo   (round 1; ~3e-7 of the pre-activation scale in exact accumulation)
+//   1 = ONE bf16-pair MMA (sm100_ptx.cuh)      (-33 % tensor work; ~1.5e-6 of the pre-activation scale)
+// Measured on B200 (gpurun r2a): the fused RGCN kernel gains 5 % from the pair scheme (cfg2 4.59 -> 4.37 ms) and its
+// error at K = L*D >= 768 is dominated by the tensor core's truncating accumulate either way (3.56e-6 vs 3.0e-6 of
+// max|out| at cfg2).  The generic GEMM is latency-bound at its shapes, gains nothing, and feeds saturating
+// activations (tanh / sigmoid of Dense layers and GRU gates) that turn an error relative to the PRE-activation scale
+// into one relative to 1: with the pair scheme five parity tests landed at 1.2-2.1e-5.  So: the GEMM keeps scheme 0;
+// the fused kernel uses scheme 1 unless its activation is tanh.  TFGNN_B200_CORR_BF16 = 0/1 forces the FUSED kernel's
+// scheme, TFGNN_B200_CORR_BF16_GEMM = 1 the GEMM's (experiments).
+int gemm_corr_bf16() {
+  static const int v = [] { const char* e = getenv("TFGNN_B200_CORR_BF16_GEMM"); return e && atoi(e) != 0 ? 1 : 0; }();
   return v;
+}
+int fused_corr_bf16(int activation) {
+  static const int v = [] { const char* e = getenv("TFGNN_B200_CORR_BF16"); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }();
+  if (v >= 0) return v;
+  return activation == TFGNN_ACT_TANH ? 0 : 1;
 }
 
 // B [K,N] row-major -> packed [2N, Kp] K-major: rows [0,N) = tf32 hi of B^T, rows [N,2N) = the correction operand:
@@ -407,10 +420,10 @@ bool gemm_tc_supported(long long M, int N, int K, const float* A, int lda, const
 
 size_t gemm_tc_packed_bytes(int N, int K) { return (size_t)2 * N * round_up(K, kTcBK) * sizeof(float); }
 
-int launch_pack_weights_tc_table(const PtrTable& W, int L, int D, int H, float* packed, cudaStream_t st) {
+int launch_pack_weights_tc_table(const PtrTable& W, int L, int D, int H, int corr_bf16, float* packed, cudaStream_t st) {
   const int Kp = round_up(L * D, kTcBK);
   const long long total = (long long)H * Kp;
-  pack_weights_tc_table_kernel<<<ceil_div(total, 256), 256, 0, st>>>(W, L, D, H, Kp, tc_corr_bf16(), packed);
+  pack_weights_tc_table_kernel<<<ceil_div(total, 256), 256, 0, st>>>(W, L, D, H, Kp, corr_bf16, packed);
   TFGNN_LAUNCH_CHECK();
   return 0;
 }
@@ -418,7 +431,7 @@ int launch_pack_weights_tc_table(const PtrTable& W, int L, int D, int H, float* 
 int launch_pack_weights_tc(const float* B, int ldb, int K, int N, float* packed, cudaStream_t st) {
   const int Kp = round_up(K, kTcBK);
   const long long total = (long long)N * Kp;
-  pack_weights_tc_kernel<<<ceil_div(total, 256), 256, 0, st>>>(B, ldb, K, N, Kp, tc_corr_bf16(), packed);
+  pack_weights_tc_kernel<<<ceil_div(total, 256), 256, 0, st>>>(B, ldb, K, N, Kp, gemm_corr_bf16(), packed);
   TFGNN_LAUNCH_CHECK();
   return 0;
 }
@@ -443,7 +456,7 @@ int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int 
   if (stages > 4) stages = 4;
   TFGNN_REQUIRE(stages >= 2, "tcgen05 GEMM: tile does not fit shared memory");
   p.num_stages = stages;
-  p.corr_bf16 = tc_corr_bf16();
+  p.corr_bf16 = gemm_corr_bf16();
   p.C = C; p.ldc = ldc; p.epi = epi;
 
   CUtensorMap map_a, map_b;
