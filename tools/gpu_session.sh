@@ -42,14 +42,14 @@ except Exception as e:
 PY
 fi
 if has wl; then
-  for wl in cfg4 cfg3 cfg5_shard; do
+  for wl in ${WLS:-cfg4 cfg3 cfg5_shard}; do
     timeout 400 python bench.py --workload $wl --skip-cpu-baseline --skip-e2e --no-clock-sampler --steps 10 > $OUT/bench_$wl.json 2> $OUT/bench_$wl.err
     echo "== $wl: $(grep -o '"ms_per_step": [0-9.]*' $OUT/bench_$wl.json | head -1) $(grep -o '"frac": [0-9.]*' $OUT/bench_$wl.json | head -1)"
     tail -2 $OUT/bench_$wl.err
   done
 fi
 if has ncu; then
-  for wl in cfg1 cfg4 cfg5_shard; do
+  for wl in ${NCU_WLS:-cfg1 cfg4 cfg5_shard}; do
     timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $OUT/launches_$wl.csv \
       python bench.py --workload $wl --steps 3 --warmup 3 --skip-e2e --skip-cpu-baseline --no-clock-sampler > $OUT/launches_$wl.log 2>&1
     echo "== launches $wl: $(wc -l < $OUT/launches_$wl.csv) lines"
