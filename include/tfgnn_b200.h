@@ -235,6 +235,25 @@ TFGNN_API int tfgnn_b200_dropout(const float* x, int64_t n, float rate, uint64_t
                                  void* stream);
 TFGNN_API int tfgnn_b200_axpby(const float* a, float alpha, const float* b, float beta, int64_t n, float* out, void* stream);
 
+/* ---- Differentiable generic path -----------------------------------------------------------
+ * The reference trains every variant by differentiating its literal op sequence (message_passing.py:95-218) with
+ * tf.GradientTape.  Variants without a fused backward kernel train through the same sequence here; these are the
+ * remaining forward / backward ops of that sequence (gather_rows <-> unsorted_segment_reduce(sum) are each other's
+ * backward, dense_bwd is above):
+ *   activation_bwd     grad_in = grad_out * act'(.); `ref` = forward OUTPUT (gelu: forward INPUT)
+ *   row_scale          out[m,:] = x[m,:] * f(s[m]); f = s | 1/(s+1e-7) | 1/max(s,1) | 1/sqrt(max(s,1))   (modes 0..3)
+ *   mul_add            out = a * b (+ c) on 2-D views with leading dimensions (FiLM: gamma * m + beta, gnn_film.py:105-107)
+ *   segment_max_bwd    gradient of unsorted_segment_max: to the elements that attain the maximum, shared among ties */
+TFGNN_API int tfgnn_b200_activation_bwd(const float* ref, const float* grad_out, int64_t n, int32_t activation,
+                                        float* grad_in, void* stream);
+TFGNN_API int tfgnn_b200_row_scale(const float* x, const float* s, int64_t M, int32_t H, int32_t mode, float* out,
+                                   void* stream);
+TFGNN_API int tfgnn_b200_mul_add(const float* a, int32_t lda, const float* b, int32_t ldb, const float* c, int32_t ldc,
+                                 int64_t M, int32_t H, float* out, int32_t ldo, void* stream);
+TFGNN_API int tfgnn_b200_segment_max_bwd(const float* data, const int32_t* segment_ids, int64_t ids_stride,
+                                         const float* segment_out, const float* segment_grad, int64_t M, int32_t H,
+                                         int64_t num_segments, float* grad_data, void* stream);
+
 /* ---- Graph-level readout and global exchange ---------------------------------------------
  * Segment primitives keyed by node_to_graph_map, which is non-decreasing (graph_dataset.py:211-217; the reference's own
  * tf.math.segment_sum requires it), so a graph is the contiguous row range graph_ptr[g] .. graph_ptr[g+1].

@@ -474,7 +474,7 @@ def test_non_differentiable_layers_raise_instead_of_truncating_gradients():
     rng = np.random.default_rng(0)
     V, D = 50, 16
     adjs = tuple(torch.from_numpy(rng.integers(0, V, size=(100, 2)).astype(np.int32)).cuda() for _ in range(2))
-    for kind in ("rgat", "gnn_film", "rgin"):
+    for kind in ("rgat",):    # the Edge-MLP family (incl. GNN-FiLM, RGIN) trains through layers/differentiable.py
         cls = get_message_passing_class(kind)
         p = cls.get_default_hyperparameters()
         p["hidden_dim"] = 12
@@ -484,6 +484,120 @@ def test_non_differentiable_layers_raise_instead_of_truncating_gradients():
             layer(MessagePassingInput(h, adjs))
         with torch.no_grad():
             layer(MessagePassingInput(h, adjs))
+
+
+def _torch_literal_reference(kind, p, w, h, adjs):
+    """float64 torch restatement of message_passing.py:95-218 + gnn_edge_mlp.py:84-107 / gnn_film.py:83-108 /
+    rgin.py:88-106 (differentiable)."""
+    t = lambda a: torch.from_numpy(np.asarray(a)).double().requires_grad_()
+    V, H = h.shape[0], p["hidden_dim"]
+    leaves = {"h": t(h), "edge": [[t(m) for m in mats] for mats in w["edge_mlps"]]}
+    if kind == "gnn_film":
+        leaves["film"] = [[t(m) for m in mats] for mats in w["film_mlps"]]
+    if kind == "rgin" and w.get("aggr_mlp") is not None:
+        leaves["aggr"] = [t(m) for m in w["aggr_mlp"]]
+    acts = {"relu": torch.relu, "tanh": torch.tanh, "leaky_relu": lambda x: torch.nn.functional.leaky_relu(x, 0.2),
+            "elu": torch.nn.functional.elu, "gelu": lambda x: torch.nn.functional.gelu(x, approximate="tanh")}
+    act = acts[p["message_activation_function"]]
+
+    def mlp(x, ws):
+        for W in ws[:-1]:
+            x = torch.relu(x @ W)
+        return x @ ws[-1]
+
+    msgs, ids = [], []
+    for l, a in enumerate(adjs):
+        src, tgt = torch.from_numpy(a[:, 0]).long(), torch.from_numpy(a[:, 1]).long()
+        hs, ht = leaves["h"][src], leaves["h"][tgt]
+        x = torch.cat([hs, ht], 1) if p["use_target_state_as_input"] else hs
+        m = mlp(x, leaves["edge"][l])
+        if p["normalize_by_num_incoming"]:
+            c = torch.bincount(tgt, minlength=V).double()
+            m = m / (c[tgt] + 1e-7)[:, None]
+        if kind == "gnn_film":
+            f = mlp(ht, leaves["film"][l])
+            m = f[:, :H] * m + f[:, H:]
+        msgs.append(m)
+        ids.append(tgt)
+    M, T = torch.cat(msgs, 0), torch.cat(ids, 0)
+    before = bool(p.get("message_activation_before_aggregation", False)) and kind != "rgin"
+    if before:
+        M = act(M)
+    agg_name = p["aggregation_function"]
+    if agg_name == "max":
+        out = torch.full((V, H), float(np.finfo(np.float32).min), dtype=torch.float64)
+        out = out.scatter_reduce(0, T[:, None].expand(-1, H), M, reduce="amax", include_self=True)
+    else:
+        out = torch.zeros((V, H), dtype=torch.float64).index_add(0, T, M)
+        cnt = torch.bincount(T, minlength=V).double().clamp(min=1)
+        if agg_name == "mean":
+            out = out / cnt[:, None]
+        elif agg_name == "sqrt_n":
+            out = out / cnt.sqrt()[:, None]
+    if "aggr" in leaves:
+        out = mlp(out, leaves["aggr"])
+    if not before:
+        out = act(out)
+    return out, leaves
+
+
+@pytest.mark.parametrize("kind,extra", [
+    ("gnn_edge_mlp", {}),                                                              # defaults: 1 hidden layer, target input
+    ("gnn_edge_mlp", dict(num_edge_MLP_hidden_layers=2, normalize_by_num_incoming=True, aggregation_function="mean",
+                          message_activation_function="gelu")),
+    ("rgcn", dict(aggregation_function="max")),
+    ("rgcn", dict(message_activation_before_aggregation=True, message_activation_function="tanh",
+                  aggregation_function="sqrt_n")),
+    ("rgin", dict(num_aggr_MLP_hidden_layers=1, normalize_by_num_incoming=True)),     # PPI_RGIN.json shape
+    ("rgin", {}),
+    ("gnn_film", {}),
+    ("gnn_film", dict(use_target_state_as_input=True, normalize_by_num_incoming=True)),  # PPI_GNN_FiLM.json shape
+])
+def test_training_through_the_differentiable_generic_path(kind, extra):
+    """Variants without a fused backward train through the reference's literal op order (layers/differentiable.py):
+    output and every gradient (node states, edge MLPs, FiLM MLPs, aggregation MLP) against float64 autograd."""
+    _need_gpu()
+    from tf2_gnn_b200.layers import MessagePassingInput, get_message_passing_class
+    rng = np.random.default_rng(4)
+    V, D, H, L = 300, 24, 32, 3
+    adjs = [rng.integers(0, V, size=(1500, 2)).astype(np.int32) for _ in range(L - 1)] + [np.zeros((0, 2), np.int32)]
+    cls = get_message_passing_class(kind)
+    p = cls.get_default_hyperparameters()
+    p["hidden_dim"] = H
+    p.update(extra)
+    w = mo.make_weights(kind, p, D, L, rng)
+    layer = cls(p)
+    layer.build(MessagePassingInput((None, D), tuple((None, 2) for _ in range(L))))
+    layer.set_weights_from_oracle_dict(w)
+    for v in layer.variables:
+        v.requires_grad_(True)
+    h = rng.uniform(-1, 1, (V, D)).astype(np.float32)
+    R = rng.uniform(-1, 1, (V, H)).astype(np.float32)
+    ht = torch.from_numpy(h).cuda().requires_grad_()
+    out = layer(MessagePassingInput(ht, tuple(torch.from_numpy(a).cuda() for a in adjs)))
+    ref, leaves = _torch_literal_reference(kind, p, w, h, adjs)
+    sentinel = ref.detach() < -1e38              # empty segments of the max aggregation (no gradient flows there)
+    Rt = torch.from_numpy(R).double()
+    (torch.where(sentinel, torch.zeros_like(ref), ref) * Rt).sum().backward()
+    o = out.detach().cpu().double()
+    assert torch.equal(o < -1e38, sentinel)
+    (torch.where(sentinel.cuda(), torch.zeros_like(out), out) * torch.from_numpy(R).cuda()).sum().backward()
+    close(torch.where(sentinel, torch.zeros_like(o), o).numpy(), torch.where(sentinel, torch.zeros_like(ref), ref).detach().numpy(),
+          what=f"{kind} forward")
+    tol = 3e-5   # gradients pass through 3-5 chained contractions / reductions, each at 1e-5 of its own scale
+    close(ht.grad.cpu().numpy(), leaves["h"].grad.numpy(), tol=tol, what=f"{kind} grad_h")
+    for l, mlp in enumerate(layer._edge_type_mlps):
+        for j, var in enumerate(mlp.layers):
+            close(var.grad.cpu().numpy(), leaves["edge"][l][j].grad.numpy() if leaves["edge"][l][j].grad is not None
+                  else np.zeros_like(w["edge_mlps"][l][j]), tol=tol, what=f"{kind} grad edge MLP {l}/{j}")
+    if kind == "gnn_film":
+        for l, mlp in enumerate(layer._edge_type_film_layer_computations):
+            g = leaves["film"][l][0].grad
+            close(mlp.layers[0].grad.cpu().numpy(), g.numpy() if g is not None else np.zeros_like(w["film_mlps"][l][0]),
+                  tol=tol, what=f"{kind} grad FiLM {l}")
+    if "aggr" in leaves:
+        for j, var in enumerate(layer._aggregation_mlp):
+            close(var.grad.cpu().numpy(), leaves["aggr"][j].grad.numpy(), tol=tol, what=f"{kind} grad aggregation MLP {j}")
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -422,8 +422,12 @@ def test_rgin_parity(n_aggr):
 
 @pytest.mark.parametrize("use_target,act_before,agg", [(False, False, "sum"), (True, False, "sum"),
                                                         (False, True, "sum"), (True, True, "max")])
-def test_film_parity(use_target, act_before, agg):
+@pytest.mark.parametrize("att", ["0", "1"])
+def test_film_parity(monkeypatch, att, use_target, act_before, agg):
+    """att = 1: aggregate-then-transform with the FiLM modulation chained through the GEMM epilogue (the form target-range
+    shards use); att = 0: projected tables + per-edge modulation.  (max / activation-before always take the latter.)"""
     _need_gpu()
+    monkeypatch.setenv("TFGNN_B200_FILM_ATT", att)
     rng = np.random.default_rng(8)
     V, D, H, L = 500, 64, 64, 4
     adjs = random_graph(rng, V, L, 3000, hub=True)
@@ -541,7 +545,10 @@ def test_target_range_shards_match_full(kind, extra):
                 assert_states_close(first, parts[-1].astype(np.float64), tol=2e-6)
             else:
                 assert np.array_equal(first, parts[-1])  # unfiltered and pre-filtered edge lists agree
-        assert_states_close(np.concatenate(parts, axis=0), full.astype(np.float64), tol=2e-6)
+        got = np.concatenate(parts, axis=0)
+        assert_states_close(got, mo.message_passing_forward(kind, p, w, h, adjs, dtype=np.float64))
+        if kind != "gnn_film":   # FiLM shards use the aggregate-then-transform form, the full batch the projected tables
+            assert_states_close(got, full.astype(np.float64), tol=2e-6)
 
 
 def _torch_reference_layer(h, adjs, Ws, normalize, agg, act, use_target=False):

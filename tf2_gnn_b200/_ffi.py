@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = (
     "tfgnn_b200_graph_offsets", "tfgnn_b200_segment_softmax", "tfgnn_b200_weighted_segment_sum",
     "tfgnn_b200_gathered_add", "tfgnn_b200_gru_gate_fwd", "tfgnn_b200_clamp", "tfgnn_b200_dense_bias_fwd",
     "tfgnn_b200_dense_bwd", "tfgnn_b200_layer_norm_bwd", "tfgnn_b200_dropout", "tfgnn_b200_axpby",
+    "tfgnn_b200_activation_bwd", "tfgnn_b200_row_scale", "tfgnn_b200_mul_add", "tfgnn_b200_segment_max_bwd",
 )
 
 _PP = POINTER(c_void_p)
@@ -116,6 +117,12 @@ def lib() -> ctypes.CDLL:
                                             c_void_p, c_void_p]
     L.tfgnn_b200_dropout.argtypes = [c_void_p, c_int64, c_float, ctypes.c_uint64, ctypes.c_uint64, c_void_p, c_void_p]
     L.tfgnn_b200_axpby.argtypes = [c_void_p, c_float, c_void_p, c_float, c_int64, c_void_p, c_void_p]
+    L.tfgnn_b200_activation_bwd.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]
+    L.tfgnn_b200_row_scale.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]
+    L.tfgnn_b200_mul_add.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_int32, c_int64, c_int32, c_void_p,
+                                     c_int32, c_void_p]
+    L.tfgnn_b200_segment_max_bwd.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_int64,
+                                             c_void_p, c_void_p]
     L.tfgnn_b200_set_l2_persist_mb.argtypes = [c_int32]
     L.tfgnn_b200_release_device_state.argtypes = []
     for name in EXPORTED_SYMBOLS:

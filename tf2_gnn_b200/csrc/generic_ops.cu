@@ -185,3 +185,147 @@ extern "C" int tfgnn_b200_layer_norm(const float* x, const float* gamma, const f
   TFGNN_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- primitives of the differentiable generic path (layers/differentiable.py) -----------------
+// The reference differentiates EVERY message-passing variant with tf.GradientTape through its literal op sequence
+// (message_passing.py:95-218).  Variants without a fused backward (hidden-layer edge MLPs, RGIN, GNN-FiLM, max aggregation,
+// activation before aggregation) train through the same op sequence here: each op below is the forward or the backward of
+// one TensorFlow op of that sequence.
+namespace tfgnn {
+
+__device__ __forceinline__ float act_grad_out(float y, int act) {   // derivative from the OUTPUT y = act(x)
+  switch (act) {
+    case TFGNN_ACT_RELU: return y > 0.f ? 1.f : 0.f;
+    case TFGNN_ACT_TANH: return 1.f - y * y;
+    case TFGNN_ACT_LEAKY_RELU: return y > 0.f ? 1.f : kLeakyReluAlpha;
+    case TFGNN_ACT_ELU: return y > 0.f ? 1.f : y + 1.f;
+    case TFGNN_ACT_SELU: return y > 0.f ? kSeluScale : y + kSeluScale * kSeluAlpha;
+    case TFGNN_ACT_SIGMOID: return y * (1.f - y);
+    default: return 1.f;
+  }
+}
+__device__ __forceinline__ float gelu_grad_in(float x) {            // gelu: derivative from the INPUT
+  const float c = 0.7978845608028654f;
+  const float t = tanhf(c * (x + 0.044715f * x * x * x));
+  return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * c * (1.0f + 3.0f * 0.044715f * x * x);
+}
+
+// grad_in = grad_out * act'(.): `ref` is the forward OUTPUT for every activation but gelu, whose `ref` is the forward INPUT
+__global__ void activation_bwd_kernel(const float* __restrict__ ref, const float* __restrict__ g, long long n, int act,
+                                      float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = g[i] * (act == TFGNN_ACT_GELU ? gelu_grad_in(ref[i]) : act_grad_out(ref[i], act));
+}
+
+// out[m, :] = x[m, :] * f(s[m]),  f = s (mode 0), 1/(s + 1e-7) (mode 1: gnn_edge_mlp.py:102-106), 1/max(s,1) (mode 2:
+// segment mean), 1/sqrt(max(s,1)) (mode 3: segment sqrt_n)
+__global__ void row_scale_kernel(const float* __restrict__ x, const float* __restrict__ s, long long M, int H, int mode,
+                                 float* __restrict__ out) {
+  const long long total = M * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float v = s[i / H];
+    const float f = mode == 0 ? v : mode == 1 ? 1.0f / (v + kSmallNumber) : mode == 2 ? 1.0f / fmaxf(v, 1.0f)
+                                                                                      : 1.0f / sqrtf(fmaxf(v, 1.0f));
+    out[i] = x[i] * f;
+  }
+}
+
+// out = a * b + c (c NULL: a * b) over strided 2-D views: element (m, j) of each operand at ptr[m * ld + j]
+__global__ void mul_add_kernel(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb,
+                               const float* __restrict__ c, int ldc, long long M, int H, float* __restrict__ out, int ldo) {
+  const long long total = M * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / H;
+    const int j = (int)(i - m * H);
+    const float v = a[m * lda + j] * b[m * ldb + j];
+    out[m * ldo + j] = c ? v + c[m * ldc + j] : v;
+  }
+}
+
+// backward of unsorted_segment_max: the gradient of a segment's maximum goes to the messages that attain it
+// (ties share the whole gradient each, as tf.math.unsorted_segment_max's gradient does through its equality mask / count:
+//  the count normalisation is applied too)
+__global__ void segment_max_bwd_kernel(const float* __restrict__ data, const int* __restrict__ ids, long long ids_stride,
+                                       const float* __restrict__ seg_out, const float* __restrict__ seg_grad,
+                                       const float* __restrict__ tie_count, long long M, int H,
+                                       long long num_segments, float* __restrict__ out) {
+  const long long total = M * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / H;
+    const int c = (int)(i - m * H);
+    const int seg = ids[m * ids_stride];
+    float g = 0.f;
+    if ((unsigned)seg < (unsigned long long)num_segments && data[i] == seg_out[(long long)seg * H + c])
+      g = seg_grad[(long long)seg * H + c] / fmaxf(tie_count[(long long)seg * H + c], 1.0f);
+    out[i] = g;
+  }
+}
+__global__ void segment_max_ties_kernel(const float* __restrict__ data, const int* __restrict__ ids, long long ids_stride,
+                                        const float* __restrict__ seg_out, long long M, int H, long long num_segments,
+                                        float* __restrict__ tie_count) {
+  const long long total = M * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / H;
+    const int c = (int)(i - m * H);
+    const int seg = ids[m * ids_stride];
+    if ((unsigned)seg < (unsigned long long)num_segments && data[i] == seg_out[(long long)seg * H + c])
+      atomicAdd(tie_count + (long long)seg * H + c, 1.0f);
+  }
+}
+
+}  // namespace tfgnn
+
+extern "C" int tfgnn_b200_activation_bwd(const float* ref, const float* grad_out, int64_t n, int32_t activation,
+                                         float* grad_in, void* stream) {
+  TFGNN_REQUIRE(n >= 0 && activation >= TFGNN_ACT_NONE && activation <= TFGNN_ACT_SIGMOID, "bad activation_bwd arguments");
+  if (n == 0) return 0;
+  TFGNN_REQUIRE(ref && grad_out && grad_in, "NULL pointer");
+  activation_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(ref, grad_out, n, activation, grad_in);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tfgnn_b200_row_scale(const float* x, const float* s, int64_t M, int32_t H, int32_t mode, float* out,
+                                    void* stream) {
+  TFGNN_REQUIRE(M >= 0 && H > 0 && mode >= 0 && mode <= 3, "bad row_scale arguments");
+  if (M == 0) return 0;
+  TFGNN_REQUIRE(x && s && out, "NULL pointer");
+  row_scale_kernel<<<grid_for(M * H), 256, 0, (cudaStream_t)stream>>>(x, s, M, H, mode, out);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tfgnn_b200_mul_add(const float* a, int32_t lda, const float* b, int32_t ldb, const float* c, int32_t ldc,
+                                  int64_t M, int32_t H, float* out, int32_t ldo, void* stream) {
+  TFGNN_REQUIRE(M >= 0 && H > 0, "bad mul_add arguments");
+  if (M == 0) return 0;
+  TFGNN_REQUIRE(a && b && out, "NULL pointer");
+  mul_add_kernel<<<grid_for(M * H), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, c, ldc, M, H, out, ldo);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tfgnn_b200_segment_max_bwd(const float* data, const int32_t* segment_ids, int64_t ids_stride,
+                                          const float* segment_out, const float* segment_grad, int64_t M, int32_t H,
+                                          int64_t num_segments, float* grad_data, void* stream) {
+  TFGNN_REQUIRE(M >= 0 && H > 0 && num_segments >= 0 && ids_stride >= 1, "bad segment_max_bwd arguments");
+  if (M == 0) return 0;
+  TFGNN_REQUIRE(data && segment_ids && segment_out && segment_grad && grad_data, "NULL pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  void* ties = nullptr;
+  int rc = pool_alloc(&ties, (size_t)num_segments * H * sizeof(float), st);
+  if (rc) return rc;
+  TFGNN_CUDA(cudaMemsetAsync(ties, 0, (size_t)num_segments * H * sizeof(float), st));
+  segment_max_ties_kernel<<<grid_for(M * H), 256, 0, st>>>(data, segment_ids, ids_stride, segment_out, M, H, num_segments,
+                                                          (float*)ties);
+  TFGNN_LAUNCH_CHECK();
+  segment_max_bwd_kernel<<<grid_for(M * H), 256, 0, st>>>(data, segment_ids, ids_stride, segment_out, segment_grad,
+                                                         (const float*)ties, M, H, num_segments, grad_data);
+  TFGNN_LAUNCH_CHECK();
+  pool_free(ties, st);
+  return 0;
+}

@@ -139,7 +139,13 @@ extern "C" int tfgnn_b200_film_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   GemmEpilogue none;
   int rc = batch_enter(b, st);
   if (rc) return rc;
-  static const bool film_att = [] { const char* e = getenv("TFGNN_B200_FILM_ATT"); return !e || atoi(e) != 0; }();
+  // TFGNN_B200_FILM_ATT: 1 = always, 0 = never, unset = on target-range shards (where the projected-table form would
+  // project all num_nodes_total sources on every rank) and when the projected tables would not fit comfortably
+  const char* film_att_str = getenv("TFGNN_B200_FILM_ATT");   // read per call: the tests sweep it
+  const int film_att_env = film_att_str ? atoi(film_att_str) : -1;
+  const bool sharded_batch = b->tgt_off != 0 || b->V_src != b->V;
+  const size_t projected_bytes = ((size_t)b->V_src * L * H + (size_t)V * 2 * L * H) * sizeof(float);
+  const bool film_att = film_att_env >= 0 ? film_att_env != 0 : (sharded_batch || projected_bytes > ((size_t)48 << 30));
   if (film_att && num_hidden_layers == 0 && aggregation != TFGNN_AGG_MAX && !act_before && D % 4 == 0 && H % 4 == 0 &&
       (reinterpret_cast<uintptr_t>(h) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
     // ---- aggregate-then-transform (round 2) ------------------------------------------------------------------
@@ -152,12 +158,10 @@ extern "C" int tfgnn_b200_film_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
     // the OWNED rows are ever multiplied (the transform-then-aggregate form projects all num_nodes_total sources on
     // every rank: 123 GB per rank at BASELINE config 5).
     const int K = L * D;
-    void *A = nullptr, *T = nullptr, *G = nullptr, *Fb = nullptr;
+    void *A = nullptr, *T = nullptr, *Fb = nullptr;
     rc = batch_scratch(b, 2, (size_t)V * K * sizeof(float), &A);
     if (rc) return rc;
     rc = batch_scratch(b, 4, (size_t)V * K * sizeof(float), &T);
-    if (rc) return rc;
-    rc = batch_scratch(b, 11, (size_t)V * H * sizeof(float), &G);
     if (rc) return rc;
     rc = batch_scratch(b, 3, (size_t)K * H * sizeof(float), &Fb);
     if (rc) return rc;
@@ -185,12 +189,22 @@ extern "C" int tfgnn_b200_film_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
       rc = launch_target_term(h_tgt, D, b->row_ptr, V, L, D, 1, (float*)T, K, 0, st);
       if (rc) return rc;
     }
+    // gamma for all types in ONE wide contraction: Gall [V, L*H] = h_v [Fgamma_0 | .. | Fgamma_{L-1}] (128-column tiles:
+    // the k-block rate of the GEMM pipeline is latency-bound, so work per k-block ~ tile width; 6 GEMMs of N = 320 ran in
+    // 80-column tiles at 4.7 ms each, the wide one takes about half of their sum)
+    const int LHw = L * H;
+    void *Gall = nullptr, *Fg = nullptr;
+    rc = batch_scratch(b, 11, (size_t)V * LHw * sizeof(float), &Gall);
+    if (rc) return rc;
+    rc = batch_scratch(b, 12, (size_t)D * LHw * sizeof(float), &Fg);
+    if (rc) return rc;
+    rc = launch_pack_horizontal(film, L, 0, D, H, 2 * H, (float*)Fg, LHw, st);   // first H columns of every F_l [D, 2H]
+    if (rc) return rc;
+    rc = node_gemm(h_tgt, D, (const float*)Fg, LHw, (float*)Gall, LHw, V, LHw, D, none, path, b, 6, st);
+    if (rc) return rc;
     for (int l = 0; l < L; ++l) {
-      // gamma_l = h_v Fgamma_l  (first H columns of F_l [D, 2H])
-      rc = node_gemm(h_tgt, D, reinterpret_cast<const float*>(film.p[l]), 2 * H, (float*)G, H, V, H, D, none, path, b, 6, st);
-      if (rc) return rc;
       GemmEpilogue chain;
-      chain.mul = (const float*)G; chain.ldm = H;
+      chain.mul = (const float*)Gall + (size_t)l * H; chain.ldm = LHw;
       chain.accumulate = 1;
       chain.finalize = 0;
       const bool last_src = !use_target && l == L - 1;

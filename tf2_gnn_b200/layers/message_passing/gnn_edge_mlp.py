@@ -117,6 +117,14 @@ class GNN_Edge_MLP(MessagePassing):
         self._check_types(prepared)
         ptrs, tensors = self._mlp_weight_ptrs()
         if torch.is_grad_enabled() and (h.requires_grad or any(t.requires_grad for t in tensors)):
+            fused_backward = (int(self._num_edge_MLP_hidden_layers) == 0 and self._aggregation_fn.name != "max"
+                              and not self._message_activation_before_aggregation and int(h.shape[1]) % 4 == 0
+                              and self._hidden_dim % 4 == 0)
+            if not fused_backward:
+                # hidden layers / max aggregation / activation before aggregation: the reference's literal op order with
+                # per-op backward kernels (layers/differentiable.py)
+                from ..differentiable import edge_mlp_family_forward
+                return edge_mlp_family_forward(self, h, prepared)
             cfg = dict(H=self._hidden_dim, n_hidden=int(self._num_edge_MLP_hidden_layers), flags=self._flags(),
                        agg=self._aggregation_fn.code, act=self._activation_fn.code, path=_ffi.PATH[self._path])
             return _EdgeMLPLayerFunction.apply(h, prepared, cfg, *tensors)

@@ -8,7 +8,8 @@ import torch
 from ... import _ffi
 from ...runtime import PreparedBatch, stream_ptr
 from .gnn_edge_mlp import EdgeMLP, GNN_Edge_MLP
-from ..node_ops import require_no_grad
+from ..differentiable import edge_mlp_family_forward
+from ..node_ops import _needs_grad
 from .message_passing import MessagePassingInput, _last_dim, register_message_passing_implementation
 
 
@@ -45,8 +46,12 @@ class GNN_FiLM(GNN_Edge_MLP):
     def call(self, inputs: MessagePassingInput, training: bool = False,
              prepared: Optional[PreparedBatch] = None):
         h, prepared = self._device_inputs(inputs, prepared)
-        require_no_grad(type(self).__name__, h, *[v.value for v in self.variables])
         self._check_types(prepared)
+        if _needs_grad(h, *[v.value for v in self.variables]):
+            # training: the reference's literal op order with per-op backward kernels (layers/differentiable.py)
+            return edge_mlp_family_forward(
+                self, h, prepared,
+                film_kernels=[[v.value for v in m.layers] for m in self._edge_type_film_layer_computations])
         if any(m.num_hidden_layers for m in self._edge_type_film_layer_computations):
             raise NotImplementedError("film_parameter_MLP_hidden_layers != [] is not built yet")
         out = torch.empty((prepared.num_nodes, self._hidden_dim), dtype=torch.float32, device=h.device)

@@ -8,7 +8,8 @@ import torch
 from ... import _ffi
 from ...runtime import PreparedBatch, stream_ptr
 from .gnn_edge_mlp import GNN_Edge_MLP
-from ..node_ops import require_no_grad
+from ..differentiable import edge_mlp_family_forward
+from ..node_ops import _needs_grad
 from .message_passing import MessagePassingInput, Variable, register_message_passing_implementation
 
 
@@ -45,8 +46,12 @@ class RGIN(GNN_Edge_MLP):
     def call(self, inputs: MessagePassingInput, training: bool = False,
              prepared: Optional[PreparedBatch] = None):
         h, prepared = self._device_inputs(inputs, prepared)
-        require_no_grad(type(self).__name__, h, *[v.value for v in self.variables])
         self._check_types(prepared)
+        if _needs_grad(h, *[v.value for v in self.variables]):
+            # training: the reference's literal op order with per-op backward kernels (layers/differentiable.py)
+            return edge_mlp_family_forward(
+                self, h, prepared, activation_before=False,
+                aggr_kernels=[v.value for v in self._aggregation_mlp] if self._aggregation_mlp is not None else None)
         out = torch.empty((prepared.num_nodes, self._hidden_dim), dtype=torch.float32, device=h.device)
         ptrs, _keep = self._mlp_weight_ptrs()
         aggr = [v.value for v in (self._aggregation_mlp or [])]
