@@ -60,4 +60,12 @@ if has full; then
     python bench.py --steps 3 --warmup 3 --skip-e2e --skip-cpu-baseline --skip-secondary --no-clock-sampler > $OUT/ncu_full.log 2>&1
   ls -la $OUT/*.ncu-rep
 fi
+if has gemmprof; then
+  timeout 300 python tools/bench_gemm.py --paths sorted_tc > $OUT/gemm_micro.txt 2>&1; cat $OUT/gemm_micro.txt
+  for shp in 2000000,320,320 500000,128,384; do
+    timeout 400 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 2 -c 1 -o $OUT/prof_gemm_${shp//,/_} -f \
+      python tools/bench_gemm.py --shapes $shp --paths sorted_tc > $OUT/ncu_gemm_${shp//,/_}.log 2>&1
+  done
+  ls -la $OUT/*.ncu-rep
+fi
 echo "session $TAG done"
