@@ -53,3 +53,32 @@ def test_algorithmic_bytes_formula_matches_survey_8d():
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(line["roofline"])
     assert {"value", "unit", "cores", "kind", "sample"} <= set(line["cpu_baseline"])
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(line["e2e"])
+
+
+def test_traffic_is_labelled_static_with_its_source():
+    """roofline.traffic is never measured inside the timed run (ncu replays kernels): it is a static figure with the ncu
+    capture it came from, or None with the reason."""
+    sys.path.insert(0, ROOT)
+    import bench
+    val, src = bench.load_traffic("cfg2", "auto")
+    assert (val is None) or (isinstance(val, int) and val > 1e9)
+    assert isinstance(src, str) and ("static" in src or "no ncu" in src)
+    val2, src2 = bench.load_traffic("no_such_workload", "auto")
+    assert val2 is None and "no ncu" in src2
+
+
+def test_bench_names_a_kernel_per_workload_kind():
+    sys.path.insert(0, ROOT)
+    import bench
+    kinds = {w["kind"] for w in bench.WORKLOADS.values()}
+    assert kinds <= set(bench.KERNEL_OF)
+    assert bench.WORKLOADS["cfg5"]["V"] == 16_000_000 and sum(bench.WORKLOADS["cfg5"]["E"]) > 255_000_000
+
+
+def test_dropout_stream_offsets_are_disjoint():
+    from tf2_gnn_b200.layers.node_ops import DropoutState
+    st = DropoutState(seed=3)
+    a = st.take(10)        # 3 Philox counters (4 values each)
+    b = st.take(1)
+    c = st.take(8)
+    assert (a, b, c) == (0, 3, 4) and st.offset == 6

@@ -186,9 +186,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             w.z = ptx::pack_bf16x2(x.z - h.z, x.z); w.w = ptx::pack_bf16x2(x.w - h.w, x.w);
             reinterpret_cast<uint4*>(lo)[idx] = w;
           } else {
+            // the raw fp32 tile stays in place as the hi operand here too (kind::tf32 ignores the low 13 mantissa bits,
+            // bitwise identical results: tools/exp_rawhi.py) - the shared-memory LSU pipe is the busiest unit of this
+            // kernel (ncu r2c: 67 % at [2M,320]x[320,320]) and this drops a third of the splitter's wavefronts
             l.x = ptx::tf32_hi(x.x - h.x); l.y = ptx::tf32_hi(x.y - h.y);
             l.z = ptx::tf32_hi(x.z - h.z); l.w = ptx::tf32_hi(x.w - h.w);
-            a[idx] = h;
             lo[idx] = l;
           }
         }

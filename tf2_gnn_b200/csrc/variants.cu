@@ -294,10 +294,21 @@ __global__ void rgat_scores_kernel(const float* __restrict__ P, long long V, int
   const float* a = reinterpret_cast<const float*>(att.p[l]) + (long long)k * 2 * d;
   const float* p = P + v * (long long)(L * K * d) + (long long)l * K * d + (long long)k * d;
   float ss = 0.f, st = 0.f;
-  for (int i = 0; i < d; ++i) {
-    const float x = p[i];
-    ss = fmaf(a[i], x, ss);
-    st = fmaf(a[d + i], x, st);
+  if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    // 16-byte loads: consecutive threads own consecutive (v,l,k) segments of d floats, so a warp walks one contiguous
+    // 32*d-float span and every fetched line is used completely through L1 (the scalar loop ran at 0.6 TB/s: ncu r2c)
+    for (int i = 0; i < d; i += 4) {
+      const float4 x = ldg_f4(p + i);
+      ss = fmaf(a[i], x.x, ss); ss = fmaf(a[i + 1], x.y, ss); ss = fmaf(a[i + 2], x.z, ss); ss = fmaf(a[i + 3], x.w, ss);
+      st = fmaf(a[d + i], x.x, st); st = fmaf(a[d + i + 1], x.y, st);
+      st = fmaf(a[d + i + 2], x.z, st); st = fmaf(a[d + i + 3], x.w, st);
+    }
+  } else {
+    for (int i = 0; i < d; ++i) {
+      const float x = p[i];
+      ss = fmaf(a[i], x, ss);
+      st = fmaf(a[d + i], x, st);
+    }
   }
   s_src[idx] = ss;
   s_tgt[idx] = st;
