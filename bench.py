@@ -74,6 +74,29 @@ def algorithmic_bytes(kind, V, E_list, D, H, params):
     return b
 
 
+def dense_flops(kind, V, E_list, D, H, params):
+    """fp32-equivalent FLOPs of the node-level contractions of one layer in the formulation the kernels use:
+    RGCN/GGNN messages 2*V*L*D*H, + GGNN GRU 2*V*(D+H)*3H, RGAT projection 2*V*L*D*H, GNN-FiLM messages + gamma + beta =
+    3 * 2*V*L*D*H.  Each product costs three tf32 MMAs (3xTF32) on the tensor cores."""
+    L = len(E_list)
+    base = 2.0 * V * L * D * H
+    if kind == "ggnn":
+        return base + 2.0 * V * (D + H) * 3 * H
+    if kind == "gnn_film":
+        return 3.0 * base
+    return base
+
+
+def load_tensor_peak():
+    """Measured dense tf32 peak = half the measured bf16 cuBLAS peak of MEASURED_PEAKS.json (TFLOP/s), else nominal 1100/... fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["bf16_tflops"]) / 2.0, "measured bf16_tflops / 2 (MEASURED_PEAKS.json)"
+    return 1590.0 / 2.0, "fallback bf16 1.59 PFLOP/s / 2 (B200_PROFILING.md)"
+
+
 def make_inputs(wl, seed):
     rng = np.random.default_rng(seed)
     V, H = wl["V"], wl["H"]
@@ -496,6 +519,16 @@ def measure_workload(name, args, rank, world, local, dev, headline):
                        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                        "algorithmic_bytes_per_step": alg, "frac_of_nominal_8TBs": achieved / 8000.0,
                        "kernel": KERNEL_OF.get(kind, kind)}
+    # the other roof: node-level contractions at fp32 accuracy on the tensor cores (3 tf32 MMAs per product)
+    flops = dense_flops(kind, V, wl["E"], H, H, params)
+    tf32_peak, tf32_src = load_tensor_peak()
+    t_hbm_ms = alg / (peak * 1e9) * 1e3
+    t_dense_ms = 3.0 * flops / (tf32_peak * 1e12) * 1e3
+    res["roofline"]["dense"] = {"fp32_equiv_flops_per_step": flops, "tf32_mma_flops_per_step": 3.0 * flops,
+                                "tf32_peak_tflops": tf32_peak, "tf32_peak_source": tf32_src,
+                                "t_hbm_ms": t_hbm_ms, "t_dense_ms": t_dense_ms,
+                                "binding": "tensor" if t_dense_ms > t_hbm_ms else "hbm",
+                                "frac_of_binding_bound": max(t_hbm_ms, t_dense_ms) / ms_per_step}
     if not args.skip_e2e:
         out_host = torch.empty((V, H), dtype=torch.float32).pin_memory()
         e2e_steps = max(4, min(args.steps, 10))
@@ -601,6 +634,51 @@ def measure_sharded(args, rank, world, local, dev):
                               "bitwise_equal": bool(torch.equal(ref[lo:hi], mine)), "max_abs_diff": diff,
                               "max_abs_ref": ref.abs().max().item()}
               del full, ref
+          # ---- the all-gather fused into the layer kernel (peer stores over NVLink from the epilogue) ----
+          if wl["kind"] == "rgcn":
+              try:
+                  from tf2_gnn_b200.sharding import PeerNodeTables
+                  tables = PeerNodeTables(V, H)
+                  n_layers = 4
+                  tables.table(0)[lo:hi].copy_(h_local)
+                  dist.all_gather_into_tensor(tables.table(0), h_local)      # the initial node states, once
+
+                  def chain():
+                      for k in range(n_layers):
+                          layer.call_allgather(tables.table(k), shard, tables.replica_ptrs(k + 1), rank)
+                          tables.barrier(k + 1)
+
+                  for _ in range(3):
+                      chain()
+                  torch.cuda.synchronize()
+                  barrier(world)
+                  ev[0].record()
+                  for _ in range(n_it):
+                      chain()
+                  ev[1].record()
+                  torch.cuda.synchronize()
+                  fused_ms = max_over_ranks(ev[0].elapsed_time(ev[1]) / (n_it * n_layers), world)
+                  fz = {"ms_per_layer": fused_ms, "edges_per_s": m_total / (fused_ms * 1e-3), "layers_chained": n_layers,
+                        "nvlink_bytes_stored_per_rank_per_layer": ag_bytes,
+                        "nvlink_GBps_per_rank": ag_bytes / (fused_ms * 1e-3) / 1e9,
+                        "what": "tfgnn_b200_rgcn_fwd_allgather: the fused kernel's epilogue stores each output tile into every "
+                                "rank's node-state table (P2P stores over NVLink, symmetric memory); no collective call, one "
+                                "signal exchange per layer"}
+                  # the chained result against the same chain built from layer + NCCL all-gather (bitwise)
+                  h_a = h_local
+                  full_t = torch.empty((V, H), dtype=torch.float32, device=dev)
+                  for k in range(n_layers):
+                      dist.all_gather_into_tensor(full_t, h_a)
+                      h_a = layer(MessagePassingInput(full_t, adj_dev), prepared=shard)
+                  dist.all_gather_into_tensor(full_t, h_a)
+                  final = tables.table(n_layers)
+                  torch.cuda.synchronize()
+                  fz["bitwise_equal_to_nccl_chain"] = bool(torch.equal(final, full_t))
+                  fz["max_abs_diff_to_nccl_chain"] = (final - full_t).abs().max().item()
+                  rec["fused_allgather"] = fz
+                  del tables, full_t
+              except Exception as e:
+                  rec["fused_allgather"] = {"error": f"{type(e).__name__}: {e}"[:300]}
           results[key] = rec
           del shard, h_full, adj_dev, h_local, out_local
           torch.cuda.empty_cache()

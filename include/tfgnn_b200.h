@@ -39,6 +39,7 @@ extern "C" {
 #define TFGNN_API
 #endif
 #define TFGNN_MAX_EDGE_TYPES 32
+#define TFGNN_MAX_PEERS 15 /* peer replicas of tfgnn_b200_rgcn_fwd_allgather (one NVSwitch domain: <= 16 GPUs) */
 
 typedef struct tfgnn_batch tfgnn_batch_t;
 
@@ -133,6 +134,21 @@ TFGNN_API int tfgnn_b200_edge_mlp_fwd(tfgnn_batch_t* batch, const float* h, int3
 TFGNN_API int tfgnn_b200_rgcn_fwd(tfgnn_batch_t* batch, const float* h, int32_t D, const float* const* W,
                         int32_t H, uint32_t flags, int32_t aggregation, int32_t activation,
                         int32_t path, float* out, void* stream);
+
+/* Layer + all-gather in ONE kernel over peer memory (SURVEY.md §8e case 2: one graph partitioned by target range over the
+ * GPUs of an NVSwitch domain, tfgnn_b200_prepare_sharded).  Same computation as tfgnn_b200_rgcn_fwd on the shard, but the
+ * epilogue of the fused kernel stores every finished 128-row output tile into the caller's own table AND into the peers'
+ * copies of it: out_replicas[r] is rank r's [num_nodes_total, H] node-state table as mapped into THIS process (CUDA P2P over
+ * NVLink: a symmetric-memory allocator, cudaIpcOpenMemHandle, NVSHMEM ...; out_replicas[own_rank] is local memory), rows
+ * target_begin + v.  When every rank has run the call, each replica holds the all-gathered new node states: the per-layer
+ * all-gather of the reference-sized alternative (ncclAllGather after the layer) overlaps the layer tile by tile instead of
+ * following it.  The caller double-buffers the tables across layers (layer k reads table k%2, writes table (k+1)%2) and
+ * synchronises the ranks between layers (a few-microsecond signal exchange).
+ * TFGNN_ERR_UNSUPPORTED when the shard does not take the fused kernel (D % 32, H % 16, H <= 512, linear messages,
+ * sum/mean/sqrt_n, activation after aggregation): fall back to the layer call + an all-gather. */
+TFGNN_API int tfgnn_b200_rgcn_fwd_allgather(tfgnn_batch_t* batch, const float* h, int32_t D, const float* const* W, int32_t H,
+                                            uint32_t flags, int32_t aggregation, int32_t activation,
+                                            float* const* out_replicas, int32_t num_replicas, int32_t own_rank, void* stream);
 
 /* Backward of tfgnn_b200_rgcn_fwd (the reference differentiates with tf.GradientTape,
  * models/graph_task_model.py:338-365).  batch_t is the SAME adjacency prepared with TFGNN_PREPARE_TRANSPOSE.

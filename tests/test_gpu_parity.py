@@ -778,3 +778,39 @@ def test_launch_counter_moves():
     p["hidden_dim"] = 32
     run_case("rgcn", p, 100, 32, 2, random_graph(rng, 100, 2, 500))
     assert _ffi.launch_count() > before
+
+
+@pytest.mark.parametrize("V,D,H,L,E,split", [(9000, 64, 64, 3, 40000, "1"), (30000, 128, 256, 4, 150000, "0"),
+                                             (3000, 320, 320, 3, 20000, "1")])
+def test_rgcn_fwd_allgather_replica_stores(monkeypatch, V, D, H, L, E, split):
+    """tfgnn_b200_rgcn_fwd_allgather on ONE GPU: the replicas are three local tables, the batch is a target-range shard.
+    Every replica must receive exactly the rows the plain sharded layer call produces, at rows [lo, hi), and nothing else
+    (multi-GPU: the same stores go to NVLink-mapped peer tables; tools / bench.py --gpus N exercise that)."""
+    _need_gpu()
+    from tf2_gnn_b200.layers import MessagePassingInput
+    from tf2_gnn_b200.runtime import PreparedBatch
+    monkeypatch.setenv("TFGNN_B200_FUSED_SPLIT", split)
+    rng = np.random.default_rng(V)
+    adjs = random_graph(rng, V, L, E, hub=True)
+    p = mo.default_hyperparameters("rgcn")
+    p.update(hidden_dim=H)
+    w = mo.make_weights("rgcn", p, D, L, rng)
+    layer = make_layer("rgcn", p, D, L, w)
+    h = torch.from_numpy(rng.uniform(-1, 1, (V, D)).astype(np.float32)).cuda()
+    adj_t = tuple(torch.from_numpy(a).cuda() for a in adjs)
+    lo, hi = (V // 3) // 128 * 128, V - 77
+    shard = PreparedBatch(adj_t, V, target_range=(lo, hi))
+    ref = layer(MessagePassingInput(h, adj_t), prepared=shard)
+    tables = [torch.full((V, H), -7.0, device="cuda") for _ in range(3)]
+    layer.call_allgather(h, shard, [t.data_ptr() for t in tables], own_rank=1)
+    torch.cuda.synchronize()
+    for t in tables:
+        assert torch.equal(t[lo:hi], ref)
+        assert bool((t[:lo] == -7.0).all()) and bool((t[hi:] == -7.0).all())
+    # a layer with a target-state input cannot take the fused kernel: the entry refuses instead of computing something else
+    p2 = dict(p, use_target_state_as_input=True)
+    layer2 = make_layer("gnn_edge_mlp", dict(mo.default_hyperparameters("gnn_edge_mlp"), hidden_dim=H), D, L,
+                        mo.make_weights("gnn_edge_mlp", dict(mo.default_hyperparameters("gnn_edge_mlp"), hidden_dim=H), D, L, rng))
+    with pytest.raises(NotImplementedError):
+        layer2.call_allgather(h, shard, [t.data_ptr() for t in tables], own_rank=0)
+    del p2

@@ -184,6 +184,8 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
     last.p[l] = mlp_weights[l * n_layers + n_hidden];
   }
 
+  if (b->n_peer_out > 0 && !(L > 0 && n_hidden == 0 && sum_like && !act_before && !use_target))
+    return unsupported("rgcn_fwd_allgather needs an RGCN-style layer (linear messages, sum/mean/sqrt_n, activation after)");
   if (L == 0) {
     // No edges at all: agg identity then activation (message_passing.py:172-177).
     EdgeReduceParams p;
@@ -221,8 +223,11 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
       epi.act = activation;
       epi.row_norm = row_norm; epi.row_ptr = b->row_ptr; epi.V = V; epi.L = L;
       return launch_fused_rgcn(h, D, b->row_ptr, b->src_sorted, b->M_in, V, L, normalize, (const float*)packed, corr, H,
-                               (float*)ring, out, ldo, epi, st);
+                               (float*)ring, out, ldo, epi, st, b->peer_out, b->n_peer_out);
     }
+    if (b->n_peer_out > 0)
+      return unsupported("rgcn_fwd_allgather: this shard does not take the fused kernel (need D % 32 == 0, 16 <= H <= 512, "
+                         "H % 16 == 0, no target-state input)");
     if (pipelined) {
       rc = launch_pack_vertical(first, L, 0, D, H, H, (float*)Wcat, H, 0, st);
       if (rc) return rc;
@@ -372,6 +377,27 @@ extern "C" int tfgnn_b200_rgcn_fwd(tfgnn_batch_t* batch, const float* h, int32_t
                                    int32_t path, float* out, void* stream) {
   return edge_mlp_core(batch, h, D, W, 0, H, flags & ~TFGNN_FLAG_USE_TARGET_STATE, aggregation, activation, path,
                        out, H, (cudaStream_t)stream);
+}
+
+extern "C" int tfgnn_b200_rgcn_fwd_allgather(tfgnn_batch_t* batch, const float* h, int32_t D, const float* const* W,
+                                             int32_t H, uint32_t flags, int32_t aggregation, int32_t activation,
+                                             float* const* out_replicas, int32_t num_replicas, int32_t own_rank,
+                                             void* stream) {
+  TFGNN_REQUIRE(batch != nullptr, "batch is NULL");
+  TFGNN_REQUIRE(out_replicas != nullptr && num_replicas >= 1 && num_replicas <= TFGNN_MAX_PEERS + 1,
+                "num_replicas must be in [1, 16]");
+  TFGNN_REQUIRE(own_rank >= 0 && own_rank < num_replicas, "own_rank out of range");
+  for (int r = 0; r < num_replicas; ++r) TFGNN_REQUIRE(out_replicas[r] != nullptr, "a replica pointer is NULL");
+  // replica tables hold ALL nodes; the kernel indexes rows of the shard: shift every base to the shard's first row
+  const size_t off = (size_t)batch->tgt_off * (size_t)H;
+  int n = 0;
+  for (int r = 0; r < num_replicas; ++r)
+    if (r != own_rank) batch->peer_out[n++] = out_replicas[r] + off;
+  batch->n_peer_out = n;   // 0 for a single replica: the plain fused layer
+  const int rc = edge_mlp_core(batch, h, D, W, 0, H, flags & ~TFGNN_FLAG_USE_TARGET_STATE, aggregation, activation,
+                               TFGNN_PATH_FUSED_TC, out_replicas[own_rank] + off, H, (cudaStream_t)stream);
+  batch->n_peer_out = 0;
+  return rc;
 }
 
 extern "C" int tfgnn_b200_dense_fwd(const float* x, const float* W, float* out, int64_t V, int32_t K, int32_t N,

@@ -131,6 +131,10 @@ struct tfgnn_batch {
   // not be used from two streams or two host threads at the same time.
   cudaStream_t cur_stream = nullptr;
   bool used = false;
+  // tfgnn_b200_rgcn_fwd_allgather: peer copies of the output table the fused kernel's epilogue also stores to (set for the
+  // duration of that call only)
+  float* peer_out[TFGNN_MAX_PEERS] = {};
+  int n_peer_out = 0;
   cudaEvent_t ev_switch = nullptr;
   // internal fork/join streams of the gather || node-GEMM pipeline (created lazily)
   static constexpr int kPipeBufs = 3;

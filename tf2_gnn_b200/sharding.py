@@ -139,3 +139,44 @@ def all_gather_node_states(h_local, bounds: Sequence[Tuple[int, int]], group=Non
     if all((hi - lo) == rows for lo, hi in bounds):
         return recv
     return torch.cat([recv[r * rows: r * rows + (hi - lo)] for r, (lo, hi) in enumerate(bounds)], dim=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# 2b. the all-gather fused into the layer kernel: node-state tables in peer-mapped (symmetric) memory
+# ------------------------------------------------------------------------------------------------
+class PeerNodeTables:
+    """Two [num_nodes, H] float32 node-state tables per rank, allocated in symmetric memory
+    (torch.distributed._symmetric_memory: CUDA VMM allocations every rank of the group maps over NVLink), so that the
+    epilogue of the fused layer kernel can store its output tiles straight into every rank's copy
+    (GNN_Edge_MLP.call_allgather / tfgnn_b200_rgcn_fwd_allgather).  Layer k reads `table(k)` and writes `table(k + 1)` on
+    all ranks; `barrier(k + 1)` is the rank synchronisation between layers.  Collective constructor."""
+
+    def __init__(self, num_nodes: int, hidden_dim: int, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group or dist.group.WORLD
+        dev = torch.device("cuda", torch.cuda.current_device())
+        try:   # older releases need the group to be enabled explicitly
+            if not symm_mem.is_symm_mem_enabled_for_group(group.group_name):
+                symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        self._tables, self._handles = [], []
+        for _ in range(2):
+            t = symm_mem.empty((int(num_nodes), int(hidden_dim)), dtype=torch.float32, device=dev)
+            self._handles.append(symm_mem.rendezvous(t, group))
+            self._tables.append(t)
+        self.rank = int(self._handles[0].rank)
+        self.world_size = int(self._handles[0].world_size)
+
+    def table(self, k: int):
+        return self._tables[k % 2]
+
+    def replica_ptrs(self, k: int):
+        """Device addresses of table k on every rank, as mapped into this process (index = rank)."""
+        return [int(p) for p in self._handles[k % 2].buffer_ptrs]
+
+    def barrier(self, k: int) -> None:
+        """All ranks have finished writing table k (enqueued on the current stream: a signal exchange in device memory)."""
+        self._handles[k % 2].barrier(channel=0)
