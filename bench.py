@@ -665,6 +665,12 @@ def measure_sharded(args, rank, world, local, dev):
                                 "rank's node-state table (P2P stores over NVLink, symmetric memory); no collective call, one "
                                 "signal exchange per layer"}
                   # the chained result against the same chain built from layer + NCCL all-gather (bitwise)
+                  dist.all_gather_into_tensor(tables.table(0), h_local)      # fresh start: the timing loop iterated the states
+                  torch.cuda.synchronize()
+                  barrier(world)
+                  chain()
+                  torch.cuda.synchronize()
+                  barrier(world)
                   h_a = h_local
                   full_t = torch.empty((V, H), dtype=torch.float32, device=dev)
                   for k in range(n_layers):
