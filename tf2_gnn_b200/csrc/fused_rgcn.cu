@@ -149,8 +149,10 @@ struct GatherIssue {
   }
   // one commit group per call of issue(): the next edge's row if there is one, else an empty group (only after
   // the last edge of the last call, so groups and consumed rows stay in step)
-  template <int NV>
+  // QT > 0: ring depth known at compile time (the default 4); FULL: D == 128 * NV, no column predicate
+  template <int NV, int QT = 0, bool FULL = false>
   __device__ __forceinline__ void issue() {
+    const int Qc = QT > 0 ? QT : Q;
     while (i_pos == i_end && ic + 1 < ncalls) next_call();
     if (i_pos < i_end) {
       if (in_blk == 32) {
@@ -163,12 +165,12 @@ struct GatherIssue {
       const float* rowp = h + (long long)s * ldh;
 #pragma unroll
       for (int j = 0; j < NV; ++j)
-        if (lane + 32 * j < C4) ptx::cp_async16(ibuf + 512u * j, rowp + 128 * j);
+        if (FULL || lane + 32 * j < C4) ptx::cp_async16(ibuf + 512u * j, rowp + 128 * j);
       ++in_blk;
       ++i_pos;
     }
     ptx::cp_async_commit();
-    if (++islot == Q) {
+    if (++islot == Qc) {
       islot = 0;
       ibuf = buf_s;
     } else {
@@ -192,12 +194,13 @@ __device__ __forceinline__ void cp_async_wait_oldest(int Q) {   // at most Q-1 g
 
 // split != 0 (split-tile mode): this CTA gathers only rows [split_rank*64, split_rank*64 + 64) of every tile; the slot
 // is shared with the peer CTA of the cluster, whose slot_ready barrier gets a (cluster-scope release) arrival as well.
-template <int NV>
-__device__ __forceinline__ void gather_warp_main(const FusedParams& p, int lane, int gw, int Q, uint8_t* bufs,
+template <int NV, int QT = 0, bool FULL = false>
+__device__ __forceinline__ void gather_warp_main(const FusedParams& p, int lane, int gw, int Q_in, uint8_t* bufs,
                                                  long long unit0, long long unit_step, long long total_units,
                                                  int ctas, int rank, int ring_row0, uint64_t* slot_ready,
                                                  uint64_t* slot_free, int split, int split_rank,
                                                  uint32_t peer_slot_ready0) {
+  const int Q = QT > 0 ? QT : Q_in;
   const int kRowsPerWarp = split ? kFuBM / 2 / kFuGatherWarps : kFuBM / kFuGatherWarps;
   const int row_off = split ? split_rank * (kFuBM / 2) : 0;
   const int D = p.D, C4 = p.D >> 2, normalize = p.normalize;
@@ -226,7 +229,7 @@ __device__ __forceinline__ void gather_warp_main(const FusedParams& p, int lane,
   int crp = g.rpA, crp_next = g.rpB;
   int cslot = 0;
   uint32_t cbuf = g.buf_s;
-  for (int i = 0; i < Q; ++i) g.template issue<NV>();   // fill the ring
+  for (int i = 0; i < Q; ++i) g.template issue<NV, QT, FULL>();   // fill the ring
 
   float4 acc[NV];
 #pragma unroll
@@ -266,7 +269,7 @@ __device__ __forceinline__ void gather_warp_main(const FusedParams& p, int lane,
       cp_async_wait_oldest(Q);
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        if (lane + 32 * j < C4) {
+        if (FULL || lane + 32 * j < C4) {
           const float4 x = ptx::lds_f4(cbuf + 512u * j);
           acc[j].x += x.x; acc[j].y += x.y; acc[j].z += x.z; acc[j].w += x.w;
         }
@@ -277,7 +280,7 @@ __device__ __forceinline__ void gather_warp_main(const FusedParams& p, int lane,
       } else {
         cbuf += g.row_bytes;
       }
-      g.template issue<NV>();   // refill the slot just read (same lane, same bytes: no cross-lane hazard)
+      g.template issue<NV, QT, FULL>();   // refill the slot just read (same lane, same bytes: no cross-lane hazard)
     }
     while (row < nrows) flush();
     // generic-proxy global writes -> visible to the TMA (async proxy) reads of this CTA
@@ -509,24 +512,29 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
               if (SPLIT) ptx::mbar_arrive_cluster_release(peer_slot_free0 + (uint32_t)(slot_it % kFuSlots) * 8u);
             }
           }
-          float4* a = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
-          float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + kFuATileBytes);
-#pragma unroll 2
-          for (int i = 0; i < kFuATileBytes / 16 / 128; ++i) {
-            const int idx = tid + i * 128;
-            const float4 x = a[idx];
+          // all 16-byte loads of this thread first, through explicit shared-space instructions (generic pointers made the
+          // compiler keep every load behind the previous iteration's stores: one shared-memory round trip per 16 bytes)
+          const uint32_t a_s = ptx::smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)tid * 16u;
+          const uint32_t lo_s = a_s + kFuATileBytes;
+          constexpr int kIt = kFuATileBytes / 16 / 128;
+          float4 xs[kIt];
+#pragma unroll
+          for (int i = 0; i < kIt; ++i) xs[i] = ptx::lds_f4(a_s + (uint32_t)i * 2048u);
+#pragma unroll
+          for (int i = 0; i < kIt; ++i) {
+            const float4 x = xs[i];
             float4 hh, ll;
             hh.x = ptx::tf32_hi(x.x); hh.y = ptx::tf32_hi(x.y); hh.z = ptx::tf32_hi(x.z); hh.w = ptx::tf32_hi(x.w);
             if (pair) {   // one tile of bf16 pairs (a | a - tf32(a)) in the bytes of the lo tile
               uint4 w;
               w.x = ptx::pack_bf16x2(x.x - hh.x, x.x); w.y = ptx::pack_bf16x2(x.y - hh.y, x.y);
               w.z = ptx::pack_bf16x2(x.z - hh.z, x.z); w.w = ptx::pack_bf16x2(x.w - hh.w, x.w);
-              reinterpret_cast<uint4*>(lo)[idx] = w;
+              ptx::sts_u4(lo_s + (uint32_t)i * 2048u, w);
             } else {
               ll.x = ptx::tf32_hi(x.x - hh.x); ll.y = ptx::tf32_hi(x.y - hh.y);
               ll.z = ptx::tf32_hi(x.z - hh.z); ll.w = ptx::tf32_hi(x.w - hh.w);
-              if (!raw_hi) a[idx] = hh;   // raw_hi: the tensor core itself drops the low 13 mantissa bits of the operand
-              lo[idx] = ll;
+              if (!raw_hi) ptx::sts_f4(a_s + (uint32_t)i * 2048u, hh);   // raw_hi: the tensor core itself drops the low 13 mantissa bits
+              ptx::sts_f4(lo_s + (uint32_t)i * 2048u, ll);
             }
           }
           ptx::fence_proxy_async_smem();
@@ -626,9 +634,16 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   } else if (warp >= kFuFirstGatherWarp) {
     // ================= gather warps =================
     const int gw = warp - kFuFirstGatherWarp;
-    gather_warp_main<NV>(p, lane, gw, p.gather_q, gbuf + (size_t)gw * p.gather_q * ((size_t)p.D * 4), unit0,
-                         unit_step, total_units, CTAS, (int)rank, ring_row0, slot_ready, slot_free, SPLIT ? 1 : 0,
-                         (int)srank, peer_slot_ready0);
+    // common case (ring depth 4, D a multiple of 128): depth and column predicate resolved at compile time - the gather
+    // loop runs once per EDGE and the kernel is co-limited by issue slots (58 %, ncu r2c)
+    if (p.gather_q == 4 && p.D == 128 * NV)
+      gather_warp_main<NV, 4, true>(p, lane, gw, 4, gbuf + (size_t)gw * 4 * ((size_t)p.D * 4), unit0, unit_step,
+                                    total_units, CTAS, (int)rank, ring_row0, slot_ready, slot_free, SPLIT ? 1 : 0,
+                                    (int)srank, peer_slot_ready0);
+    else
+      gather_warp_main<NV>(p, lane, gw, p.gather_q, gbuf + (size_t)gw * p.gather_q * ((size_t)p.D * 4), unit0,
+                           unit_step, total_units, CTAS, (int)rank, ring_row0, slot_ready, slot_free, SPLIT ? 1 : 0,
+                           (int)srank, peer_slot_ready0);
   }
 
   ptx::tc_fence_before_sync();

@@ -170,12 +170,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         ptx::mbar_wait(&full[s], ph);
-        float4* a = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes);
-        float4* lo = reinterpret_cast<float4*>(smem + (size_t)s * stage_bytes + kTcATileBytes);
+        // All eight 16-byte loads first, through explicit shared-space instructions: with generic pointers the compiler
+        // could not hoist a load above the previous iteration's stores (possible aliasing), so every thread paid one
+        // shared-memory round trip per 16 bytes: ~20 % of all stall samples sat on the LOP3 waiting for its LD (ncu r2c).
+        const uint32_t a_s = ptx::smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)tid * 16u;
+        const uint32_t lo_s = a_s + kTcATileBytes;
+        constexpr int kIt = kTcATileBytes / 16 / 128;
+        float4 xs[kIt];
 #pragma unroll
-        for (int i = 0; i < kTcATileBytes / 16 / 128; ++i) {
-          const int idx = tid + i * 128;
-          const float4 x = a[idx];
+        for (int i = 0; i < kIt; ++i) xs[i] = ptx::lds_f4(a_s + (uint32_t)i * 2048u);
+#pragma unroll
+        for (int i = 0; i < kIt; ++i) {
+          const float4 x = xs[i];
           float4 h, l;
           h.x = ptx::tf32_hi(x.x); h.y = ptx::tf32_hi(x.y); h.z = ptx::tf32_hi(x.z); h.w = ptx::tf32_hi(x.w);
           if (p.corr_bf16) {
@@ -184,14 +190,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             uint4 w;
             w.x = ptx::pack_bf16x2(x.x - h.x, x.x); w.y = ptx::pack_bf16x2(x.y - h.y, x.y);
             w.z = ptx::pack_bf16x2(x.z - h.z, x.z); w.w = ptx::pack_bf16x2(x.w - h.w, x.w);
-            reinterpret_cast<uint4*>(lo)[idx] = w;
+            ptx::sts_u4(lo_s + (uint32_t)i * 2048u, w);
           } else {
-            // the raw fp32 tile stays in place as the hi operand here too (kind::tf32 ignores the low 13 mantissa bits,
-            // bitwise identical results: tools/exp_rawhi.py) - the shared-memory LSU pipe is the busiest unit of this
-            // kernel (ncu r2c: 67 % at [2M,320]x[320,320]) and this drops a third of the splitter's wavefronts
+            // the raw fp32 tile stays in place as the hi operand here too (bitwise identical results) - the
+            // shared-memory LSU pipe is the busiest unit of this kernel (ncu r2c: 67 % at [2M,320]x[320,320])
             l.x = ptx::tf32_hi(x.x - h.x); l.y = ptx::tf32_hi(x.y - h.y);
             l.z = ptx::tf32_hi(x.z - h.z); l.w = ptx::tf32_hi(x.w - h.w);
-            lo[idx] = l;
+            ptx::sts_f4(lo_s + (uint32_t)i * 2048u, l);
           }
         }
         ptx::fence_proxy_async_smem();

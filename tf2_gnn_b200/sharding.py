@@ -157,11 +157,6 @@ class PeerNodeTables:
         import torch.distributed._symmetric_memory as symm_mem
         group = group or dist.group.WORLD
         dev = torch.device("cuda", torch.cuda.current_device())
-        try:   # older releases need the group to be enabled explicitly
-            if not symm_mem.is_symm_mem_enabled_for_group(group.group_name):
-                symm_mem.enable_symm_mem_for_group(group.group_name)
-        except Exception:
-            pass
         self._tables, self._handles = [], []
         for _ in range(2):
             t = symm_mem.empty((int(num_nodes), int(hidden_dim)), dtype=torch.float32, device=dev)
