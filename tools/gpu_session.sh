@@ -62,6 +62,7 @@ if has full; then
 fi
 if has gemmprof; then
   timeout 300 python tools/bench_gemm.py --paths sorted_tc > $OUT/gemm_micro.txt 2>&1; cat $OUT/gemm_micro.txt
+  if [ -n "${GEMM_NO_NCU:-}" ]; then echo "session $TAG done (gemm micro only)"; exit 0; fi
   for shp in 2000000,320,320 500000,128,384; do
     timeout 400 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 2 -c 1 -o $OUT/prof_gemm_${shp//,/_} -f \
       python tools/bench_gemm.py --shapes $shp --paths sorted_tc > $OUT/ncu_gemm_${shp//,/_}.log 2>&1
