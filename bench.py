@@ -296,6 +296,17 @@ def max_over_ranks(x, world):
     return float(t.item())
 
 
+def all_ranks_true(flag, world):
+    """Logical AND of a per-rank condition (collective)."""
+    if world == 1:
+        return bool(flag)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device="cuda" if torch.cuda.is_available() else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
 def barrier(world):
     if world > 1:
         import torch.distributed as dist
@@ -643,21 +654,29 @@ def measure_sharded(args, rank, world, local, dev):
                   tables.table(0)[lo:hi].copy_(h_local)
                   dist.all_gather_into_tensor(tables.table(0), h_local)      # the initial node states, once
 
-                  def chain():
-                      for k in range(n_layers):
-                          layer.call_allgather(tables.table(k), shard, tables.replica_ptrs(k + 1), rank)
-                          tables.barrier(k + 1)
+                  def make_chain(use_mc):
+                      def chain():
+                          for k in range(n_layers):
+                              layer.call_allgather(tables.table(k), shard, tables.replica_ptrs(k + 1), rank,
+                                                   multicast_ptr=tables.multicast_ptr(k + 1) if use_mc else 0)
+                              tables.barrier(k + 1)
+                      return chain
 
-                  for _ in range(3):
-                      chain()
-                  torch.cuda.synchronize()
-                  barrier(world)
-                  ev[0].record()
-                  for _ in range(n_it):
-                      chain()
-                  ev[1].record()
-                  torch.cuda.synchronize()
-                  fused_ms = max_over_ranks(ev[0].elapsed_time(ev[1]) / (n_it * n_layers), world)
+                  def time_chain(chain):
+                      for _ in range(3):
+                          chain()
+                      torch.cuda.synchronize()
+                      barrier(world)
+                      ev[0].record()
+                      for _ in range(n_it):
+                          chain()
+                      ev[1].record()
+                      torch.cuda.synchronize()
+                      return max_over_ranks(ev[0].elapsed_time(ev[1]) / (n_it * n_layers), world)
+
+                  have_mc = all_ranks_true(tables.multicast_ptr(0) != 0 and tables.multicast_ptr(1) != 0, world)
+                  chain = make_chain(False)
+                  fused_ms = time_chain(chain)
                   fz = {"ms_per_layer": fused_ms, "edges_per_s": m_total / (fused_ms * 1e-3), "layers_chained": n_layers,
                         "nvlink_bytes_stored_per_rank_per_layer": ag_bytes,
                         "nvlink_GBps_per_rank": ag_bytes / (fused_ms * 1e-3) / 1e9,
@@ -681,6 +700,22 @@ def measure_sharded(args, rank, world, local, dev):
                   torch.cuda.synchronize()
                   fz["bitwise_equal_to_nccl_chain"] = bool(torch.equal(final, full_t))
                   fz["max_abs_diff_to_nccl_chain"] = (final - full_t).abs().max().item()
+                  if have_mc:
+                      # the same through the switch's multicast: one multimem.st per 16 bytes instead of one store per peer
+                      mc_chain = make_chain(True)
+                      mc_ms = time_chain(mc_chain)
+                      dist.all_gather_into_tensor(tables.table(0), h_local)
+                      torch.cuda.synchronize()
+                      barrier(world)
+                      mc_chain()
+                      torch.cuda.synchronize()
+                      barrier(world)
+                      fz["multicast"] = {"ms_per_layer": mc_ms, "edges_per_s": m_total / (mc_ms * 1e-3),
+                                         "nvlink_bytes_stored_per_rank_per_layer": ag_bytes // max(world - 1, 1),
+                                         "bitwise_equal_to_nccl_chain": bool(torch.equal(tables.table(n_layers), full_t)),
+                                         "what": "multimem.st to the symmetric-memory multicast address: NVSwitch replicates"}
+                  else:
+                      fz["multicast"] = None
                   rec["fused_allgather"] = fz
                   del tables, full_t
               except Exception as e:

@@ -142,13 +142,17 @@ TFGNN_API int tfgnn_b200_rgcn_fwd(tfgnn_batch_t* batch, const float* h, int32_t 
  * NVLink: a symmetric-memory allocator, cudaIpcOpenMemHandle, NVSHMEM ...; out_replicas[own_rank] is local memory), rows
  * target_begin + v.  When every rank has run the call, each replica holds the all-gathered new node states: the per-layer
  * all-gather of the reference-sized alternative (ncclAllGather after the layer) overlaps the layer tile by tile instead of
- * following it.  The caller double-buffers the tables across layers (layer k reads table k%2, writes table (k+1)%2) and
+ * following it.  out_multicast (may be NULL): a MULTICAST mapping of the same tables (NVSwitch multicast object, e.g.
+ * cuMulticastBindMem / a symmetric-memory multicast pointer): the epilogue then issues ONE multimem.st per 16 bytes and the
+ * switch replicates it to every GPU, so a rank's NVLink egress per layer is its own rows once instead of once per peer.
+ * The caller double-buffers the tables across layers (layer k reads table k%2, writes table (k+1)%2) and
  * synchronises the ranks between layers (a few-microsecond signal exchange).
  * TFGNN_ERR_UNSUPPORTED when the shard does not take the fused kernel (D % 32, H % 16, H <= 512, linear messages,
  * sum/mean/sqrt_n, activation after aggregation): fall back to the layer call + an all-gather. */
 TFGNN_API int tfgnn_b200_rgcn_fwd_allgather(tfgnn_batch_t* batch, const float* h, int32_t D, const float* const* W, int32_t H,
                                             uint32_t flags, int32_t aggregation, int32_t activation,
-                                            float* const* out_replicas, int32_t num_replicas, int32_t own_rank, void* stream);
+                                            float* const* out_replicas, int32_t num_replicas, int32_t own_rank,
+                                            float* out_multicast, void* stream);
 
 /* Backward of tfgnn_b200_rgcn_fwd (the reference differentiates with tf.GradientTape,
  * models/graph_task_model.py:338-365).  batch_t is the SAME adjacency prepared with TFGNN_PREPARE_TRANSPOSE.

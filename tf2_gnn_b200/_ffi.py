@@ -125,7 +125,7 @@ def lib() -> ctypes.CDLL:
     L.tfgnn_b200_segment_max_bwd.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_int64,
                                              c_void_p, c_void_p]
     L.tfgnn_b200_rgcn_fwd_allgather.argtypes = [c_void_p, c_void_p, c_int32, _PP, c_int32, c_uint32, c_int32, c_int32, _PP,
-                                                c_int32, c_int32, c_void_p]
+                                                c_int32, c_int32, c_void_p, c_void_p]
     L.tfgnn_b200_set_l2_persist_mb.argtypes = [c_int32]
     L.tfgnn_b200_release_device_state.argtypes = []
     for name in EXPORTED_SYMBOLS:

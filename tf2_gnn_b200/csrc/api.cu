@@ -223,7 +223,7 @@ int edge_mlp_core(tfgnn_batch* b, const float* h, int D, const float* const* mlp
       epi.act = activation;
       epi.row_norm = row_norm; epi.row_ptr = b->row_ptr; epi.V = V; epi.L = L;
       return launch_fused_rgcn(h, D, b->row_ptr, b->src_sorted, b->M_in, V, L, normalize, (const float*)packed, corr, H,
-                               (float*)ring, out, ldo, epi, st, b->peer_out, b->n_peer_out);
+                               (float*)ring, out, ldo, epi, st, b->peer_out, b->n_peer_out, b->mc_out);
     }
     if (b->n_peer_out > 0)
       return unsupported("rgcn_fwd_allgather: this shard does not take the fused kernel (need D % 32 == 0, 16 <= H <= 512, "
@@ -382,7 +382,7 @@ extern "C" int tfgnn_b200_rgcn_fwd(tfgnn_batch_t* batch, const float* h, int32_t
 extern "C" int tfgnn_b200_rgcn_fwd_allgather(tfgnn_batch_t* batch, const float* h, int32_t D, const float* const* W,
                                              int32_t H, uint32_t flags, int32_t aggregation, int32_t activation,
                                              float* const* out_replicas, int32_t num_replicas, int32_t own_rank,
-                                             void* stream) {
+                                             float* out_multicast, void* stream) {
   TFGNN_REQUIRE(batch != nullptr, "batch is NULL");
   TFGNN_REQUIRE(out_replicas != nullptr && num_replicas >= 1 && num_replicas <= TFGNN_MAX_PEERS + 1,
                 "num_replicas must be in [1, 16]");
@@ -394,9 +394,11 @@ extern "C" int tfgnn_b200_rgcn_fwd_allgather(tfgnn_batch_t* batch, const float* 
   for (int r = 0; r < num_replicas; ++r)
     if (r != own_rank) batch->peer_out[n++] = out_replicas[r] + off;
   batch->n_peer_out = n;   // 0 for a single replica: the plain fused layer
+  batch->mc_out = (out_multicast && n > 0) ? out_multicast + off : nullptr;
   const int rc = edge_mlp_core(batch, h, D, W, 0, H, flags & ~TFGNN_FLAG_USE_TARGET_STATE, aggregation, activation,
                                TFGNN_PATH_FUSED_TC, out_replicas[own_rank] + off, H, (cudaStream_t)stream);
   batch->n_peer_out = 0;
+  batch->mc_out = nullptr;
   return rc;
 }
 

@@ -135,6 +135,7 @@ struct tfgnn_batch {
   // duration of that call only)
   float* peer_out[TFGNN_MAX_PEERS] = {};
   int n_peer_out = 0;
+  float* mc_out = nullptr;   // multicast mapping of all replicas (one multimem.st reaches every GPU)
   cudaEvent_t ev_switch = nullptr;
   // internal fork/join streams of the gather || node-GEMM pipeline (created lazily)
   static constexpr int kPipeBufs = 3;

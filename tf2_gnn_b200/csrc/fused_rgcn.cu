@@ -65,6 +65,7 @@ struct FusedParams {
   // fused all-gather (tfgnn_b200_rgcn_fwd_allgather): peer copies of the output table, NVLink-mapped; same row indexing as C
   float* C_peer[TFGNN_MAX_PEERS];
   int n_peer;
+  float* C_mc;   // multicast mapping of all replicas (NVSwitch replicates one multimem.st), or null
   GemmEpilogue epi;
 };
 
@@ -616,10 +617,18 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           if (grow < p.V) {
             const float4 val = *reinterpret_cast<const float4*>(stage + r * kFuEpiPitch + cc);
             const long long off = grow * p.ldc + n0 + c0 + cc;
-            ptx::st_f4_hint(p.C + off, val, pol_stream);
-            // the all-gather of the sharded layer, tile by tile: the same 16 bytes go to every peer's copy of the table
-            // over NVLink (plain stores to P2P-mapped memory; the copies become the next layer's source table)
-            for (int pr = 0; pr < p.n_peer; ++pr) *reinterpret_cast<float4*>(p.C_peer[pr] + off) = val;
+            if (p.C_mc) {
+              // the all-gather of the sharded layer through the switch: ONE multimem.st, NVSwitch replicates the 16 bytes
+              // into every GPU's copy of the table (this GPU's included)
+              asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.C_mc + off), "f"(val.x),
+                           "f"(val.y), "f"(val.z), "f"(val.w)
+                           : "memory");
+            } else {
+              ptx::st_f4_hint(p.C + off, val, pol_stream);
+              // the all-gather of the sharded layer, tile by tile: the same 16 bytes go to every peer's copy of the table
+              // over NVLink (plain stores to P2P-mapped memory; the copies become the next layer's source table)
+              for (int pr = 0; pr < p.n_peer; ++pr) *reinterpret_cast<float4*>(p.C_peer[pr] + off) = val;
+            }
           }
         }
         __syncwarp();
@@ -757,7 +766,7 @@ size_t fused_rgcn_ring_bytes(int D, int L, int H) {
 
 int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src, long long M, int V, int L,
                       int normalize, const float* packedB, int corr_bf16, int H, float* ring, float* out, int ldo,
-                      const GemmEpilogue& epi, cudaStream_t st, float* const* peer_out, int n_peer_out) {
+                      const GemmEpilogue& epi, cudaStream_t st, float* const* peer_out, int n_peer_out, float* mc_out) {
   EncodeTiledFn encode = fu_encode_fn();
   if (!encode) {
     set_error(TFGNN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -777,6 +786,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   p.corr_bf16 = corr_bf16;
   p.n_peer = 0;
   for (int r = 0; r < n_peer_out && r < TFGNN_MAX_PEERS; ++r) p.C_peer[p.n_peer++] = peer_out[r];
+  p.C_mc = mc_out;
   p.N = H;
   p.m_tiles = ((long long)V + kFuBM - 1) / kFuBM;
   if (sms > kFuMaxGrid) sms = kFuMaxGrid;

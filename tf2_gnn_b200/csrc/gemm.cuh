@@ -38,7 +38,7 @@ bool fused_rgcn_supported(long long V, int L, int D, int H, const float* h, cons
 size_t fused_rgcn_ring_bytes(int D, int L, int H);
 int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src, long long M, int V, int L, int normalize,
                       const float* packedB, int corr_bf16, int H, float* ring, float* out, int ldo, const GemmEpilogue& epi,
-                      cudaStream_t st, float* const* peer_out = nullptr, int n_peer_out = 0);
+                      cudaStream_t st, float* const* peer_out = nullptr, int n_peer_out = 0, float* mc_out = nullptr);
 
 int gemm_corr_bf16();                 // correction scheme of the 3xTF32 contractions (gemm_tc.cu)
 int fused_corr_bf16(int activation);

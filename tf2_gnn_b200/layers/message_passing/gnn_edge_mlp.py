@@ -135,13 +135,15 @@ class GNN_Edge_MLP(MessagePassing):
             _ffi.PATH[self._path], out.data_ptr(), stream_ptr()))
         return out
 
-    def call_allgather(self, node_embeddings: torch.Tensor, prepared: PreparedBatch, replica_ptrs, own_rank: int) -> None:
+    def call_allgather(self, node_embeddings: torch.Tensor, prepared: PreparedBatch, replica_ptrs, own_rank: int,
+                       multicast_ptr: int = 0) -> None:
         """The layer on a target-range shard with the all-gather fused into the kernel's epilogue
         (tfgnn_b200_rgcn_fwd_allgather, SURVEY.md §8e case 2): `node_embeddings` is this rank's full [V, D] source table,
         `replica_ptrs[r]` the device address, mapped into this process, of rank r's [V, H] OUTPUT table (e.g.
         sharding.PeerNodeTables).  Output rows [target_begin, target_end) of every replica are written; nothing is
         returned.  Raises NotImplementedError when the shard does not take the fused kernel (use the plain call + an
-        all-gather then)."""
+        all-gather then).  `multicast_ptr`: a multicast (NVSwitch) mapping of the same tables, if the platform has one: the
+        epilogue then issues one multimem.st instead of one store per peer."""
         from ctypes import c_void_p
         if int(self._num_edge_MLP_hidden_layers) != 0 or self._use_target_state_as_input:
             raise NotImplementedError("call_allgather needs an RGCN-style layer (no hidden layers, source state only)")
@@ -151,7 +153,7 @@ class GNN_Edge_MLP(MessagePassing):
         _ffi.check(_ffi.lib().tfgnn_b200_rgcn_fwd_allgather(
             prepared.handle, node_embeddings.data_ptr(), int(node_embeddings.shape[1]), _ffi.ptr_array(tensors),
             self._hidden_dim, self._flags(), self._aggregation_fn.code, self._activation_fn.code, reps, len(replica_ptrs),
-            int(own_rank), stream_ptr()))
+            int(own_rank), c_void_p(int(multicast_ptr) or None), stream_ptr()))
 
     def _message_function(self, edge_source_states, edge_target_states, num_incoming_to_node_per_message,
                           edge_type_idx: int, training: bool):

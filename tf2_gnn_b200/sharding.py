@@ -172,6 +172,19 @@ class PeerNodeTables:
         """Device addresses of table k on every rank, as mapped into this process (index = rank)."""
         return [int(p) for p in self._handles[k % 2].buffer_ptrs]
 
+    def multicast_ptr(self, k: int) -> int:
+        """Multicast (NVSwitch / NVLS) address of table k: one store to it lands in every rank's table; 0 if unsupported."""
+        h = self._handles[k % 2]
+        try:
+            return int(h.multicast_ptr) if h.has_multicast_support(h.device.type, h.device.index) else 0
+        except TypeError:
+            try:
+                return int(h.multicast_ptr or 0)
+            except Exception:
+                return 0
+        except Exception:
+            return 0
+
     def barrier(self, k: int) -> None:
         """All ranks have finished writing table k (enqueued on the current stream: a signal exchange in device memory)."""
         self._handles[k % 2].barrier(channel=0)
