@@ -42,6 +42,7 @@ struct TcParams {
   long long m_tiles, total_tiles;
   int num_k_blocks, num_stages;
   int corr_bf16;   // 1: corrections as one bf16-pair MMA (sm100_ptx.cuh), 0: two tf32 MMAs (round-1 scheme)
+  int prefetch_a;  // 1: L2-prefetch the A tile of this CTA's NEXT output tile while the current one is loaded
   float* C;
   int ldc;
   GemmEpilogue epi;
@@ -113,6 +114,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           ptx::mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + (size_t)s * stage_bytes;
           ptx::mbar_arrive_expect_tx(&full[s], kTcATileBytes + 2 * b_tile_bytes);
+          if (p.prefetch_a) {
+            // The pipeline holds only 3 stages of 50-64 KB, so its k-block rate is (stages / TMA latency): ~1 us per k-block
+            // when A comes from HBM under load.  The next tile's A lines are requested into L2 now, ~10 k-blocks early.
+            const long long nt = tile + gridDim.x;
+            if (nt < p.total_tiles && (nt / p.n_tiles) != (tile / p.n_tiles))
+              ptx::tma_prefetch_2d(&map_a, kb * kTcBK, (int)((nt / p.n_tiles) * kTcBM));
+          }
           ptx::tma_load_2d(st, &map_a, &full[s], kb * kTcBK, m0);
           ptx::tma_load_2d(st + 2 * kTcATileBytes, &map_b, &full[s], kb * kTcBK, n0);
           ptx::tma_load_2d(st + 2 * kTcATileBytes + b_tile_bytes, &map_b, &full[s], kb * kTcBK, p.N + n0);
@@ -464,6 +472,10 @@ int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int 
   TFGNN_REQUIRE(stages >= 2, "tcgen05 GEMM: tile does not fit shared memory");
   p.num_stages = stages;
   p.corr_bf16 = gemm_corr_bf16();
+  {
+    const char* e = getenv("TFGNN_B200_GEMM_PREFETCH");   // read per call (A/B experiments)
+    p.prefetch_a = e ? (atoi(e) != 0) : 1;
+  }
   p.C = C; p.ldc = ldc; p.epi = epi;
 
   CUtensorMap map_a, map_b;

@@ -59,6 +59,14 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// Prefetch a 2-D tile into L2 (no shared-memory destination, no barrier): issued a whole tile ahead by the GEMM's producer so
+// that the later cp.async.bulk.tensor finds its lines in L2 instead of paying a loaded-HBM round trip inside the pipeline.
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+
 // 2-D tile load with an L2 cache-policy operand (createpolicy).
 __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0,
                                                  int c1, uint64_t policy) {
