@@ -645,14 +645,14 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int gw = warp - kFuFirstGatherWarp;
     // common case (ring depth 4, D a multiple of 128): depth and column predicate resolved at compile time - the gather
     // loop runs once per EDGE and the kernel is co-limited by issue slots (58 %, ncu r2c)
-    if (p.gather_q == 4 && p.D == 128 * NV)
-      gather_warp_main<NV, 4, true>(p, lane, gw, 4, gbuf + (size_t)gw * 4 * ((size_t)p.D * 4), unit0, unit_step,
-                                    total_units, CTAS, (int)rank, ring_row0, slot_ready, slot_free, SPLIT ? 1 : 0,
-                                    (int)srank, peer_slot_ready0);
-    else
-      gather_warp_main<NV>(p, lane, gw, p.gather_q, gbuf + (size_t)gw * p.gather_q * ((size_t)p.D * 4), unit0,
-                           unit_step, total_units, CTAS, (int)rank, ring_row0, slot_ready, slot_free, SPLIT ? 1 : 0,
-                           (int)srank, peer_slot_ready0);
+    uint8_t* my_bufs = gbuf + (size_t)gw * p.gather_q * ((size_t)p.D * 4);
+#define TFGNN_FU_GATHER(QT, FULL)                                                                                      \
+    gather_warp_main<NV, QT, FULL>(p, lane, gw, p.gather_q, my_bufs, unit0, unit_step, total_units, CTAS, (int)rank,     \
+                                   ring_row0, slot_ready, slot_free, SPLIT ? 1 : 0, (int)srank, peer_slot_ready0)
+    if (p.gather_q == 4 && p.D == 128 * NV) TFGNN_FU_GATHER(4, true);
+    else if (p.gather_q == 4) TFGNN_FU_GATHER(4, false);       // e.g. D = 320: the third 16-byte column group is half empty
+    else TFGNN_FU_GATHER(0, false);
+#undef TFGNN_FU_GATHER
   }
 
   ptx::tc_fence_before_sync();
