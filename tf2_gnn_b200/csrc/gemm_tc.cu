@@ -32,8 +32,7 @@ constexpr int kTcThreads = 320;
 constexpr int kTcTmemCols = 512;
 constexpr int kTcAccStride = 256;               // TMEM columns per accumulator stage (main + correction)
 constexpr int kTcSmemLimit = 227 * 1024;
-constexpr int kTcEpiPitch = 20;                 // floats per staged row (16 + 4 pad, keeps 16 B alignment); 16-column chunks
-                                                // keep the staging at 10 KB so that 80-column tiles get a 4th pipeline stage
+constexpr int kTcEpiPitch = 36;                 // floats per staged row (32 + 4 pad, keeps 16 B alignment)
 constexpr int kTcEpiBytes = 4 * 32 * kTcEpiPitch * 4;  // 4 epilogue warps x 32 rows
 
 struct TcParams {
@@ -141,59 +140,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       ptx::tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * kTcAccStride;
       const uint32_t c_tmem = d_tmem + corr_off;
-      // Software pipeline over K blocks: the MAIN product of block i reads the raw fp32 tile (the splitter never rewrites it)
-      // and is issued as soon as the TMA bytes have landed; the CORRECTION products of block i-1 follow, by which time its
-      // splitter pass has long finished.  The split is thereby off the TMA -> MMA -> stage-free chain that, with 3-4 stages
-      // in flight, sets the k-block rate of this kernel (ncu r2c: tensor pipe 31 % at K = 320).
-      int prev_s = -1, prev_kb = 0;
-      uint32_t prev_ph = 0;
-      auto issue_corr = [&](int cs, int ckb, bool last) {   // lane 0 only
-        const uint32_t st = ptx::smem_u32(smem + (size_t)cs * stage_bytes);
-        const uint64_t a_hi = ptx::umma_desc_k_sw128(st);
-        const uint64_t a_lo = ptx::umma_desc_k_sw128(st + kTcATileBytes);
-        const uint64_t b_hi = ptx::umma_desc_k_sw128(st + 2 * kTcATileBytes);
-        const uint64_t b_lo = ptx::umma_desc_k_sw128(st + 2 * kTcATileBytes + b_tile_bytes);
-#pragma unroll
-        for (int k = 0; k < kTcBK / 8; ++k) {
-          const uint64_t adv = (uint64_t)(k * 32 >> 4);
-          if (p.corr_bf16) {
-            ptx::mma_bf16_ss(c_tmem, a_lo + adv, b_lo + adv, idesc_bf, (ckb | k) != 0);   // pair tiles: a lo(b) + lo(a) b
-          } else {
-            ptx::mma_tf32_ss(c_tmem, a_lo + adv, b_hi + adv, idesc, (ckb | k) != 0);
-            ptx::mma_tf32_ss(c_tmem, a_hi + adv, b_lo + adv, idesc, 1);
-          }
-        }
-        ptx::mma_commit(&empty[cs]);                      // main + corrections of that stage have retired: stage free
-        if (last) ptx::mma_commit(&tmem_full[acc]);
-      };
       for (int kb = 0; kb < p.num_k_blocks; ++kb, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         ptx::mbar_wait(&full[s], ph);
+        ptx::mbar_wait(&split[s], ph);
         ptx::tc_fence_after_sync();
         if (lane == 0) {
           const uint32_t st = ptx::smem_u32(smem + (size_t)s * stage_bytes);
-          const uint64_t a_hi = ptx::umma_desc_k_sw128(st);                       // raw fp32: the tensor core truncates
+          const uint64_t a_hi = ptx::umma_desc_k_sw128(st);
+          const uint64_t a_lo = ptx::umma_desc_k_sw128(st + kTcATileBytes);
           const uint64_t b_hi = ptx::umma_desc_k_sw128(st + 2 * kTcATileBytes);
+          const uint64_t b_lo = ptx::umma_desc_k_sw128(st + 2 * kTcATileBytes + b_tile_bytes);
 #pragma unroll
           for (int k = 0; k < kTcBK / 8; ++k) {
-            const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 8 tf32 = 32 B along K inside the swizzle row
+            const uint64_t adv = (uint64_t)(k * 32 >> 4);  // 8 tf32 (or 16 bf16) = 32 B along K inside the swizzle row
+            if (p.corr_bf16) {
+              ptx::mma_bf16_ss(c_tmem, a_lo + adv, b_lo + adv, idesc_bf, (kb | k) != 0);   // pair tiles: a lo(b) + lo(a) b
+            } else {
+              ptx::mma_tf32_ss(c_tmem, a_lo + adv, b_hi + adv, idesc, (kb | k) != 0);
+              ptx::mma_tf32_ss(c_tmem, a_hi + adv, b_lo + adv, idesc, 1);
+            }
             ptx::mma_tf32_ss(d_tmem, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
           }
+          ptx::mma_commit(&empty[s]);
+          if (kb == p.num_k_blocks - 1) ptx::mma_commit(&tmem_full[acc]);
         }
         __syncwarp();
-        if (prev_s >= 0) {
-          ptx::mbar_wait(&split[prev_s], prev_ph);
-          ptx::tc_fence_after_sync();
-          if (lane == 0) issue_corr(prev_s, prev_kb, false);
-          __syncwarp();
-        }
-        prev_s = s; prev_ph = ph; prev_kb = kb;
       }
-      ptx::mbar_wait(&split[prev_s], prev_ph);
-      ptx::tc_fence_after_sync();
-      if (lane == 0) issue_corr(prev_s, prev_kb, true);
-      __syncwarp();
     }
   } else if (warp < 6) {
     // ================= A splitters (128 threads) =================
@@ -255,8 +229,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool chained = p.epi.mul != nullptr || p.epi.accumulate || !p.epi.finalize;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTcAccStride;
       float* stage = epi_stage + (size_t)(warp - 6) * 32 * kTcEpiPitch;
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-        const int ncols = 16;
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        const int ncols = min(32, p.block_n - c0);     // 32 or 16
         // TMEM -> registers (row = lane), epilogue math, -> smem staging tile [32 rows][ncols]
         {
           // TMEM -> registers: main and correction accumulators of up to 32 columns, ONE wait

@@ -47,26 +47,24 @@ struct RgatParams {
 //   far are rescaled by exp(m_old - m_new).  Every edge's score and P row are read once instead of twice (round 1 walked
 //   each target's edges twice: 13 ms of the 22 ms cfg3 layer).
 template <int PASS>
-__device__ __forceinline__ void rgat_walk(const RgatParams& p, int l, int e_lo, int e_hi, float st, int k, int c, int lane,
-                                          bool col_ok, float& m, float& den, float4& acc) {
-  constexpr int U = 8;   // edges in flight per lane: 8 row loads of 16 B + 8 score loads (round 1: 4; the kernel is bound
-                         // by independent loads in flight, not by arithmetic)
+__device__ __forceinline__ void rgat_walk(const RgatParams& p, int l, int e_lo, int e_hi, float st, int k, int c,
+                                          int lane, bool col_ok, float& m, float& den, float4& acc) {
   const long long LK = (long long)p.L * p.K, LH = (long long)p.L * p.H;
   for (int base = e_lo; base < e_hi; base += 32) {
     const int n = min(32, e_hi - base);
     const int my_src = lane < n ? __ldg(p.src + base + lane) : 0;
-    for (int j0 = 0; j0 < n; j0 += U) {
-      float sc[U];
-      float4 x[U];
+    for (int j0 = 0; j0 < n; j0 += 4) {
+      float sc[4];
+      float4 x[4];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int u = 0; u < 4; ++u) {
         const long long s = __shfl_sync(0xffffffffu, my_src, (j0 + u) & 31);
         const bool ok = (j0 + u < n) && col_ok;
         sc[u] = ok ? __ldg(p.s_src + s * LK + l * p.K + k) : 0.f;
         if (PASS >= 1) x[u] = ok ? ldg_f4(p.P + s * LH + (long long)l * p.H + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int u = 0; u < 4; ++u) {
         if (j0 + u < n) {
           const float score = rgat_leaky(sc[u] + st);
           if (PASS == 0) {
