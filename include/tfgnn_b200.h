@@ -263,7 +263,13 @@ TFGNN_API int tfgnn_b200_axpby(const float* a, float alpha, const float* b, floa
  *   activation_bwd     grad_in = grad_out * act'(.); `ref` = forward OUTPUT (gelu: forward INPUT)
  *   row_scale          out[m,:] = x[m,:] * f(s[m]); f = s | 1/(s+1e-7) | 1/max(s,1) | 1/sqrt(max(s,1))   (modes 0..3)
  *   mul_add            out = a * b (+ c) on 2-D views with leading dimensions (FiLM: gamma * m + beta, gnn_film.py:105-107)
- *   segment_max_bwd    gradient of unsorted_segment_max: to the elements that attain the maximum, shared among ties */
+ *   segment_max_bwd    gradient of unsorted_segment_max: to the elements that attain the maximum, shared among ties
+ *   softmax_apply      exp(s - m) or exp((s - m) - log z) on per-element gathered segment max / sum (the two elementwise
+ *                      stages of dpu_utils unsorted_segment_(log_)softmax: rgat.py:147-151,
+ *                      nodes_to_graph_representation.py:179-185)
+ *   head_scale         out[e, k*d+i] = w[e,k] * x[e, k*d+i]  (attention-weighted messages rgat.py:152-155, readout :219-220)
+ *   head_dot           out[e,k] = sum_i a[e,k*d+i] * b[e,k*d+i]  (gradient of head_scale with respect to w)
+ *   gru_gate_bwd       backward of gru_gate_fwd: grad_gx, grad_gh [V,3H] and the direct path grad_out * z [V,H] */
 TFGNN_API int tfgnn_b200_activation_bwd(const float* ref, const float* grad_out, int64_t n, int32_t activation,
                                         float* grad_in, void* stream);
 TFGNN_API int tfgnn_b200_row_scale(const float* x, const float* s, int64_t M, int32_t H, int32_t mode, float* out,
@@ -273,6 +279,14 @@ TFGNN_API int tfgnn_b200_mul_add(const float* a, int32_t lda, const float* b, in
 TFGNN_API int tfgnn_b200_segment_max_bwd(const float* data, const int32_t* segment_ids, int64_t ids_stride,
                                          const float* segment_out, const float* segment_grad, int64_t M, int32_t H,
                                          int64_t num_segments, float* grad_data, void* stream);
+TFGNN_API int tfgnn_b200_softmax_apply(const float* scores, const float* seg_max_per_elem, const float* seg_sum_per_elem,
+                                       int64_t n, float* out, void* stream);
+TFGNN_API int tfgnn_b200_head_scale(const float* x, const float* w, int64_t M, int32_t num_heads, int32_t head_dim, float* out,
+                                    void* stream);
+TFGNN_API int tfgnn_b200_head_dot(const float* a, const float* b, int64_t M, int32_t num_heads, int32_t head_dim, float* out,
+                                  void* stream);
+TFGNN_API int tfgnn_b200_gru_gate_bwd(const float* gx, const float* gh, const float* h, const float* grad_out, int64_t num_rows,
+                                      int32_t H, float* grad_gx, float* grad_gh, float* grad_h_direct, void* stream);
 
 /* ---- Graph-level readout and global exchange ---------------------------------------------
  * Segment primitives keyed by node_to_graph_map, which is non-decreasing (graph_dataset.py:211-217; the reference's own

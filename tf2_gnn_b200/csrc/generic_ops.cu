@@ -329,3 +329,118 @@ extern "C" int tfgnn_b200_segment_max_bwd(const float* data, const int32_t* segm
   pool_free(ties, st);
   return 0;
 }
+
+// ---- attention / softmax pieces of the differentiable generic path (rgat.py:133-160, nodes_to_graph_representation.py:176-227)
+namespace tfgnn {
+
+// out = exp(s - m)                      (z == nullptr)
+// out = exp((s - m) - log(z))           (dpu_utils unsorted_segment_log_softmax, then tf.exp: rgat.py:147-151)
+__global__ void softmax_apply_kernel(const float* __restrict__ s, const float* __restrict__ m, const float* __restrict__ z,
+                                     long long n, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float r = s[i] - m[i];
+    out[i] = z ? expf(r - logf(z[i])) : expf(r);
+  }
+}
+
+// out[e, k*d + i] = w[e, k] * x[e, k*d + i]     (tf.expand_dims(attention, -1) * messages, rgat.py:152-155)
+__global__ void head_scale_kernel(const float* __restrict__ x, const float* __restrict__ w, long long M, int K, int d,
+                                  float* __restrict__ out) {
+  const int H = K * d;
+  const long long total = M * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i / H;
+    const int k = (int)(i - e * H) / d;
+    out[i] = w[e * K + k] * x[i];
+  }
+}
+
+// out[e, k] = sum_i a[e, k*d + i] * b[e, k*d + i]   (gradient of head_scale with respect to the weights)
+__global__ void head_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, long long M, int K, int d,
+                                float* __restrict__ out) {
+  const long long total = M * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i / K;
+    const int k = (int)(i - e * K);
+    const float* pa = a + e * (long long)K * d + (long long)k * d;
+    const float* pb = b + e * (long long)K * d + (long long)k * d;
+    float s = 0.f;
+    for (int j = 0; j < d; ++j) s = fmaf(pa[j], pb[j], s);
+    out[i] = s;
+  }
+}
+
+// Keras GRUCell(reset_after=True) gate backward given gx = inputs K + b0, gh = h U + b1 (not modified): dgx, dgh, and the
+// direct path dL/dh' * z through the convex combination.
+__global__ void gru_gate_bwd_out_kernel(const float* __restrict__ gx, const float* __restrict__ gh, const float* __restrict__ h,
+                                        const float* __restrict__ grad_out, long long V, int H, float* __restrict__ dgx,
+                                        float* __restrict__ dgh, float* __restrict__ dh_direct) {
+  const long long total = V * H;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long v = i / H;
+    const int c = (int)(i - v * H);
+    const float* x = gx + v * 3 * H;
+    const float* y = gh + v * 3 * H;
+    const float ghh = y[2 * H + c];
+    const float z = 1.0f / (1.0f + expf(-(x[c] + y[c])));
+    const float r = 1.0f / (1.0f + expf(-(x[H + c] + y[H + c])));
+    const float hh = tanhf(x[2 * H + c] + r * ghh);
+    const float g = grad_out[i];
+    const float da = g * (1.0f - z) * (1.0f - hh * hh);
+    const float daz = g * (h[i] - hh) * z * (1.0f - z);
+    const float dar = da * ghh * r * (1.0f - r);
+    float* ox = dgx + v * 3 * H;
+    float* oy = dgh + v * 3 * H;
+    ox[c] = daz;          oy[c] = daz;
+    ox[H + c] = dar;      oy[H + c] = dar;
+    ox[2 * H + c] = da;   oy[2 * H + c] = da * r;
+    dh_direct[i] = g * z;
+  }
+}
+
+}  // namespace tfgnn
+
+extern "C" int tfgnn_b200_softmax_apply(const float* scores, const float* seg_max_per_elem, const float* seg_sum_per_elem,
+                                        int64_t n, float* out, void* stream) {
+  TFGNN_REQUIRE(n >= 0, "negative size");
+  if (n == 0) return 0;
+  TFGNN_REQUIRE(scores && seg_max_per_elem && out, "NULL pointer");
+  softmax_apply_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(scores, seg_max_per_elem, seg_sum_per_elem, n, out);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tfgnn_b200_head_scale(const float* x, const float* w, int64_t M, int32_t num_heads, int32_t head_dim,
+                                     float* out, void* stream) {
+  TFGNN_REQUIRE(M >= 0 && num_heads > 0 && head_dim > 0, "bad head_scale arguments");
+  if (M == 0) return 0;
+  TFGNN_REQUIRE(x && w && out, "NULL pointer");
+  head_scale_kernel<<<grid_for(M * num_heads * head_dim), 256, 0, (cudaStream_t)stream>>>(x, w, M, num_heads, head_dim, out);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tfgnn_b200_head_dot(const float* a, const float* b, int64_t M, int32_t num_heads, int32_t head_dim, float* out,
+                                   void* stream) {
+  TFGNN_REQUIRE(M >= 0 && num_heads > 0 && head_dim > 0, "bad head_dot arguments");
+  if (M == 0) return 0;
+  TFGNN_REQUIRE(a && b && out, "NULL pointer");
+  head_dot_kernel<<<grid_for(M * num_heads), 256, 0, (cudaStream_t)stream>>>(a, b, M, num_heads, head_dim, out);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int tfgnn_b200_gru_gate_bwd(const float* gx, const float* gh, const float* h, const float* grad_out,
+                                       int64_t num_rows, int32_t H, float* grad_gx, float* grad_gh, float* grad_h_direct,
+                                       void* stream) {
+  TFGNN_REQUIRE(num_rows >= 0 && H > 0, "bad gru_gate_bwd sizes");
+  if (num_rows == 0) return 0;
+  TFGNN_REQUIRE(gx && gh && h && grad_out && grad_gx && grad_gh && grad_h_direct, "NULL pointer");
+  gru_gate_bwd_out_kernel<<<grid_for(num_rows * H), 256, 0, (cudaStream_t)stream>>>(gx, gh, h, grad_out, num_rows, H,
+                                                                                   grad_gx, grad_gh, grad_h_direct);
+  TFGNN_LAUNCH_CHECK();
+  return 0;
+}

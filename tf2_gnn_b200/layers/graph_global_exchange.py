@@ -69,7 +69,10 @@ class GraphGlobalExchange:
             n2g = torch.as_tensor(n2g)
         n2g = n2g.to(device=x.device, dtype=torch.int32).contiguous()
         num_graphs = int(inputs.num_graphs)
-        node_ops.require_no_grad(type(self).__name__, x, *[v.value for v in self.variables])
+        if node_ops._needs_grad(x, *[v.value for v in self.variables]):
+            # training: the reference's op order with per-op backward kernels; per-node copies are materialised
+            from .differentiable import per_node_graph_representations
+            return x, per_node_graph_representations(self, x, n2g, num_graphs, training), None
         self._node_to_graph_representation_layer.dropout_state = self.dropout_state
         graph_reprs = self._node_to_graph_representation_layer.call(
             NodesToGraphRepresentationInput(x, n2g, num_graphs), training=training)
@@ -92,6 +95,9 @@ class GraphGlobalMeanExchange(GraphGlobalExchange):
 
     def call(self, inputs: GraphGlobalExchangeInput, training: bool = False):
         x, g, index = self._prepare(inputs, training)
+        if node_ops._needs_grad(x, g):
+            from .differentiable import _AddFunction
+            return _AddFunction.apply(x, g, 0.5, 0.5)
         return node_ops.gathered_add(x, g, index, scale=0.5)
 
 
@@ -115,6 +121,9 @@ class GraphGlobalGRUExchange(GraphGlobalExchange):
 
     def call(self, inputs: GraphGlobalExchangeInput, training: bool = False):
         x, g, index = self._prepare(inputs, training)
+        if node_ops._needs_grad(x, g, self._gru_kernel.value, self._gru_recurrent_kernel.value, self._gru_bias.value):
+            from .differentiable import gru_cell
+            return gru_cell(g, x, self._gru_kernel.value, self._gru_recurrent_kernel.value, self._gru_bias.value)
         return node_ops.gru_cell(g, index, x, self._gru_kernel.value, self._gru_recurrent_kernel.value,
                                  self._gru_bias.value)
 
@@ -139,6 +148,9 @@ class GraphGlobalMLPExchange(GraphGlobalExchange):
         x, g, index = self._prepare(inputs, training)
         H = self._hidden_dim
         W1, W2 = self._mlp.kernels[0].value, self._mlp.kernels[1].value
+        if node_ops._needs_grad(x, g, W1, W2):
+            # tf.concat([per_node_graph_representations, node_embeddings], -1) -> MLP (graph_global_exchange.py:176-181)
+            return self._mlp(torch.cat([g, x], dim=-1), training, self.dropout_state)
         # first layer split by rows: [g || x] W1 = g W1[:H] + x W1[H:]; the graph half once per graph (or per node when the
         # training-time dropout already materialised per-node copies: index is None then)
         gp = node_ops.dense(g, W1[:H])

@@ -7,7 +7,7 @@ import torch
 
 from ... import _ffi
 from ...runtime import PreparedBatch, stream_ptr
-from ..node_ops import require_no_grad
+from ..node_ops import _needs_grad
 from .message_passing import (MessagePassing, MessagePassingInput, Variable, _last_dim,
                               register_message_passing_implementation)
 
@@ -45,7 +45,10 @@ class RGAT(MessagePassing):
     def call(self, inputs: MessagePassingInput, training: bool = False,
              prepared: Optional[PreparedBatch] = None):
         h, prepared = self._device_inputs(inputs, prepared)
-        require_no_grad(type(self).__name__, h, *[v.value for v in self.variables])
+        if _needs_grad(h, *[v.value for v in self.variables]):
+            # training: the reference's literal op order with per-op backward kernels (layers/differentiable.py)
+            from ..differentiable import rgat_forward
+            return rgat_forward(self, h, prepared)
         if prepared.num_edge_types != len(self._edge_type_to_message_computation_layer):
             raise ValueError("number of adjacency lists differs from the number the layer was built for")
         if self._hidden_dim % self._num_heads:
