@@ -135,6 +135,15 @@ TFGNN_API int tfgnn_b200_rgcn_fwd(tfgnn_batch_t* batch, const float* h, int32_t 
                         int32_t H, uint32_t flags, int32_t aggregation, int32_t activation,
                         int32_t path, float* out, void* stream);
 
+/* RGCN layer followed by LayerNormalization (gnn.py:299-321 with use_inter_layer_layernorm, e.g. QM9_RGCN.json): when the
+ * layer takes the fused kernel with one N pass (H <= 256) the normalisation runs in the kernel's epilogue - every epilogue
+ * thread owns a whole output row in TMEM, so mean / variance are two more sweeps over its columns and the [V,H] round trip
+ * through HBM of a separate LayerNorm pass disappears.  Otherwise the stand-alone kernel is applied in place: the result is
+ * the same either way.  out = LayerNorm(rgcn(h)); the un-normalised layer output is not produced. */
+TFGNN_API int tfgnn_b200_rgcn_ln_fwd(tfgnn_batch_t* batch, const float* h, int32_t D, const float* const* W, int32_t H,
+                                     uint32_t flags, int32_t aggregation, int32_t activation, int32_t path,
+                                     const float* ln_gamma, const float* ln_beta, float ln_epsilon, float* out, void* stream);
+
 /* Layer + all-gather in ONE kernel over peer memory (SURVEY.md §8e case 2: one graph partitioned by target range over the
  * GPUs of an NVSwitch domain, tfgnn_b200_prepare_sharded).  Same computation as tfgnn_b200_rgcn_fwd on the shard, but the
  * epilogue of the fused kernel stores every finished 128-row output tile into the caller's own table AND into the peers'

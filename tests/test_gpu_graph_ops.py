@@ -811,3 +811,58 @@ def test_per_batch_path_makes_no_synchronising_allocations_after_warmup():
     ms = (time.perf_counter() - t0) / n * 1e3
     print(f"prepare + layer on a PPI-sized batch: {ms:.3f} ms per batch")
     assert ms < 2.0, ms
+
+
+@pytest.mark.parametrize("V,H,act,agg", [(50_000, 128, "leaky_relu", "sum"),     # QM9_RGCN.json shape: pairs, 391 tiles
+                                         (3000, 256, "relu", "mean"),            # small batch: LayerNorm keeps one CTA per tile
+                                         (20_000, 64, "tanh", "sqrt_n"),
+                                         (6000, 320, "relu", "sum")])            # H > 256: composed fallback, same result
+def test_layernorm_fused_into_the_layer_kernel(V, H, act, agg):
+    """tfgnn_b200_rgcn_ln_fwd: LayerNorm in the fused kernel's epilogue (gnn.py:299-321 with use_inter_layer_layernorm) against
+    the float64 oracle and against the composed layer + LayerNorm kernels."""
+    _need_gpu()
+    from tf2_gnn_b200.layers import MessagePassingInput, get_message_passing_class, node_ops
+    rng = np.random.default_rng(V + H)
+    D, L = H, 3
+    adjs = [rng.integers(0, V, size=(3 * V, 2)).astype(np.int32) for _ in range(L)]
+    cls = get_message_passing_class("rgcn")
+    p = cls.get_default_hyperparameters()
+    p.update(hidden_dim=H, message_activation_function=act, aggregation_function=agg)
+    w = mo.make_weights("rgcn", p, D, L, rng)
+    layer = cls(p)
+    layer.build(MessagePassingInput((None, D), tuple((None, 2) for _ in range(L))))
+    layer.set_weights_from_oracle_dict(w)
+    h = rng.uniform(-1, 1, (V, D)).astype(np.float32)
+    g = rng.uniform(0.5, 1.5, H).astype(np.float32)
+    b = rng.uniform(-0.2, 0.2, H).astype(np.float32)
+    inp = MessagePassingInput(torch.from_numpy(h).cuda(), tuple(torch.from_numpy(a).cuda() for a in adjs))
+    gt, bt = torch.from_numpy(g).cuda(), torch.from_numpy(b).cuda()
+    fused = layer.call_with_layernorm(inp, gt, bt, 1e-3)
+    mp = layer(inp)
+    composed = node_ops.layer_norm(mp, gt, bt, 1e-3)
+    ref = mo.layer_norm(mp.cpu().numpy().astype(np.float64), g.astype(np.float64), b.astype(np.float64))   # teacher forced
+    close(fused.cpu().numpy(), ref, what="fused LayerNorm epilogue")
+    close(composed.cpu().numpy(), ref, what="composed LayerNorm")
+    fused2 = layer.call_with_layernorm(inp, gt, bt, 1e-3)
+    assert torch.equal(fused, fused2)
+
+
+def test_gnn_stack_uses_the_fused_layernorm_and_matches_the_unfused_stack():
+    """QM9_RGCN-shaped stack (LayerNorm after every layer): the call that does not ask for all representations takes the fused
+    layer + LayerNorm kernel; its result must agree with the call that does (which composes the ops) to fp32 rounding."""
+    _need_gpu()
+    from tf2_gnn_b200.layers import GNN, GNNInput
+    rng = np.random.default_rng(5)
+    V, F, L = 20_000, 15, 3
+    params = GNN.get_default_hyperparameters("rgcn")
+    params.update(hidden_dim=128, num_layers=4, use_inter_layer_layernorm=True, residual_every_num_layers=2,
+                  dense_every_num_layers=32, global_exchange_every_num_layers=10000,
+                  message_activation_function="leaky_relu")
+    gnn = GNN(params)
+    inp = GNNInput(torch.from_numpy(rng.uniform(-1, 1, (V, F)).astype(np.float32)).cuda(),
+                   tuple(torch.from_numpy(rng.integers(0, V, size=(60_000, 2)).astype(np.int32)).cuda() for _ in range(L)),
+                   torch.zeros(V, dtype=torch.int32).cuda(), 1)
+    fused = gnn(inp, training=False)
+    composed, reps = gnn(inp, training=False, return_all_representations=True)
+    assert all(r is not None for r in reps)
+    close(fused.cpu().numpy(), composed.cpu().numpy().astype(np.float64), tol=5e-6, what="fused vs composed stack")

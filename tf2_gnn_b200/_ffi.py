@@ -39,7 +39,7 @@ EXPORTED_SYMBOLS = (
     "tfgnn_b200_dense_bwd", "tfgnn_b200_layer_norm_bwd", "tfgnn_b200_dropout", "tfgnn_b200_axpby",
     "tfgnn_b200_activation_bwd", "tfgnn_b200_row_scale", "tfgnn_b200_mul_add", "tfgnn_b200_segment_max_bwd",
     "tfgnn_b200_rgcn_fwd_allgather", "tfgnn_b200_softmax_apply", "tfgnn_b200_head_scale", "tfgnn_b200_head_dot",
-    "tfgnn_b200_gru_gate_bwd",
+    "tfgnn_b200_gru_gate_bwd", "tfgnn_b200_rgcn_ln_fwd",
 )
 
 _PP = POINTER(c_void_p)
@@ -132,6 +132,8 @@ def lib() -> ctypes.CDLL:
     L.tfgnn_b200_head_dot.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p]
     L.tfgnn_b200_gru_gate_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
                                           c_void_p, c_void_p]
+    L.tfgnn_b200_rgcn_ln_fwd.argtypes = [c_void_p, c_void_p, c_int32, _PP, c_int32, c_uint32, c_int32, c_int32, c_int32,
+                                         c_void_p, c_void_p, c_float, c_void_p, c_void_p]
     L.tfgnn_b200_set_l2_persist_mb.argtypes = [c_int32]
     L.tfgnn_b200_release_device_state.argtypes = []
     for name in EXPORTED_SYMBOLS:

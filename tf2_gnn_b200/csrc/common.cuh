@@ -136,6 +136,10 @@ struct tfgnn_batch {
   float* peer_out[TFGNN_MAX_PEERS] = {};
   int n_peer_out = 0;
   float* mc_out = nullptr;   // multicast mapping of all replicas (one multimem.st reaches every GPU)
+  // tfgnn_b200_rgcn_ln_fwd: LayerNormalization parameters for the fused epilogue (set for the duration of that call only)
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  float ln_eps = 0.f;
   cudaEvent_t ev_switch = nullptr;
   // internal fork/join streams of the gather || node-GEMM pipeline (created lazily)
   static constexpr int kPipeBufs = 3;

@@ -565,6 +565,53 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       const float inv_rn = row_ok ? 1.0f / fu_row_norm(p.epi, row) : 1.0f;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kFuAccStride;
       float* stage = epi_stage + (size_t)(warp - 8) * 32 * kFuEpiPitch;
+      // one 16-column chunk of this thread's row: TMEM -> registers, row norm / bias / activation
+      auto load_chunk = [&](int col, float* v) {
+        uint32_t mv[16], cv[16];
+        ptx::tmem_ld_x16_nowait(taddr + col, mv);
+        ptx::tmem_ld_x16_nowait(taddr + corr_off + col, cv);
+        ptx::tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(mv[j]) + __uint_as_float(cv[j]);
+        // uniform branches hoisted out of the element loops (predicated-off code still costs issue slots
+        // and instruction-cache space: the epilogue was ~48 us per 128x256 tile before)
+        if (p.epi.row_norm) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] *= inv_rn;
+        }
+        if (p.epi.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(p.epi.bias + n0 + col);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 bb = __ldg(bp + j);
+            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+          }
+        }
+        apply_act_vec<16>(v, p.epi.act);
+      };
+      // Fused LayerNormalization (gnn.py:317-321 right after the message-passing layer): this thread owns one whole row
+      // (single N pass), so mean and variance are two extra sweeps over its TMEM columns - no [V,H] round trip through HBM.
+      // Two-pass variance (mean first) like Keras: no cancellation.
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      const bool ln = p.epi.ln_gamma != nullptr;
+      if (ln && !(p.debug_skip & 4)) {
+        float s1 = 0.f;
+        for (int col = 0; col < p.block_n; col += 16) {
+          float v[16];
+          load_chunk(col, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s1 += v[j];
+        }
+        ln_mean = s1 / (float)p.block_n;
+        float s2 = 0.f;
+        for (int col = 0; col < p.block_n; col += 16) {
+          float v[16];
+          load_chunk(col, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { const float dlt = v[j] - ln_mean; s2 = fmaf(dlt, dlt, s2); }
+        }
+        ln_rstd = rsqrtf(s2 / (float)p.block_n + p.epi.ln_eps);
+      }
       // 32 output columns per store phase, in two TMEM round trips of 16 columns (the 72-register budget of this 896-thread
       // CTA does not hold 64 accumulator words at once): every row is then written in 128-byte contiguous pieces - full
       // lines for the local stores, and twice the NVLink payload per packet for the peer / multicast stores of the fused
@@ -572,28 +619,20 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
       for (int c0 = 0; c0 < ((p.debug_skip & 4) ? 0 : p.block_n); c0 += 32) {
         const int ncols = (p.block_n - c0) < 32 ? (p.block_n - c0) : 32;   // 32, or a 16-column tail
         for (int half = 0; half * 16 < ncols; ++half) {
-          uint32_t mv[16], cv[16];
-          ptx::tmem_ld_x16_nowait(taddr + c0 + half * 16, mv);
-          ptx::tmem_ld_x16_nowait(taddr + corr_off + c0 + half * 16, cv);
-          ptx::tmem_wait_ld();
           float v[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(mv[j]) + __uint_as_float(cv[j]);
-          // uniform branches hoisted out of the element loops (predicated-off code still costs issue slots
-          // and instruction-cache space: the epilogue was ~48 us per 128x256 tile before)
-          if (p.epi.row_norm) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] *= inv_rn;
-          }
-          if (p.epi.bias) {
-            const float4* bp = reinterpret_cast<const float4*>(p.epi.bias + n0 + c0 + half * 16);
+          load_chunk(c0 + half * 16, v);
+          if (ln) {
+            const float4* gp = reinterpret_cast<const float4*>(p.epi.ln_gamma + n0 + c0 + half * 16);
+            const float4* bp = reinterpret_cast<const float4*>(p.epi.ln_beta + n0 + c0 + half * 16);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float4 bb = __ldg(bp + j);
-              v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+              const float4 gg = __ldg(gp + j), bb = __ldg(bp + j);
+              v[4 * j] = (v[4 * j] - ln_mean) * ln_rstd * gg.x + bb.x;
+              v[4 * j + 1] = (v[4 * j + 1] - ln_mean) * ln_rstd * gg.y + bb.y;
+              v[4 * j + 2] = (v[4 * j + 2] - ln_mean) * ln_rstd * gg.z + bb.z;
+              v[4 * j + 3] = (v[4 * j + 3] - ln_mean) * ln_rstd * gg.w + bb.w;
             }
           }
-          apply_act_vec<16>(v, p.epi.act);
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
             *reinterpret_cast<float4*>(stage + lane * kFuEpiPitch + half * 16 + j) =
@@ -788,7 +827,10 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   const int split_env = split_str ? atoi(split_str) : 1;
   const char* pair_str = getenv("TFGNN_B200_FUSED_PAIR");
   const int pair_env = pair_str ? atoi(pair_str) : 1;
-  const bool split = split_env != 0 && pair_env != 2 && 2 * p.m_tiles <= sms && H % 32 == 0 && H / 2 >= 16 && H / 2 <= 256;
+  const bool want_ln = epi.ln_gamma != nullptr;   // the row statistics need the whole row in one CTA: single N pass, no split
+  TFGNN_REQUIRE(!want_ln || H <= 256, "fused LayerNorm needs hidden_dim <= 256 (one N pass)");
+  const bool split = !want_ln && split_env != 0 && pair_env != 2 && 2 * p.m_tiles <= sms && H % 32 == 0 && H / 2 >= 16 &&
+                     H / 2 <= 256;
   p.n_tiles = split ? 1 : (H > 256 ? 2 : 1);            // N passes (per CTA)
   p.block_n = split ? H / 2 : H / p.n_tiles;
   p.num_slots = fused_num_slots(L, H, split);

@@ -14,6 +14,11 @@ struct GemmEpilogue {
   int row_norm = 0;  // 0 none, 1 mean (/max(cnt,1)), 2 sqrt_n (/sqrt(max(cnt,1)))
   // FiLM-style chained contractions (variants.cu): val = (accumulate ? C_old : 0) + (mul ? mul[row, n] * acc : acc);
   // row-norm / bias / activation are applied only when `finalize` (the last contraction of the chain).
+  // LayerNormalization over the finished row, fused into the fused RGCN kernel's epilogue (gnn.py:317-321 directly after the
+  // message-passing layer): y = (x - mean) * rsqrt(var + eps) * gamma + beta over all N columns; single N pass only
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  float ln_eps = 0.f;
   const float* mul = nullptr;   // [M, ldm] elementwise multiplier (gamma), rows/cols aligned with C
   int ldm = 0;
   int accumulate = 0;

@@ -174,13 +174,15 @@ class GNN:
 
     def call(self, inputs: GNNInput, training: bool = False, return_all_representations: bool = False):
         """gnn.py:234-274."""
-        cur, all_reps = self._internal_call(inputs, training)
+        cur, all_reps = self._internal_call(inputs, training, want_all_representations=return_all_representations)
         if return_all_representations:
             return cur, all_reps
         return cur
 
-    def _internal_call(self, inputs: GNNInput, training: bool = False):
-        """gnn.py:276-329."""
+    def _internal_call(self, inputs: GNNInput, training: bool = False, want_all_representations: bool = True):
+        """gnn.py:276-329.  When the caller does not ask for the per-layer representations (the reference's traced function
+        always returns them and `call` drops them), a message-passing layer that is directly followed by its LayerNorm runs
+        both in one fused call (`call_with_layernorm`) and the tuple holds None for that layer."""
         feats = to_device_f32(inputs.node_features)
         adjs = tuple(to_device_adj(a, feats.device) for a in inputs.adjacency_lists)
         if all(a is b for a, b in zip(adjs, inputs.adjacency_lists)):
@@ -205,13 +207,23 @@ class GNN:
                 if layer_idx > 0:
                     cur = node_ops.residual_average(cur, last)
                 last = tmp
-            cur = mp_layer(MessagePassingInput(cur, adjs), training=training, prepared=prepared)
-            all_reps.append(cur)
-            if layer_idx and layer_idx % self._global_exchange_every_num_layers == 0:   # gnn.py:307-315
-                cur = self._global_exchange_layers[str(layer_idx)](
-                    GraphGlobalExchangeInput(cur, n2g, int(inputs.num_graphs)), training=training)
-            if self._use_inter_layer_layernorm:
-                cur = self._inter_layer_layernorms[layer_idx](cur)
+            has_exchange = bool(layer_idx and layer_idx % self._global_exchange_every_num_layers == 0)
+            if (self._use_inter_layer_layernorm and not has_exchange and not want_all_representations
+                    and hasattr(mp_layer, "call_with_layernorm")):
+                ln = self._inter_layer_layernorms[layer_idx]
+                if not mp_layer.built:
+                    mp_layer.build(MessagePassingInput(tuple(cur.shape), tuple(tuple(a.shape) for a in adjs)))
+                cur = mp_layer.call_with_layernorm(MessagePassingInput(cur, adjs), ln.gamma.value, ln.beta.value, ln.epsilon,
+                                                   prepared=prepared)     # gnn.py:299-304 + 317-321 in one call
+                all_reps.append(None)
+            else:
+                cur = mp_layer(MessagePassingInput(cur, adjs), training=training, prepared=prepared)
+                all_reps.append(cur)
+                if has_exchange:                                                         # gnn.py:307-315
+                    cur = self._global_exchange_layers[str(layer_idx)](
+                        GraphGlobalExchangeInput(cur, n2g, int(inputs.num_graphs)), training=training)
+                if self._use_inter_layer_layernorm:
+                    cur = self._inter_layer_layernorms[layer_idx](cur)
             if layer_idx % self._dense_every_num_layers == 0:
                 cur = self._dense_layers[str(layer_idx)](cur)
         return cur, tuple(all_reps)

@@ -135,6 +135,34 @@ class GNN_Edge_MLP(MessagePassing):
             _ffi.PATH[self._path], out.data_ptr(), stream_ptr()))
         return out
 
+    def call_with_layernorm(self, inputs: MessagePassingInput, gamma: torch.Tensor, beta: torch.Tensor, epsilon: float,
+                            prepared: Optional[PreparedBatch] = None) -> torch.Tensor:
+        """LayerNormalization(layer(inputs)) — the pair gnn.py:299-321 runs with use_inter_layer_layernorm — as ONE call
+        (tfgnn_b200_rgcn_ln_fwd): for RGCN-style layers the normalisation happens in the fused kernel's epilogue.  Other
+        configurations, and any call that records gradients, compose the two ops."""
+        h, prepared = self._device_inputs(inputs, prepared)
+        ptrs, tensors = self._mlp_weight_ptrs()
+        fusable = (int(self._num_edge_MLP_hidden_layers) == 0 and not self._use_target_state_as_input
+                   and type(self)._compute_is_plain_edge_mlp())
+        if not fusable or (torch.is_grad_enabled() and (h.requires_grad or gamma.requires_grad or beta.requires_grad
+                                                        or any(t.requires_grad for t in tensors))):
+            from ..node_ops import layer_norm
+            return layer_norm(self.call(MessagePassingInput(h, inputs.adjacency_lists), prepared=prepared), gamma, beta,
+                              epsilon)
+        self._check_types(prepared)
+        out = torch.empty((prepared.num_nodes, self._hidden_dim), dtype=torch.float32, device=h.device)
+        _ffi.check(_ffi.lib().tfgnn_b200_rgcn_ln_fwd(
+            prepared.handle, h.data_ptr(), int(h.shape[1]), ptrs, self._hidden_dim, self._flags(), self._aggregation_fn.code,
+            self._activation_fn.code, _ffi.PATH[self._path], gamma.data_ptr(), beta.data_ptr(), float(epsilon),
+            out.data_ptr(), stream_ptr()))
+        return out
+
+    @classmethod
+    def _compute_is_plain_edge_mlp(cls) -> bool:
+        """True for the classes whose call() is the plain edge-MLP layer (GNN_Edge_MLP, RGCN); GGNN / RGIN / GNN-FiLM add
+        their own node update or modulation and take the composed path."""
+        return cls.__name__ in ("GNN_Edge_MLP", "RGCN")
+
     def call_allgather(self, node_embeddings: torch.Tensor, prepared: PreparedBatch, replica_ptrs, own_rank: int,
                        multicast_ptr: int = 0) -> None:
         """The layer on a target-range shard with the all-gather fused into the kernel's epilogue
