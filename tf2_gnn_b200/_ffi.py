@@ -11,7 +11,9 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_uint32, c_void_p
 from typing import Optional, Sequence
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libtfgnn_b200.so")
+# TFGNN_B200_LIB: an alternative build of the same in-tree library (kernel A/B experiments, tools/build_variants.sh)
+_LIB_PATH = os.environ.get("TFGNN_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc",
+                                                             "libtfgnn_b200.so")
 _lib: Optional[ctypes.CDLL] = None
 
 # enums of include/tfgnn_b200.h
