@@ -866,3 +866,31 @@ def test_gnn_stack_uses_the_fused_layernorm_and_matches_the_unfused_stack():
     composed, reps = gnn(inp, training=False, return_all_representations=True)
     assert all(r is not None for r in reps)
     close(fused.cpu().numpy(), composed.cpu().numpy().astype(np.float64), tol=5e-6, what="fused vs composed stack")
+
+
+def test_ops_without_a_backward_raise_instead_of_truncating_gradients():
+    """an op without a backward must not hand back a tensor without grad_fn.  What is left without one:
+    the generic user-plugin MessagePassing.call and the forward-only graph primitives."""
+    _need_gpu()
+    from tf2_gnn_b200.layers import MessagePassing, MessagePassingInput, node_ops
+
+    class PassSourceStates(MessagePassing):
+        def __init__(self):
+            super().__init__(super().get_default_hyperparameters())
+
+        def _message_function(self, edge_source_states, edge_target_states, num_incoming_to_node_per_message,
+                              edge_type_idx, training):
+            return edge_source_states
+
+    rng = np.random.default_rng(0)
+    V = 40
+    adjs = (torch.from_numpy(rng.integers(0, V, size=(90, 2)).astype(np.int32)).cuda(),)
+    h = torch.rand((V, 7), device="cuda", requires_grad=True)
+    layer = PassSourceStates()
+    with pytest.raises(NotImplementedError):
+        layer(MessagePassingInput(h, adjs))
+    with torch.no_grad():
+        assert tuple(layer(MessagePassingInput(h, adjs)).shape) == (V, 7)
+    ptr = node_ops.graph_offsets(torch.zeros(V, dtype=torch.int32, device="cuda"), 1)
+    with pytest.raises(NotImplementedError):
+        node_ops.segment_softmax(torch.rand((V, 2), device="cuda", requires_grad=True), ptr)
