@@ -612,12 +612,10 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         }
         ln_rstd = rsqrtf(s2 / (float)p.block_n + p.epi.ln_eps);
       }
-      // 32 output columns per store phase, in two TMEM round trips of 16 columns (the 72-register budget of this 896-thread
-      // CTA does not hold 64 accumulator words at once): every row is then written in 128-byte contiguous pieces - full
-      // lines for the local stores, and twice the NVLink payload per packet for the peer / multicast stores of the fused
-      // all-gather (N = 8, round 2: 64-byte pieces moved 400 GB/s per GPU against NCCL's 612).
-      for (int c0 = 0; c0 < ((p.debug_skip & 4) ? 0 : p.block_n); c0 += 32) {
-        const int ncols = (p.block_n - c0) < 32 ? (p.block_n - c0) : 32;   // 32, or a 16-column tail
+      // 16 output columns per TMEM round trip and store phase.  (32-column phases - 128-byte row pieces - were tried for the
+      // NVLink stores of the fused all-gather: 1-2 % slower on one GPU in a same-box A/B, gpurun r2l, so not kept.)
+      for (int c0 = 0; c0 < ((p.debug_skip & 4) ? 0 : p.block_n); c0 += 16) {
+        const int ncols = 16;
         for (int half = 0; half * 16 < ncols; ++half) {
           float v[16];
           load_chunk(c0 + half * 16, v);
@@ -680,8 +678,9 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
 #define TFGNN_FU_GATHER(QT, FULL)                                                                                      \
     gather_warp_main<NV, QT, FULL>(p, lane, gw, p.gather_q, my_bufs, unit0, unit_step, total_units, CTAS, (int)rank,     \
                                    ring_row0, slot_ready, slot_free, SPLIT ? 1 : 0, (int)srank, peer_slot_ready0)
+    // same-box A/B (gpurun r2l): the compile-time variant wins at D = 256 (4.56 vs 4.77 ms) but loses at D = 320, where the
+    // third column group is half empty (6.84 with the generic loop vs 6.95 with a <4, false> instantiation)
     if (p.gather_q == 4 && p.D == 128 * NV) TFGNN_FU_GATHER(4, true);
-    else if (p.gather_q == 4) TFGNN_FU_GATHER(4, false);       // e.g. D = 320: the third 16-byte column group is half empty
     else TFGNN_FU_GATHER(0, false);
 #undef TFGNN_FU_GATHER
   }
