@@ -499,8 +499,12 @@ def test_gnn_stack_parity(kind, extra):
     close_as_fp32(out.cpu().numpy(), ref, ref32)
     for a, b, c in zip(all_reps, ref_all, ref32_all):
         close_as_fp32(a.cpu().numpy(), b, c)
+    # Without per-layer representations the stack may fuse LayerNorm into the layer kernel's epilogue: a
+    # different rounding order, so the same parity bar (not bit equality) against the oracle; repeated calls
+    # of the same path are bit-identical.
     out2 = gnn(inp)
-    assert np.array_equal(out2.cpu().numpy(), out.cpu().numpy())
+    close_as_fp32(out2.cpu().numpy(), ref, ref32)
+    assert np.array_equal(gnn(inp).cpu().numpy(), out2.cpu().numpy())
 
 
 @pytest.mark.parametrize("kind,extra", [("rgcn", {}), ("gnn_film", dict(use_target_state_as_input=True)),
