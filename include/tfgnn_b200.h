@@ -376,9 +376,11 @@ TFGNN_API int tfgnn_b200_assemble_batch(const int64_t* node_offsets, const int64
  * Two things in this library outlive a call and are shared with the host framework's CUDA context:
  *   (1) the fused RGCN kernel keeps its hand-off ring and the packed weights resident in L2 with evict_last hints,
  *       which only bind inside a persisting-L2 carve-out.  The first fused launch on a device therefore saves the
- *       current cudaLimitPersistingL2CacheSize and raises it to `megabytes` (default 72; never lowered if the host
- *       already reserves more).  set_l2_persist_mb(0) opts out (results identical, ~4 GB more HBM traffic per cfg2
- *       layer); -1 returns to the default / TFGNN_B200_L2_PERSIST_MB.
+ *       current cudaLimitPersistingL2CacheSize and raises it (never lowers it).  Default size: what the launch
+ *       keeps resident (ring + packed weights + 4 MB), at least 72 MB, at most the device maximum, raised again by
+ *       a later launch that needs more; set_l2_persist_mb(megabytes) fixes the size instead, set_l2_persist_mb(0)
+ *       opts out (results identical, ~4 GB more HBM traffic per cfg2 layer); -1 returns to the default /
+ *       TFGNN_B200_L2_PERSIST_MB.
  *   (2) a private stream-ordered memory pool (cudaMemPool) that caches the library's own buffers.
  * tfgnn_b200_release_device_state() restores the saved L2 limit on every device and trims the pool; the Python
  * shim registers it with atexit.

@@ -67,29 +67,32 @@ __device__ __forceinline__ float apply_act_t(float x) {
 // Activation of N register values with the switch hoisted OUT of the element loop: only the selected
 // case's (short) loop is ever fetched.  Inlining apply_act() per element put every libdevice expansion
 // (tanhf, expm1f, ...) N times into the epilogue: ~80 KB of straight-line SASS that thrashed the
-// instruction cache (measured: ~30 us per 128x128 output tile in the tcgen05 epilogue).
-template <int ACT, int N>
-__device__ __noinline__ void apply_act_vec_t(float* v) {
-#pragma unroll
-  for (int j = 0; j < N; ++j) v[j] = apply_act(v[j], ACT);
+// instruction cache (measured: ~30 us per 128x128 output tile in the tcgen05 epilogue).  The transcendental
+// cases therefore go through ONE out-of-line copy - which takes and returns VALUES: an out-of-line function
+// over `float*` (round 1) made the caller's array addressable, so every epilogue kept its chunk in LOCAL
+// memory (STL/LDL around each chunk, also on the relu path; 17-20 us per 128x256 tile in the fused kernel).
+static __device__ __noinline__ float4 apply_act_slow4(float4 x, int act) {
+  return make_float4(apply_act(x.x, act), apply_act(x.y, act), apply_act(x.z, act), apply_act(x.w, act));
 }
+static __device__ __noinline__ float apply_act_slow1(float x, int act) { return apply_act(x, act); }
 template <int N>
-__device__ __forceinline__ void apply_act_vec(float* v, int act) {
-  switch (act) {
-    case TFGNN_ACT_RELU:
+__device__ __forceinline__ void apply_act_vec(float (&v)[N], int act) {
+  if (act == TFGNN_ACT_NONE) return;
+  if (act == TFGNN_ACT_RELU) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = fmaxf(v[j], 0.0f);
-      break;
-    case TFGNN_ACT_LEAKY_RELU:
+    for (int j = 0; j < N; ++j) v[j] = fmaxf(v[j], 0.0f);
+  } else if (act == TFGNN_ACT_LEAKY_RELU) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = v[j] > 0.0f ? v[j] : kLeakyReluAlpha * v[j];
-      break;
-    case TFGNN_ACT_TANH: apply_act_vec_t<TFGNN_ACT_TANH, N>(v); break;
-    case TFGNN_ACT_ELU: apply_act_vec_t<TFGNN_ACT_ELU, N>(v); break;
-    case TFGNN_ACT_SELU: apply_act_vec_t<TFGNN_ACT_SELU, N>(v); break;
-    case TFGNN_ACT_GELU: apply_act_vec_t<TFGNN_ACT_GELU, N>(v); break;
-    case TFGNN_ACT_SIGMOID: apply_act_vec_t<TFGNN_ACT_SIGMOID, N>(v); break;
-    default: break;
+    for (int j = 0; j < N; ++j) v[j] = v[j] > 0.0f ? v[j] : kLeakyReluAlpha * v[j];
+  } else if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int j = 0; j < N; j += 4) {
+      const float4 r = apply_act_slow4(make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]), act);
+      v[j] = r.x; v[j + 1] = r.y; v[j + 2] = r.z; v[j + 3] = r.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) v[j] = apply_act_slow1(v[j], act);
   }
 }
 

@@ -20,8 +20,11 @@
 // shared memory left over by the GEMM pipeline (64 KB for 16 warps x 4 rows at D = 256), not by registers.
 #include <cuda.h>
 
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "gemm.cuh"
 #include "sm100_ptx.cuh"
@@ -66,8 +69,20 @@ struct FusedParams {
   float* C_peer[TFGNN_MAX_PEERS];
   int n_peer;
   float* C_mc;   // multicast mapping of all replicas (NVSwitch replicates one multimem.st), or null
+  uint32_t sleep_crit, sleep_long;   // nanosleep between barrier probes (0 = spin): K-loop waits / once-per-tile waits
+  int epi_direct;    // 1: epilogue stores straight from registers (each thread its row's 64 B pieces), 0: through the staging tile
+  int epi_helpers;   // 1: single accumulator and direct stores -> the splitter warps drain the upper half of the columns
+  long long* trace;   // debug (TFGNN_B200_FUSED_TRACE=file): kFuTraceSlots clock64 stamps per CTA, see fu_trace()
   GemmEpilogue epi;
 };
+
+// Debug timeline: slot 0 kernel entry, 1 set-up done, 2 exit, 3 / 4 globaltimer at entry / exit; 8+cc gather warp 0 finished call cc
+// (cc < 40); 48+2t / 49+2t first MMA / last commit of tile t (t < 16); 80+2t / 81+2t epilogue start / end of tile t;
+// 112+t TMA producer got the first slot of unit t.  SM-local clock64: comparable inside one CTA only.
+constexpr int kFuTraceSlots = 128;
+__device__ __forceinline__ void fu_trace(const FusedParams& p, int idx) {
+  if (p.trace) p.trace[(size_t)blockIdx.x * kFuTraceSlots + idx] = clock64();
+}
 
 __device__ __forceinline__ float fu_row_norm(const GemmEpilogue& e, long long row) {
   if (e.row_norm == 0) return 1.0f;
@@ -244,7 +259,7 @@ __device__ __forceinline__ void gather_warp_main(const FusedParams& p, int lane,
     crp_next = g.rp_of(cc + 2);
     const int slot = cc % kFuSlots;
     if (split) ptx::mbar_wait_cluster(&slot_free[slot], ((cc / kFuSlots) & 1) ^ 1);   // the peer's reads are done too
-    else ptx::mbar_wait(&slot_free[slot], ((cc / kFuSlots) & 1) ^ 1);
+    else ptx::mbar_wait_backoff(&slot_free[slot], ((cc / kFuSlots) & 1) ^ 1, p.sleep_long);
     float* dst = ring + ((size_t)ring_row0 + (size_t)slot * kFuBM + (size_t)row_off + (size_t)gw * kRowsPerWarp) * D + 4 * lane;
     int row = 0;
     int seg_begin = __shfl_sync(0xffffffffu, rp, 0);
@@ -287,6 +302,7 @@ __device__ __forceinline__ void gather_warp_main(const FusedParams& p, int lane,
     // generic-proxy global writes -> visible to the TMA (async proxy) reads of this CTA
     asm volatile("fence.proxy.async.global;" ::: "memory");
     __syncwarp();
+    if (lane == 0 && gw == 0 && cc < 40) fu_trace(p, 8 + cc);
     if (lane == 0) {
       if (split) {   // both CTAs of the cluster read the whole slot: tell the peer's TMA producer too
         ptx::mbar_arrive_cluster_release(ptx::mapa_shared(ptx::smem_u32(&slot_ready[slot]), (uint32_t)split_rank));
@@ -348,6 +364,12 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   const int kFuSlots = p.num_slots;
   const int kb_per_tile = p.L * p.kb_per_type;
 
+  if (threadIdx.x == 0 && p.trace) {
+    fu_trace(p, 0);
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.trace[(size_t)blockIdx.x * kFuTraceSlots + 3] = (long long)gt;
+  }
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_a);
     ptx::prefetch_tensormap(&map_b);
@@ -358,7 +380,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 4 * CTAS);  // one arrival per epilogue warp
+      ptx::mbar_init(&tmem_empty[a], (p.epi_helpers ? 8 : 4) * CTAS);  // one arrival per epilogue (+ helper) warp
     }
     for (int r = 0; r < kFuMaxSlots; ++r) {
       ptx::mbar_init(&slot_ready[r], kFuGatherWarps * (SPLIT ? 2 : 1));   // split: the peer's gather warps arrive too
@@ -384,16 +406,159 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
   __syncthreads();
   if (kClu == 2) ptx::cluster_sync_all();   // both halves of the pair's TMEM are allocated before the first MMA
   ptx::tc_fence_after_sync();
+  if (threadIdx.x == 0) fu_trace(p, 1);
   // the leader's barriers that collect arrivals from both CTAs (split[], tmem_empty[])
   const uint32_t split_remote0 = CTAS == 2 ? ptx::mapa_shared(ptx::smem_u32(&split[0]), 0) : 0u;
   const uint32_t tmem_empty_remote0 = CTAS == 2 ? ptx::mapa_shared(ptx::smem_u32(&tmem_empty[0]), 0) : 0u;
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t n_acc = p.block_n <= 128 ? 2 : 1;
-  const uint32_t corr_off = p.block_n <= 128 ? 128 : 256;
   // first ring row of this CTA (split-tile mode: of this CLUSTER, both CTAs fill and read the same slots)
   const int ring_row0 = (SPLIT ? blockIdx.x / 2 : blockIdx.x) * kFuSlots * kFuBM;
   const uint32_t peer_slot_ready0 = SPLIT ? ptx::mapa_shared(ptx::smem_u32(&slot_ready[0]), srank ^ 1u) : 0u;
   const uint32_t peer_slot_free0 = SPLIT ? ptx::mapa_shared(ptx::smem_u32(&slot_free[0]), srank ^ 1u) : 0u;
+
+  // ---- epilogue of one (tile, column range) ----
+  // Run by the epilogue warps and - when the tile has a single accumulator pair, so that the next tile's MMAs wait for the drain
+  // anyway - by the splitter warps as well ("helpers": the upper half of the columns; same TMEM lane quarters, warp & 3).
+  // Trace r2n (tools/fused_trace_summary.py): 17-20 us per 128x256 tile with 4 warps, a staging tile and the chunk in local
+  // memory, against 47 us of K loop, strictly serialised.
+  const uint32_t n_acc = p.block_n <= 128 ? 2 : 1;
+  const uint32_t corr_off = p.block_n <= 128 ? 128 : 256;
+  const bool helpers = p.epi_helpers != 0;
+  const int epi_half = ((p.block_n / 16 + 1) / 2) * 16;
+  auto epilogue_cols = [&](long long tp, uint32_t tile_count, int col_begin, int col_end, float* stage, bool traced) {
+    const int q = warp & 3;
+    const uint64_t pol_stream = ptx::policy_evict_first();
+    const long long m0 = ((tp / n_pass) * CTAS + rank) * kFuBM;
+    const int n0 = (int)(tp % n_pass) * p.block_n + (int)srank * p.block_n;
+    const uint32_t acc = tile_count % n_acc, acc_ph = (tile_count / n_acc) & 1;
+    ptx::mbar_wait_backoff(&tmem_full[acc], acc_ph, p.sleep_long);
+    ptx::tc_fence_after_sync();
+    if (traced && lane == 0 && tile_count < 16) fu_trace(p, 80 + 2 * (int)tile_count);
+    const long long row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.V;
+    const float inv_rn = row_ok ? 1.0f / fu_row_norm(p.epi, row) : 1.0f;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kFuAccStride;
+    // one 16-column chunk of this thread's row: TMEM -> registers, row norm / bias / activation (all indices compile-time:
+    // the chunk stays in registers)
+    auto load_chunk = [&](int col, float (&v)[16]) {
+      uint32_t mv[16], cv[16];
+      ptx::tmem_ld_x16_nowait(taddr + col, mv);
+      ptx::tmem_ld_x16_nowait(taddr + corr_off + col, cv);
+      ptx::tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(mv[j]) + __uint_as_float(cv[j]);
+      // uniform branches hoisted out of the element loops (predicated-off code still costs issue slots
+      // and instruction-cache space: the epilogue was ~48 us per 128x256 tile before)
+      if (p.epi.row_norm) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= inv_rn;
+      }
+      if (p.epi.bias) {
+        const float4* bp = reinterpret_cast<const float4*>(p.epi.bias + n0 + col);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 bb = __ldg(bp + j);
+          v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+        }
+      }
+      apply_act_vec<16>(v, p.epi.act);
+    };
+    // Fused LayerNormalization (gnn.py:317-321 right after the message-passing layer): this thread owns one whole row
+    // (single N pass, no helpers), so mean and variance are two extra sweeps over its TMEM columns - no [V,H] round trip
+    // through HBM.  Two-pass variance (mean first) like Keras: no cancellation.
+    float ln_mean = 0.f, ln_rstd = 1.f;
+    const bool ln = p.epi.ln_gamma != nullptr;
+    if (ln && !(p.debug_skip & 4)) {
+      float s1 = 0.f;
+      for (int col = 0; col < p.block_n; col += 16) {
+        float v[16];
+        load_chunk(col, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s1 += v[j];
+      }
+      ln_mean = s1 / (float)p.block_n;
+      float s2 = 0.f;
+      for (int col = 0; col < p.block_n; col += 16) {
+        float v[16];
+        load_chunk(col, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const float dlt = v[j] - ln_mean; s2 = fmaf(dlt, dlt, s2); }
+      }
+      ln_rstd = rsqrtf(s2 / (float)p.block_n + p.epi.ln_eps);
+    }
+    auto ln_affine = [&](int col, float (&v)[16]) {
+      const float4* gp = reinterpret_cast<const float4*>(p.epi.ln_gamma + n0 + col);
+      const float4* bp = reinterpret_cast<const float4*>(p.epi.ln_beta + n0 + col);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 gg = __ldg(gp + j), bb = __ldg(bp + j);
+        v[4 * j] = (v[4 * j] - ln_mean) * ln_rstd * gg.x + bb.x;
+        v[4 * j + 1] = (v[4 * j + 1] - ln_mean) * ln_rstd * gg.y + bb.y;
+        v[4 * j + 2] = (v[4 * j + 2] - ln_mean) * ln_rstd * gg.z + bb.z;
+        v[4 * j + 3] = (v[4 * j + 3] - ln_mean) * ln_rstd * gg.w + bb.w;
+      }
+    };
+    if (p.debug_skip & 4) col_end = col_begin;
+    if (p.epi_direct) {
+      // Straight from registers: each thread stores its own row's 64 B piece of the chunk (four 16 B stores; the L2 merges
+      // the pieces of a line before it is written back).  No staging tile, no warp barrier, a third of the instructions.
+      float* crow = p.C + row * p.ldc + n0;
+      for (int col = col_begin; col < col_end; col += 16) {
+        float v[16];
+        load_chunk(col, v);
+        if (ln) ln_affine(col, v);
+        if (row_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            ptx::st_f4_hint(crow + col + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]), pol_stream);
+        }
+      }
+    } else {
+      // Through a padded staging tile to 64 B row pieces, 8 rows per store instruction: the form the NVLink stores of the
+      // fused all-gather want.  (32-column phases - 128-byte row pieces - were tried for them: 1-2 % slower on one GPU in a
+      // same-box A/B, gpurun r2l, so not kept.)
+      for (int c0 = col_begin; c0 < col_end; c0 += 16) {
+        {
+          float v[16];
+          load_chunk(c0, v);
+          if (ln) ln_affine(c0, v);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4*>(stage + lane * kFuEpiPitch + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        __syncwarp();
+        const int rr = lane >> 2, cc = (lane & 3) * 4;
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+          const int r = r0 + rr;
+          const long long grow = m0 + q * 32 + r;
+          if (grow < p.V) {
+            const float4 val = *reinterpret_cast<const float4*>(stage + r * kFuEpiPitch + cc);
+            const long long off = grow * p.ldc + n0 + c0 + cc;
+            if (p.C_mc) {
+              // the all-gather of the sharded layer through the switch: ONE multimem.st, NVSwitch replicates the 16 bytes
+              // into every GPU's copy of the table (this GPU's included)
+              asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.C_mc + off), "f"(val.x),
+                           "f"(val.y), "f"(val.z), "f"(val.w)
+                           : "memory");
+            } else {
+              ptx::st_f4_hint(p.C + off, val, pol_stream);
+              // the all-gather of the sharded layer, tile by tile: the same 16 bytes go to every peer's copy of the table
+              // over NVLink (plain stores to P2P-mapped memory; the copies become the next layer's source table)
+              for (int pr = 0; pr < p.n_peer; ++pr) *reinterpret_cast<float4*>(p.C_peer[pr] + off) = val;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    ptx::tc_fence_before_sync();
+    __syncwarp();
+    if (traced && lane == 0 && tile_count < 16) fu_trace(p, 81 + 2 * (int)tile_count);
+    if (lane == 0) {
+      if (CTAS == 2 && rank != 0) ptx::mbar_arrive_cluster(tmem_empty_remote0 + acc * 8u);
+      else ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  };
 
   // N passes: main + correction accumulators need 2*block_n <= 512 TMEM columns, so H in (256, 512] is covered
   // in two passes of block_n = H/2 columns over the SAME gathered ring slots (the ring then holds all L types of
@@ -410,11 +575,12 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           const uint32_t sq = slot_it + l;
           const int slot = sq % kFuSlots;
           if (SPLIT) ptx::mbar_wait_cluster(&slot_ready[slot], (sq / kFuSlots) & 1);   // half of the rows come from the peer SM
-          else ptx::mbar_wait(&slot_ready[slot], (sq / kFuSlots) & 1);
+          else ptx::mbar_wait_backoff(&slot_ready[slot], (sq / kFuSlots) & 1, p.sleep_long);
+          if (l == 0 && pass == 0 && slot_it / p.L < 16) fu_trace(p, 112 + (int)(slot_it / p.L));
           for (int kb = 0; kb < p.kb_per_type; ++kb, ++it) {
             const int s = it % S;
             const uint32_t ph = (it / S) & 1;
-            ptx::mbar_wait(&empty[s], ph ^ 1);
+            ptx::mbar_wait_backoff(&empty[s], ph ^ 1, p.sleep_crit);
             uint8_t* st = smem + (size_t)s * stage_bytes;
             const bool skip_b = p.debug_skip & 8;   // timing experiment: no weight stream (results invalid)
             ptx::mbar_arrive_expect_tx(&full[s], kFuATileBytes + (skip_b ? 0 : 2 * b_tile_bytes));
@@ -437,17 +603,18 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     for (long long tp = unit0 * n_pass; rank == 0 && tp < total_units * n_pass;
          tp = (tp % n_pass == n_pass - 1) ? tp + (unit_step - 1) * n_pass + 1 : tp + 1, ++tile_count) {
       const uint32_t acc = tile_count % n_acc, acc_ph = (tile_count / n_acc) & 1;
-      ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+      ptx::mbar_wait_backoff(&tmem_empty[acc], acc_ph ^ 1, p.sleep_long);
       ptx::tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + acc * kFuAccStride;
       const uint32_t c_tmem = d_tmem + corr_off;
       for (int kb = 0; kb < kb_per_tile; ++kb, ++it) {
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
-        ptx::mbar_wait(&full[s], ph);
-        ptx::mbar_wait(&split[s], ph);   // pair: arrivals of both CTAs' splitter warps = both operand halves staged
+        ptx::mbar_wait_backoff(&full[s], ph, p.sleep_crit);
+        ptx::mbar_wait_backoff(&split[s], ph, p.sleep_crit);   // pair: arrivals of both CTAs' splitter warps = both operand halves staged
         ptx::tc_fence_after_sync();
         if (lane == 0) {
+          if (kb == 0 && tile_count < 16) fu_trace(p, 48 + 2 * (int)tile_count);
           const uint32_t st = ptx::smem_u32(smem + (size_t)s * stage_bytes);
           const uint64_t a_hi = ptx::umma_desc_k<kRowBytes>(st);
           const uint64_t a_lo = ptx::umma_desc_k<kRowBytes>(st + kFuATileBytes);
@@ -481,6 +648,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
             ptx::mma_commit(&empty[s]);
             if (kb == kb_per_tile - 1) ptx::mma_commit(&tmem_full[acc]);
           }
+          if (kb == kb_per_tile - 1 && tile_count < 16) fu_trace(p, 49 + 2 * (int)tile_count);
         }
         __syncwarp();
       }
@@ -490,7 +658,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int tid = threadIdx.x - 128;
     const bool raw_hi = (p.debug_skip & 32) || p.corr_bf16;   // the fp32 tile stays in place as the hi operand
     const bool pair = p.corr_bf16;
-    uint32_t it = 0, slot_base_it = 0;
+    uint32_t it = 0, slot_base_it = 0, tile_count = 0;
     for (long long unit = unit0; unit < total_units; unit += unit_step, slot_base_it += p.L) {
      for (int pass = 0; pass < n_pass; ++pass) {
       for (int l = 0; l < p.L; ++l) {
@@ -498,7 +666,7 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         for (int kb = 0; kb < p.kb_per_type; ++kb, ++it) {
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
-          ptx::mbar_wait(&full[s], ph);
+          ptx::mbar_wait_backoff(&full[s], ph, p.sleep_crit);
           if (kb == p.kb_per_type - 1 && pass == n_pass - 1) {
             // all TMA reads of the slot have landed: its lines are dead.  Discard them from L2 so that they are
             // never written back to HBM (the ring is pure on-chip hand-off), then hand the slot back.
@@ -546,129 +714,18 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
           }
         }
       }
+      // single accumulator: nothing to split until this tile is drained - drain the upper half of its columns
+      if (helpers) epilogue_cols(unit * n_pass + pass, tile_count, epi_half, p.block_n, nullptr, false);
+      ++tile_count;
      }
     }
   } else if (warp >= 8 && warp < kFuFirstGatherWarp) {
     // ================= epilogue (warps 8..11 -> TMEM lane quarters 0..3) =================
-    const int q = warp & 3;
     uint32_t tile_count = 0;
-    const uint64_t pol_stream = ptx::policy_evict_first();
+    const int col_end = helpers ? epi_half : p.block_n;
     for (long long tp = unit0 * n_pass; tp < total_units * n_pass;
-         tp = (tp % n_pass == n_pass - 1) ? tp + (unit_step - 1) * n_pass + 1 : tp + 1, ++tile_count) {
-      const long long m0 = ((tp / n_pass) * CTAS + rank) * kFuBM;
-      const int n0 = (int)(tp % n_pass) * p.block_n + (int)srank * p.block_n;
-      const uint32_t acc = tile_count % n_acc, acc_ph = (tile_count / n_acc) & 1;
-      ptx::mbar_wait(&tmem_full[acc], acc_ph);
-      ptx::tc_fence_after_sync();
-      const long long row = m0 + q * 32 + lane;
-      const bool row_ok = row < p.V;
-      const float inv_rn = row_ok ? 1.0f / fu_row_norm(p.epi, row) : 1.0f;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kFuAccStride;
-      float* stage = epi_stage + (size_t)(warp - 8) * 32 * kFuEpiPitch;
-      // one 16-column chunk of this thread's row: TMEM -> registers, row norm / bias / activation
-      auto load_chunk = [&](int col, float* v) {
-        uint32_t mv[16], cv[16];
-        ptx::tmem_ld_x16_nowait(taddr + col, mv);
-        ptx::tmem_ld_x16_nowait(taddr + corr_off + col, cv);
-        ptx::tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(mv[j]) + __uint_as_float(cv[j]);
-        // uniform branches hoisted out of the element loops (predicated-off code still costs issue slots
-        // and instruction-cache space: the epilogue was ~48 us per 128x256 tile before)
-        if (p.epi.row_norm) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] *= inv_rn;
-        }
-        if (p.epi.bias) {
-          const float4* bp = reinterpret_cast<const float4*>(p.epi.bias + n0 + col);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 bb = __ldg(bp + j);
-            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
-          }
-        }
-        apply_act_vec<16>(v, p.epi.act);
-      };
-      // Fused LayerNormalization (gnn.py:317-321 right after the message-passing layer): this thread owns one whole row
-      // (single N pass), so mean and variance are two extra sweeps over its TMEM columns - no [V,H] round trip through HBM.
-      // Two-pass variance (mean first) like Keras: no cancellation.
-      float ln_mean = 0.f, ln_rstd = 1.f;
-      const bool ln = p.epi.ln_gamma != nullptr;
-      if (ln && !(p.debug_skip & 4)) {
-        float s1 = 0.f;
-        for (int col = 0; col < p.block_n; col += 16) {
-          float v[16];
-          load_chunk(col, v);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) s1 += v[j];
-        }
-        ln_mean = s1 / (float)p.block_n;
-        float s2 = 0.f;
-        for (int col = 0; col < p.block_n; col += 16) {
-          float v[16];
-          load_chunk(col, v);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) { const float dlt = v[j] - ln_mean; s2 = fmaf(dlt, dlt, s2); }
-        }
-        ln_rstd = rsqrtf(s2 / (float)p.block_n + p.epi.ln_eps);
-      }
-      // 16 output columns per TMEM round trip and store phase.  (32-column phases - 128-byte row pieces - were tried for the
-      // NVLink stores of the fused all-gather: 1-2 % slower on one GPU in a same-box A/B, gpurun r2l, so not kept.)
-      for (int c0 = 0; c0 < ((p.debug_skip & 4) ? 0 : p.block_n); c0 += 16) {
-        const int ncols = 16;
-        for (int half = 0; half * 16 < ncols; ++half) {
-          float v[16];
-          load_chunk(c0 + half * 16, v);
-          if (ln) {
-            const float4* gp = reinterpret_cast<const float4*>(p.epi.ln_gamma + n0 + c0 + half * 16);
-            const float4* bp = reinterpret_cast<const float4*>(p.epi.ln_beta + n0 + c0 + half * 16);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 gg = __ldg(gp + j), bb = __ldg(bp + j);
-              v[4 * j] = (v[4 * j] - ln_mean) * ln_rstd * gg.x + bb.x;
-              v[4 * j + 1] = (v[4 * j + 1] - ln_mean) * ln_rstd * gg.y + bb.y;
-              v[4 * j + 2] = (v[4 * j + 2] - ln_mean) * ln_rstd * gg.z + bb.z;
-              v[4 * j + 3] = (v[4 * j + 3] - ln_mean) * ln_rstd * gg.w + bb.w;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            *reinterpret_cast<float4*>(stage + lane * kFuEpiPitch + half * 16 + j) =
-                make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-        __syncwarp();
-        const int f4_per_row = ncols / 4;
-        const int rows_per_it = 32 / f4_per_row;
-        const int rr = lane / f4_per_row, cc = (lane % f4_per_row) * 4;
-        for (int r0 = 0; r0 < 32; r0 += rows_per_it) {
-          const int r = r0 + rr;
-          const long long grow = m0 + q * 32 + r;
-          if (grow < p.V) {
-            const float4 val = *reinterpret_cast<const float4*>(stage + r * kFuEpiPitch + cc);
-            const long long off = grow * p.ldc + n0 + c0 + cc;
-            if (p.C_mc) {
-              // the all-gather of the sharded layer through the switch: ONE multimem.st, NVSwitch replicates the 16 bytes
-              // into every GPU's copy of the table (this GPU's included)
-              asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.C_mc + off), "f"(val.x),
-                           "f"(val.y), "f"(val.z), "f"(val.w)
-                           : "memory");
-            } else {
-              ptx::st_f4_hint(p.C + off, val, pol_stream);
-              // the all-gather of the sharded layer, tile by tile: the same 16 bytes go to every peer's copy of the table
-              // over NVLink (plain stores to P2P-mapped memory; the copies become the next layer's source table)
-              for (int pr = 0; pr < p.n_peer; ++pr) *reinterpret_cast<float4*>(p.C_peer[pr] + off) = val;
-            }
-          }
-        }
-        __syncwarp();
-      }
-      ptx::tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) {
-        if (CTAS == 2 && rank != 0) ptx::mbar_arrive_cluster(tmem_empty_remote0 + acc * 8u);
-        else ptx::mbar_arrive(&tmem_empty[acc]);
-      }
-    }
+         tp = (tp % n_pass == n_pass - 1) ? tp + (unit_step - 1) * n_pass + 1 : tp + 1, ++tile_count)
+      epilogue_cols(tp, tile_count, 0, col_end, epi_stage + (size_t)(warp - 8) * 32 * kFuEpiPitch, warp == 8);
   } else if (warp >= kFuFirstGatherWarp) {
     // ================= gather warps =================
     const int gw = warp - kFuFirstGatherWarp;
@@ -681,12 +738,21 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // same-box A/B (gpurun r2l): the compile-time variant wins at D = 256 (4.56 vs 4.77 ms) but loses at D = 320, where the
     // third column group is half empty (6.84 with the generic loop vs 6.95 with a <4, false> instantiation)
     if (p.gather_q == 4 && p.D == 128 * NV) TFGNN_FU_GATHER(4, true);
+#ifdef TFGNN_FU_GATHER_Q4_ALL
+    else if (p.gather_q == 4) TFGNN_FU_GATHER(4, false);
+#endif
     else TFGNN_FU_GATHER(0, false);
 #undef TFGNN_FU_GATHER
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0 && p.trace) {
+    fu_trace(p, 2);
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.trace[(size_t)blockIdx.x * kFuTraceSlots + 4] = (long long)gt;
+  }
   if (kClu == 2) ptx::cluster_sync_all();   // the leader's MMAs read the peer's shared memory / remote arrivals: leave together
   if (warp == 1) {
     ptx::tc_fence_after_sync();
@@ -740,32 +806,42 @@ int set_l2_persist_mb(int mb) {
   return 0;
 }
 
-static int ensure_l2_persist_carveout() {
+static size_t g_l2_effective[64] = {};   // persisting bytes in effect on the device since the last ensure()
+
+// need_bytes: what this launch wants resident (its ring + packed weights).  Default policy: max(72 MB, need + 4 MB), clamped
+// to the device maximum and only ever RAISED (H = 320 at 1M nodes: the ring is 97 MB, and with a 72 MB carve-out 2.7 GB of
+// it per layer were written back to HBM, ncu r2n); an explicit size (API / environment) is taken as is.
+static int ensure_l2_persist_carveout(size_t need_bytes) {
   int dev = 0;
   TFGNN_CUDA(cudaGetDevice(&dev));
   if (dev < 0 || dev >= 64) return 0;
   std::lock_guard<std::mutex> lock(g_l2_mu);
-  if (g_l2_set[dev]) return 0;
-  g_l2_set[dev] = true;
   long long want_mb = g_l2_want_mb;
   if (want_mb < 0) {
-    const char* e = getenv("TFGNN_B200_L2_PERSIST_MB");
-    want_mb = e ? atoi(e) : 72;
+    static const int env_mb = [] { const char* e = getenv("TFGNN_B200_L2_PERSIST_MB"); return e ? atoi(e) : -1; }();
+    want_mb = env_mb;
   }
-  if (want_mb <= 0) return 0;
+  size_t want = want_mb >= 0 ? (size_t)want_mb << 20 : std::max((size_t)72 << 20, need_bytes + ((size_t)4 << 20));
+  if (g_l2_set[dev] && (want_mb >= 0 || g_l2_effective[dev] >= want)) return 0;
+  g_l2_set[dev] = true;
+  if (want == 0) return 0;
   int max_persist = 0;
   if (cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev) != cudaSuccess || max_persist <= 0) {
     cudaGetLastError();
     return 0;
   }
-  size_t want = (size_t)want_mb << 20;
   if (want > (size_t)max_persist) want = (size_t)max_persist;
   size_t cur = 0;
   if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) != cudaSuccess) { cudaGetLastError(); return 0; }
-  if (cur >= want) return 0;                  // the host already reserves at least as much: leave it alone
-  g_l2_saved[dev] = cur + 1;                  // +1: "saved" marker (0 = nothing to restore)
+  g_l2_effective[dev] = cur;
+  if (cur >= want) {                          // the host (or an earlier launch) already reserves at least as much
+    if (want == (size_t)max_persist) g_l2_effective[dev] = (size_t)-1;   // nothing more to get: stop asking
+    return 0;
+  }
+  if (!g_l2_saved[dev]) g_l2_saved[dev] = cur + 1;   // +1: "saved" marker (0 = nothing to restore)
   cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);
   cudaGetLastError();
+  g_l2_effective[dev] = want == (size_t)max_persist ? (size_t)-1 : want;
   return 0;
 }
 
@@ -778,6 +854,7 @@ void restore_l2_persist_carveout() {
     if (cudaSetDevice(d) == cudaSuccess) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, g_l2_saved[d] - 1);
     g_l2_saved[d] = 0;
     g_l2_set[d] = false;
+    g_l2_effective[d] = 0;
   }
   cudaSetDevice(cur_dev);
   cudaGetLastError();
@@ -828,8 +905,12 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   const int pair_env = pair_str ? atoi(pair_str) : 1;
   const bool want_ln = epi.ln_gamma != nullptr;   // the row statistics need the whole row in one CTA: single N pass, no split
   TFGNN_REQUIRE(!want_ln || H <= 256, "fused LayerNorm needs hidden_dim <= 256 (one N pass)");
-  const bool split = !want_ln && split_env != 0 && pair_env != 2 && 2 * p.m_tiles <= sms && H % 32 == 0 && H / 2 >= 16 &&
-                     H / 2 <= 256;
+  // Large batches at H > 256 (TFGNN_B200_FUSED_SPLIT=2, experiment): the split form covers all H columns in ONE pass (each CTA
+  // holds main + correction accumulators of H/2 columns) and its clusters share their ring slots, so the ring is half as large
+  // (H = 320 at 1M nodes: 47 MB instead of 97 MB, which no longer fits the 79 MB persisting carve-out and spilled ~4 GB per layer).
+  const bool split_big = split_env == 2 && H > 256;
+  const bool split = !want_ln && split_env != 0 && pair_env != 2 && (2 * p.m_tiles <= sms || split_big) && H % 32 == 0 &&
+                     H / 2 >= 16 && H / 2 <= 256;
   p.n_tiles = split ? 1 : (H > 256 ? 2 : 1);            // N passes (per CTA)
   p.block_n = split ? H / 2 : H / p.n_tiles;
   p.num_slots = fused_num_slots(L, H, split);
@@ -837,11 +918,23 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   // 16 floats, H=320 6.47 vs 6.61 ms (half as many barrier round trips per byte; 2 stages of 64 KB still fit)
   static const int bk_env = [] { const char* e = getenv("TFGNN_B200_FUSED_BK"); return e ? atoi(e) : 32; }();
   p.C = out; p.ldc = ldo; p.epi = epi;
+  // Epilogue form.  TFGNN_B200_EPI_DIRECT=0: always through the staging tile; TFGNN_B200_EPI_HELPERS=0: epilogue warps only
+  // (read per call: the tests sweep both).
+  {
+    const char* ed = getenv("TFGNN_B200_EPI_DIRECT");
+    const char* eh = getenv("TFGNN_B200_EPI_HELPERS");
+    p.epi_direct = (p.n_peer == 0 && p.C_mc == nullptr && !(ed && atoi(ed) == 0)) ? 1 : 0;
+    p.epi_helpers = (p.epi_direct && p.block_n > 128 && !want_ln && !(eh && atoi(eh) == 0)) ? 1 : 0;
+    const char* sc = getenv("TFGNN_B200_SLEEP_CRIT");
+    const char* sl = getenv("TFGNN_B200_SLEEP_LONG");
+    p.sleep_crit = sc ? (uint32_t)atoi(sc) : 0u;
+    p.sleep_long = sl ? (uint32_t)atoi(sl) : 0u;
+  }
   // CTA pairs (cta_group::2) when there is at least one 128-target tile per SM; tiny batches keep single CTAs
   // TFGNN_B200_FUSED_PAIR: 0 = never, 1 = default rule, 2 = whenever there are two tiles (tests); read per call
   const bool pair_ok = !split && (p.block_n / 2) % 8 == 0 && sms >= 2;
   const int ctas = (pair_ok && ((pair_env == 1 && p.m_tiles >= sms) || (pair_env == 2 && p.m_tiles >= 2))) ? 2 : 1;
-  int grid = split ? (int)(2 * p.m_tiles) : (int)(p.m_tiles < sms ? p.m_tiles : sms);
+  int grid = split ? (int)(2 * p.m_tiles < (sms & ~1) ? 2 * p.m_tiles : (sms & ~1)) : (int)(p.m_tiles < sms ? p.m_tiles : sms);
   if (ctas == 2) grid &= ~1;
   // shared memory: S pipeline stages + epilogue staging + Q row slots for each of the 16 gather warps.
   // Q = 4 rolling copies per warp saturate HBM in isolation (tools/gather_ceiling.cu); the pipeline gets what is left.
@@ -908,7 +1001,8 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   // L2 set-aside for the evict_last (persisting) lines: the ring + the packed weights.  Without a carve-out
   // the evict_last hint is advisory only and the ring gets written back to HBM (measured: +4 GB/layer).
   {
-    const int rc_l2 = ensure_l2_persist_carveout();
+    const int rc_l2 = ensure_l2_persist_carveout((size_t)grid * p.num_slots * kFuBM * D * sizeof(float) +
+                                                 (size_t)2 * H * L * D * sizeof(float));
     if (rc_l2) return rc_l2;
   }
   static std::once_flag attr_once;
@@ -926,6 +1020,11 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
 #undef TFGNN_FU_SET
   });
   TFGNN_CUDA(attr_err);
+  p.trace = nullptr;
+  if (const char* tr = getenv("TFGNN_B200_FUSED_TRACE"); tr && *tr) {
+    TFGNN_CUDA(cudaMalloc(&p.trace, (size_t)grid * kFuTraceSlots * sizeof(long long)));
+    TFGNN_CUDA(cudaMemset(p.trace, 0, (size_t)grid * kFuTraceSlots * sizeof(long long)));
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kFuThreads);
@@ -959,6 +1058,18 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   }
 #undef TFGNN_FU_LAUNCH
   TFGNN_LAUNCH_CHECK();
+  if (p.trace) {   // debug only: synchronous dump of the LAST launch's stamps (one binary file, grid x kFuTraceSlots int64)
+    std::vector<long long> host((size_t)grid * kFuTraceSlots);
+    TFGNN_CUDA(cudaStreamSynchronize(st));
+    TFGNN_CUDA(cudaMemcpy(host.data(), p.trace, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.trace);
+    if (FILE* f = fopen(getenv("TFGNN_B200_FUSED_TRACE"), "wb")) {
+      const long long hdr[4] = {grid, kFuTraceSlots, split ? 1 : 0, ctas};
+      fwrite(hdr, sizeof(long long), 4, f);
+      fwrite(host.data(), sizeof(long long), host.size(), f);
+      fclose(f);
+    }
+  }
   return 0;
 }
 

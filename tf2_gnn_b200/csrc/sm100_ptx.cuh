@@ -27,6 +27,8 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// (The suspend-time-hint form of try_wait compiles to the SAME SYNCS.PHASECHK.TRANS64.TRYWAIT as the plain one on sm_100a -
+// checked in the SASS - so it is not used.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done;
@@ -39,6 +41,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
   } while (!done);
+}
+// Same, with `ns` nanoseconds of nanosleep between probes (ns == 0: plain spin).  A waiting warp re-issues YIELD / TRYWAIT /
+// BRA every 15-50 cycles: in the fused kernel the waiting roles (TMA, MMA, splitters, epilogue) issued 30 % of ALL warp
+// instructions (ncu source page, gpurun r2n: 418 M probe triples per launch at H = 320), on the same schedulers as the gather
+// warps.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  const uint32_t addr = smem_u32(bar);
+  for (;;) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (ns) asm volatile("nanosleep.u32 %0;" ::"r"(ns));
+  }
 }
 
 // ---- proxy fences ----------------------------------------------------------------------------
