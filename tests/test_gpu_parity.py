@@ -397,11 +397,16 @@ def test_activations(act):
     run_case("rgcn", p, 200, 32, 2, adjs)
 
 
-def test_ggnn_parity():
+@pytest.mark.parametrize("fused_gru", ["1", "0"])
+@pytest.mark.parametrize("V,H", [(700, 128), (1000, 96), (257, 32), (300, 40)])
+def test_ggnn_parity(V, H, fused_gru, monkeypatch):
+    """GGNN layer (ggnn.py:68-89).  fused_gru=1: the GRU update is ONE tcgen05 contraction over [agg | h] with the gate math
+    in its epilogue (hidden_dim % 32 == 0; 40 falls back); 0: two GEMMs + the gate kernel.  Same oracle, same bar."""
     _need_gpu()
+    monkeypatch.setenv("TFGNN_B200_GGNN_FUSED_GRU", fused_gru)
     rng = np.random.default_rng(4)
-    V, H, L = 700, 128, 5
-    adjs = random_graph(rng, V, L, 2100, self_loops=True)
+    L = 5
+    adjs = random_graph(rng, V, L, 3 * V, self_loops=True)
     p = mo.default_hyperparameters("ggnn")
     p["hidden_dim"] = H
     run_case("ggnn", p, V, H, L, adjs)

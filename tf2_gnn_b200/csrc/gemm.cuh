@@ -38,6 +38,13 @@ int launch_pack_weights_tc_table(const PtrTable& W, int L, int D, int H, int cor
 int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int ldc, long long M, int N,
                    int K, const GemmEpilogue& epi, cudaStream_t st);
 
+// GGNN's GRU update as one contraction over [agg | h] with the gate math in the epilogue (gemm_tc.cu)
+bool gemm_tc_gru_supported(long long V, int H, const float* agg, int lda, const float* h, int ldh, const float* out, int ldo);
+size_t gemm_tc_gru_packed_bytes(int H);
+int launch_gemm_tc_gru(const float* agg, int lda, const float* h, int ldh, const float* gru_kernel,
+                       const float* gru_recurrent_kernel, const float* gru_bias, float* packed, float* out, int ldo,
+                       long long V, int H, cudaStream_t st);
+
 // Fused RGCN-style layer (fused_rgcn.cu): gather -> segment-sum -> 3xTF32 tcgen05 -> epilogue in one kernel.
 bool fused_rgcn_supported(long long V, int L, int D, int H, const float* h, const float* out, int ldo);
 size_t fused_rgcn_ring_bytes(int D, int L, int H);

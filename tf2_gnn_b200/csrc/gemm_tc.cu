@@ -45,6 +45,14 @@ struct TcParams {
   int prefetch_a;  // 1: L2-prefetch the A tile of this CTA's NEXT output tile while the current one is loaded
   float* C;
   int ldc;
+  // K blocks [0, kb_split) come from map_a, the rest from map_a2 (A = [A1 | A2] without materialising the concatenation)
+  int kb_split;
+  // GRU mode (launch_gemm_tc_gru): the N tile of 128 columns holds the pre-activations [z | r | x_h | h_h] of 32 hidden units;
+  // the epilogue applies the Keras GRUCell gate math (reset_after) and writes the 32 new states of each row.
+  int gru;
+  const float* gru_h;   // previous state rows [M, gru_ldh]
+  int gru_ldh;
+  const float* gru_bias;   // [N] in the tile layout: b0_z + b1_z | b0_r + b1_r | b0_h | b1_h per 32 units
   GemmEpilogue epi;
 };
 
@@ -60,8 +68,8 @@ __device__ __forceinline__ float tc_row_norm(const GemmEpilogue& e, long long ro
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-               const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+               const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.num_stages;
@@ -80,6 +88,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_a);
+    ptx::prefetch_tensormap(&map_a2);
     ptx::prefetch_tensormap(&map_b);
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(&full[s], 1);
@@ -118,10 +127,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // The pipeline holds only 3 stages of 50-64 KB, so its k-block rate is (stages / TMA latency): ~1 us per k-block
             // when A comes from HBM under load.  The next tile's A lines are requested into L2 now, ~10 k-blocks early.
             const long long nt = tile + gridDim.x;
-            if (nt < p.total_tiles && (nt / p.n_tiles) != (tile / p.n_tiles))
+            if (nt < p.total_tiles && (nt / p.n_tiles) != (tile / p.n_tiles) && kb < p.kb_split)
               ptx::tma_prefetch_2d(&map_a, kb * kTcBK, (int)((nt / p.n_tiles) * kTcBM));
           }
-          ptx::tma_load_2d(st, &map_a, &full[s], kb * kTcBK, m0);
+          if (kb < p.kb_split) ptx::tma_load_2d(st, &map_a, &full[s], kb * kTcBK, m0);
+          else ptx::tma_load_2d(st, &map_a2, &full[s], (kb - p.kb_split) * kTcBK, m0);
           ptx::tma_load_2d(st + 2 * kTcATileBytes, &map_b, &full[s], kb * kTcBK, n0);
           ptx::tma_load_2d(st + 2 * kTcATileBytes + b_tile_bytes, &map_b, &full[s], kb * kTcBK, p.N + n0);
         }
@@ -229,6 +239,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool chained = p.epi.mul != nullptr || p.epi.accumulate || !p.epi.finalize;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTcAccStride;
       float* stage = epi_stage + (size_t)(warp - 6) * 32 * kTcEpiPitch;
+      if (p.gru) {
+        // Keras GRUCell, reset_after (ggnn.py:84-87) on the 32 hidden units of this tile, 8 at a time, straight from TMEM:
+        //   z = sigmoid(acc_z + bz), r = sigmoid(acc_r + br), hh = tanh(acc_x + bx + r * (acc_h + bh)), h' = z h + (1 - z) hh
+        // (acc_z / acc_r already hold agg K + h U: one contraction over K = [agg | h]); each thread stores its row's 32 B pieces.
+        const int u0 = (int)(tile % p.n_tiles) * 32;
+        const float* hrow = p.gru_h + row * p.gru_ldh + u0;
+        float* orow = p.C + row * p.ldc + u0;
+        for (int g = 0; g < 32; g += 8) {
+          uint32_t m[4][8], c[4][8];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            ptx::tmem_ld_x8_nowait(taddr + 32 * t + g, m[t]);
+            ptx::tmem_ld_x8_nowait(taddr + corr_off + 32 * t + g, c[t]);
+          }
+          ptx::tmem_wait_ld();
+          float pre[4][8];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const float4* bp = reinterpret_cast<const float4*>(p.gru_bias + n0 + 32 * t + g);
+            const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pre[t][j] = (__uint_as_float(m[t][j]) + __uint_as_float(c[t][j])) + bb[j];
+          }
+          if (row_ok) {
+            const float4 h0 = __ldg(reinterpret_cast<const float4*>(hrow + g));
+            const float4 h1 = __ldg(reinterpret_cast<const float4*>(hrow + g + 4));
+            const float hp[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float z = 1.0f / (1.0f + expf(-pre[0][j]));
+              const float r = 1.0f / (1.0f + expf(-pre[1][j]));
+              const float hh = tanhf(pre[2][j] + r * pre[3][j]);
+              o[j] = z * hp[j] + (1.0f - z) * hh;
+            }
+            *reinterpret_cast<float4*>(orow + g) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(orow + g + 4) = make_float4(o[4], o[5], o[6], o[7]);
+          }
+        }
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(&tmem_empty[acc]);
+        continue;
+      }
       for (int c0 = 0; c0 < p.block_n; c0 += 32) {
         const int ncols = min(32, p.block_n - c0);     // 32 or 16
         // TMEM -> registers (row = lane), epilogue math, -> smem staging tile [32 rows][ncols]
@@ -381,6 +435,37 @@ __global__ void pack_weights_tc_table_kernel(PtrTable W, int L, int D, int H, in
   else out[total + idx] = ptx::tf32_hi(x - h);
 }
 
+// GRU weights in the tile layout of the gate epilogue: output column n = 128 t + 32 gate + j belongs to hidden unit
+// u = 32 t + j; rows k < H of the [2H, 4H] operand multiply the aggregated messages (GRUCell.kernel [H, 3H], gate order
+// z | r | h as in Keras), rows k >= H the previous state (recurrent_kernel): gate 2 ("x_h") has no recurrent part, gate 3
+// ("h_h") no input part.  Written directly in the packed K-major hi / lo form; the bias vector in the same column order.
+__global__ void pack_gru_weights_kernel(const float* __restrict__ Kx, const float* __restrict__ Uh,
+                                        const float* __restrict__ bias, int H, int Kp, float* __restrict__ out,
+                                        float* __restrict__ bias_out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = 4 * H;
+  const long long total = (long long)N * Kp;
+  if (idx >= total) return;
+  const int k = (int)(idx % Kp);
+  const int n = (int)(idx / Kp);
+  const int t = n / 128, gate = (n % 128) / 32, u = 32 * t + (n % 32);
+  float x = 0.f;
+  if (k < H) {
+    if (gate < 3) x = __ldg(Kx + (long long)k * 3 * H + gate * H + u);
+  } else if (k < 2 * H) {
+    const int gsrc = gate == 3 ? 2 : gate;
+    if (gate != 2) x = __ldg(Uh + (long long)(k - H) * 3 * H + gsrc * H + u);
+  }
+  const float h = ptx::tf32_hi(x);
+  out[idx] = h;
+  out[total + idx] = ptx::tf32_hi(x - h);
+  if (k == 0) {
+    const float* b0 = bias;           // input bias  [3H]
+    const float* b1 = bias + 3 * H;   // recurrent bias [3H]
+    bias_out[n] = gate == 0 ? b0[u] + b1[u] : gate == 1 ? b0[H + u] + b1[H + u] : gate == 2 ? b0[2 * H + u] : b1[2 * H + u];
+  }
+}
+
 // ---- host side -------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -451,8 +536,16 @@ int launch_pack_weights_tc(const float* B, int ldb, int K, int N, float* packed,
   return 0;
 }
 
-int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int ldc, long long M, int N, int K,
-                   const GemmEpilogue& epi, cudaStream_t st) {
+struct TcExtra {             // optional second A operand / GRU epilogue (launch_gemm_tc_gru)
+  const float* A2 = nullptr;
+  int lda2 = 0, K1 = 0;      // A = [A1 (K1 columns) | A2 (K - K1 columns)]
+  const float* gru_h = nullptr;
+  int gru_ldh = 0;
+  const float* gru_bias = nullptr;
+};
+
+static int launch_gemm_tc_impl(const float* A, int lda, const float* packedB, float* C, int ldc, long long M, int N, int K,
+                               const GemmEpilogue& epi, const TcExtra& ex, cudaStream_t st) {
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) {
     set_error(TFGNN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
@@ -461,7 +554,7 @@ int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int 
   const int Kp = round_up(K, kTcBK);
   TcParams p{};
   p.M = M; p.N = N; p.K = K;
-  p.block_n = pick_block_n(N);
+  p.block_n = ex.gru_h ? 128 : pick_block_n(N);
   p.n_tiles = N / p.block_n;
   p.m_tiles = (M + kTcBM - 1) / kTcBM;
   p.total_tiles = p.m_tiles * p.n_tiles;
@@ -477,10 +570,15 @@ int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int 
     p.prefetch_a = e ? (atoi(e) != 0) : 1;
   }
   p.C = C; p.ldc = ldc; p.epi = epi;
+  const int K1 = ex.A2 ? ex.K1 : K;
+  p.kb_split = ex.A2 ? K1 / kTcBK : p.num_k_blocks;
+  p.gru = ex.gru_h ? 1 : 0;
+  if (p.gru) p.corr_bf16 = 0;   // pack_gru_weights_kernel writes the two-MMA (tf32 lo) correction operand
+  p.gru_h = ex.gru_h; p.gru_ldh = ex.gru_ldh; p.gru_bias = ex.gru_bias;
 
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_a2, map_b;
   {
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    cuuint64_t dims[2] = {(cuuint64_t)K1, (cuuint64_t)M};
     cuuint64_t strides[1] = {(cuuint64_t)lda * sizeof(float)};
     cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)kTcBM};
     cuuint32_t estr[2] = {1, 1};
@@ -489,6 +587,20 @@ int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int 
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
       set_error(TFGNN_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed with code " + std::to_string((int)r));
+      return TFGNN_ERR_CUDA;
+    }
+  }
+  map_a2 = map_a;
+  if (ex.A2) {
+    cuuint64_t dims[2] = {(cuuint64_t)(K - K1), (cuuint64_t)M};
+    cuuint64_t strides[1] = {(cuuint64_t)ex.lda2 * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)kTcBK, (cuuint32_t)kTcBM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&map_a2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ex.A2), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error(TFGNN_ERR_CUDA, "cuTensorMapEncodeTiled(A2) failed with code " + std::to_string((int)r));
       return TFGNN_ERR_CUDA;
     }
   }
@@ -516,9 +628,38 @@ int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int 
   TFGNN_CUDA(cudaGetDevice(&dev));
   TFGNN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
-  gemm_tc_kernel<<<grid, kTcThreads, smem_bytes, st>>>(map_a, map_b, p);
+  gemm_tc_kernel<<<grid, kTcThreads, smem_bytes, st>>>(map_a, map_a2, map_b, p);
   TFGNN_LAUNCH_CHECK();
   return 0;
+}
+
+int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int ldc, long long M, int N, int K,
+                   const GemmEpilogue& epi, cudaStream_t st) {
+  return launch_gemm_tc_impl(A, lda, packedB, C, ldc, M, N, K, epi, TcExtra{}, st);
+}
+
+// The whole GRU update of GGNN as ONE contraction with a gate epilogue (ggnn.py:84-87):
+//   [agg | h] [2H] x W_gru [2H, 4H]  ->  per hidden unit z, r, x_h, h_h pre-activations  ->  h' = z h + (1 - z) tanh(x_h + r h_h)
+// instead of two [V,H]x[H,3H] GEMMs writing gx / gh (2 x 768 MB at cfg4), and a gate kernel reading them back.
+bool gemm_tc_gru_supported(long long V, int H, const float* agg, int lda, const float* h, int ldh, const float* out, int ldo) {
+  if (H % 32 != 0 || H < 32) return false;
+  if ((reinterpret_cast<uintptr_t>(h) & 15) || ldh % 4 != 0) return false;
+  return gemm_tc_supported(V, 4 * H, 2 * H, agg, lda, out, ldo);
+}
+size_t gemm_tc_gru_packed_bytes(int H) { return gemm_tc_packed_bytes(4 * H, 2 * H) + (size_t)4 * H * sizeof(float); }
+int launch_gemm_tc_gru(const float* agg, int lda, const float* h, int ldh, const float* gru_kernel,
+                       const float* gru_recurrent_kernel, const float* gru_bias, float* packed, float* out, int ldo,
+                       long long V, int H, cudaStream_t st) {
+  const int N = 4 * H, K = 2 * H;
+  const long long total = (long long)N * K;   // K is a multiple of 32 already
+  float* bias_tiles = packed + 2 * total;
+  pack_gru_weights_kernel<<<ceil_div(total, 256), 256, 0, st>>>(gru_kernel, gru_recurrent_kernel, gru_bias, H, K, packed,
+                                                               bias_tiles);
+  TFGNN_LAUNCH_CHECK();
+  TcExtra ex;
+  ex.A2 = h; ex.lda2 = ldh; ex.K1 = H;
+  ex.gru_h = h; ex.gru_ldh = ldh; ex.gru_bias = bias_tiles;
+  return launch_gemm_tc_impl(agg, lda, packed, out, ldo, V, N, K, GemmEpilogue{}, ex, st);
 }
 
 }  // namespace tfgnn

@@ -195,6 +195,12 @@ __device__ __forceinline__ void tmem_ld_x16_nowait(uint32_t taddr, uint32_t* r) 
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x8_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors ---------------------------------------------------------------------------

@@ -42,13 +42,28 @@ extern "C" int tfgnn_b200_ggnn_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
   if (rc) return rc;
   rc = batch_scratch(b, 8, (size_t)V * H * sizeof(float), &agg);
   if (rc) return rc;
-  rc = batch_scratch(b, 9, (size_t)V * 3 * H * sizeof(float), &gx);
-  if (rc) return rc;
-  rc = batch_scratch(b, 10, (size_t)V * 3 * H * sizeof(float), &gh);
-  if (rc) return rc;
   // ggnn.py:68-89: aggregation of the messages, no activation (act_before is ignored too).
   rc = edge_mlp_core(b, h, D, mlp_weights, num_hidden_layers, H, flags & ~TFGNN_FLAG_ACT_BEFORE_AGGREGATION,
                      aggregation, TFGNN_ACT_NONE, path, (float*)agg, H, st);
+  if (rc) return rc;
+  {
+    // The GRU update as ONE tcgen05 contraction over [agg | h] with the gate math in its epilogue: no [V,3H] tables.
+    // TFGNN_B200_GGNN_FUSED_GRU=0 keeps the two GEMMs + gate kernel (read per call: the tests compare the two).
+    const char* e = getenv("TFGNN_B200_GGNN_FUSED_GRU");
+    const bool want = !(e && atoi(e) == 0) &&
+                      (path == TFGNN_PATH_AUTO || path == TFGNN_PATH_SORTED_TC || path == TFGNN_PATH_FUSED_TC);
+    const float* h_tgt0 = h + (size_t)b->tgt_off * D;
+    if (want && gemm_tc_gru_supported(V, H, (const float*)agg, H, h_tgt0, D, out, H)) {
+      void* packed = nullptr;
+      rc = batch_scratch(b, 6, gemm_tc_gru_packed_bytes(H), &packed);
+      if (rc) return rc;
+      return launch_gemm_tc_gru((const float*)agg, H, h_tgt0, D, gru_kernel, gru_recurrent_kernel, gru_bias, (float*)packed,
+                                out, H, V, H, st);
+    }
+  }
+  rc = batch_scratch(b, 9, (size_t)V * 3 * H * sizeof(float), &gx);
+  if (rc) return rc;
+  rc = batch_scratch(b, 10, (size_t)V * 3 * H * sizeof(float), &gh);
   if (rc) return rc;
   GemmEpilogue ex, eh;
   ex.bias = gru_bias;
