@@ -442,10 +442,15 @@ def test_film_parity(monkeypatch, att, use_target, act_before, agg):
     run_case("gnn_film", p, V, D, L, adjs)
 
 
+@pytest.mark.parametrize("fused_scores", ["1", "0"])
 @pytest.mark.parametrize("V,D,H,K,L,E", [(5, 3, 12, 3, 3, 3), (400, 64, 64, 4, 3, 3000), (300, 32, 36, 3, 2, 2000),
-                                         (1000, 128, 128, 4, 3, 8000)])
-def test_rgat_parity(V, D, H, K, L, E):
+                                         (1000, 128, 128, 4, 3, 8000), (700, 64, 256, 8, 2, 5000),
+                                         (600, 32, 64, 2, 5, 4000)])
+def test_rgat_parity(V, D, H, K, L, E, fused_scores, monkeypatch):
+    """fused_scores=1: the attention score halves come out of the projection GEMM's epilogue where the tile layout allows
+    it (per-head dim % 16 == 0: (64,4), (128,4), (256,8), (64,2)); 0: the separate score kernel.  Same oracle, same bar."""
     _need_gpu()
+    monkeypatch.setenv("TFGNN_B200_RGAT_FUSED_SCORES", fused_scores)
     rng = np.random.default_rng(V + H)
     adjs = random_graph(rng, V, L, E, hub=V > 100, dups=True)
     p = mo.default_hyperparameters("rgat")

@@ -23,6 +23,13 @@ struct GemmEpilogue {
   int ldm = 0;
   int accumulate = 0;
   int finalize = 1;
+  // RGAT (tcgen05 GEMM only): while the projected row P[v, l*H + k*d + i] passes through the epilogue, its per-head attention
+  // score halves s_src[v,l,k] = a_l[k,:d] . P_l[v,k,:], s_tgt[v,l,k] = a_l[k,d:] . P_l[v,k,:] (rgat.py:111-121) are written as
+  // well: no second pass over P.  Needs d % 16 == 0 and N tiles that hold whole heads (gemm_tc_scores_supported).
+  float* score_src = nullptr;   // [M, L*K]
+  float* score_tgt = nullptr;
+  PtrTable score_att{};         // a_l [K, 2d] per type
+  int score_H = 0, score_K = 0, score_d = 0;
 };
 
 // fp32 SIMT GEMM, any shape / alignment (universal fallback).  C[M,N] = epi(A[M,K] B[K,N]).
@@ -33,6 +40,7 @@ int launch_gemm_simt(const float* A, int lda, const float* B, int ldb, float* C,
 // gemm_tc_supported(); B is given K-major-packed by pack_weights_tc (see gemm_tc.cu).
 bool gemm_tc_supported(long long M, int N, int K, const float* A, int lda, const float* C, int ldc);
 size_t gemm_tc_packed_bytes(int N, int K);
+bool gemm_tc_scores_supported(int N, int H, int d);   // RGAT scores in the epilogue of an [M, N = L*H] projection
 int launch_pack_weights_tc(const float* B, int ldb, int K, int N, float* packed, cudaStream_t st);
 int launch_pack_weights_tc_table(const PtrTable& W, int L, int D, int H, int corr_bf16, float* packed, cudaStream_t st);
 int launch_gemm_tc(const float* A, int lda, const float* packedB, float* C, int ldc, long long M, int N,

@@ -239,6 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const bool chained = p.epi.mul != nullptr || p.epi.accumulate || !p.epi.finalize;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTcAccStride;
       float* stage = epi_stage + (size_t)(warp - 6) * 32 * kTcEpiPitch;
+      float sc_s = 0.f, sc_t = 0.f;   // RGAT score accumulators of the current head (epi.score_src)
       if (p.gru) {
         // Keras GRUCell, reset_after (ggnn.py:84-87) on the 32 hidden units of this tile, 8 at a time, straight from TMEM:
         //   z = sigmoid(acc_z + bz), r = sigmoid(acc_r + br), hh = tanh(acc_x + bx + r * (acc_h + bh)), h' = z h + (1 - z) hh
@@ -320,6 +321,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   }
                 }
                 apply_act_vec<16>(v, p.epi.act);
+              }
+              if (p.epi.score_src) {
+                // RGAT: this row's attention score halves, head by head, while its 16-column chunks pass (a chunk lies inside
+                // one head: d % 16 == 0; a tile holds whole heads, visited in ascending column order)
+                const int col = n0 + c0 + half * 16;
+                const int l = col / p.epi.score_H, ct = col - l * p.epi.score_H;
+                const int k = ct / p.epi.score_d, i0 = ct - k * p.epi.score_d;
+                const float* a = reinterpret_cast<const float*>(p.epi.score_att.p[l]) + (size_t)k * 2 * p.epi.score_d + i0;
+                if (i0 == 0) { sc_s = 0.f; sc_t = 0.f; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float4 as = __ldg(reinterpret_cast<const float4*>(a) + j);
+                  const float4 at = __ldg(reinterpret_cast<const float4*>(a + p.epi.score_d) + j);
+                  sc_s = fmaf(as.x, v[4 * j], sc_s); sc_s = fmaf(as.y, v[4 * j + 1], sc_s);
+                  sc_s = fmaf(as.z, v[4 * j + 2], sc_s); sc_s = fmaf(as.w, v[4 * j + 3], sc_s);
+                  sc_t = fmaf(at.x, v[4 * j], sc_t); sc_t = fmaf(at.y, v[4 * j + 1], sc_t);
+                  sc_t = fmaf(at.z, v[4 * j + 2], sc_t); sc_t = fmaf(at.w, v[4 * j + 3], sc_t);
+                }
+                if (i0 + 16 == p.epi.score_d && row_ok) {
+                  const long long o = row * (long long)(p.N / p.epi.score_d) + (long long)l * p.epi.score_K + k;
+                  p.epi.score_src[o] = sc_s;
+                  p.epi.score_tgt[o] = sc_t;
+                }
               }
 #pragma unroll
               for (int j = 0; j < 16; j += 4)
@@ -518,6 +542,10 @@ bool gemm_tc_supported(long long M, int N, int K, const float* A, int lda, const
   return device_is_sm100() && get_encode_fn() != nullptr;
 }
 
+bool gemm_tc_scores_supported(int N, int H, int d) {
+  const int bn = pick_block_n(N);
+  return bn > 0 && d % 16 == 0 && H % d == 0 && bn % d == 0 && N % H == 0 && (bn % H == 0 || H % bn == 0);
+}
 size_t gemm_tc_packed_bytes(int N, int K) { return (size_t)2 * N * round_up(K, kTcBK) * sizeof(float); }
 
 int launch_pack_weights_tc_table(const PtrTable& W, int L, int D, int H, int corr_bf16, float* packed, cudaStream_t st) {

@@ -70,13 +70,20 @@ __device__ __forceinline__ void rgat_walk(const RgatParams& p, int l, int e_lo, 
           if (PASS == 0) {
             m = fmaxf(m, score);
           } else if (PASS == 2) {
-            const float m_new = fmaxf(m, score);
-            const float rescale = expf(m - m_new);      // 1 when the maximum stays; 0 for the very first edge (m = -FLT_MAX)
-            const float w = expf(score - m_new);
-            m = m_new;
-            den = fmaf(den, rescale, w);
-            acc.x = fmaf(acc.x, rescale, w * x[u].x); acc.y = fmaf(acc.y, rescale, w * x[u].y);
-            acc.z = fmaf(acc.z, rescale, w * x[u].z); acc.w = fmaf(acc.w, rescale, w * x[u].w);
+            // one expf per edge: either the maximum grows (weight of this edge is exp(0) = 1, the sums so far are rescaled;
+            // the very first edge has m = -FLT_MAX: rescale = 0) or it stays (no rescale)
+            if (score > m) {
+              const float rescale = expf(m - score);
+              m = score;
+              den = fmaf(den, rescale, 1.0f);
+              acc.x = fmaf(acc.x, rescale, x[u].x); acc.y = fmaf(acc.y, rescale, x[u].y);
+              acc.z = fmaf(acc.z, rescale, x[u].z); acc.w = fmaf(acc.w, rescale, x[u].w);
+            } else {
+              const float w = expf(score - m);
+              den += w;
+              acc.x = fmaf(w, x[u].x, acc.x); acc.y = fmaf(w, x[u].y, acc.y);
+              acc.z = fmaf(w, x[u].z, acc.z); acc.w = fmaf(w, x[u].w, acc.w);
+            }
           } else {
             const float w = expf(score - m);
             den += w;

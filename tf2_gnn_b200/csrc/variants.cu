@@ -424,12 +424,24 @@ extern "C" int tfgnn_b200_rgat_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
     rc = launch_pack_horizontal(wt, L, 0, D, H, H, (float*)Wcat, LH, st);
     if (rc) return rc;
     GemmEpilogue none;
+    // Attention score halves in the projection's epilogue when the tcgen05 GEMM takes the shape and its column tiles hold
+    // whole heads (TFGNN_B200_RGAT_FUSED_SCORES=0: separate kernel; read per call, the tests compare the two)
+    const char* fs = getenv("TFGNN_B200_RGAT_FUSED_SCORES");
+    const bool tc_path = (path == TFGNN_PATH_AUTO || path == TFGNN_PATH_SORTED_TC || path == TFGNN_PATH_FUSED_TC);
+    const bool fuse_scores = !(fs && atoi(fs) == 0) && tc_path && gemm_tc_supported(Vs, LH, D, h, D, (const float*)P, LH) &&
+                             gemm_tc_scores_supported(LH, H, d);
+    if (fuse_scores) {
+      none.score_src = (float*)ss; none.score_tgt = (float*)stt; none.score_att = at;
+      none.score_H = H; none.score_K = K; none.score_d = d;
+    }
     rc = node_gemm(h, D, (const float*)Wcat, LH, (float*)P, LH, Vs, LH, D, none, path, b, 6, st);
     if (rc) return rc;
-    const long long total = Vs * L * K;
-    rgat_scores_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)P, Vs, L, K, d, at, (float*)ss,
-                                                            (float*)stt);
-    TFGNN_LAUNCH_CHECK();
+    if (!fuse_scores) {
+      const long long total = Vs * L * K;
+      rgat_scores_kernel<<<ceil_div(total, 256), 256, 0, st>>>((const float*)P, Vs, L, K, d, at, (float*)ss,
+                                                              (float*)stt);
+      TFGNN_LAUNCH_CHECK();
+    }
   }
   const bool vec = (d % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && L > 0;
   if (vec) return launch_rgat_aggregate(b, (const float*)P, (const float*)ss, (const float*)stt, K, d, activation, out, st);
