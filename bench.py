@@ -381,9 +381,9 @@ def reference_arm(args, wl, rank, world):
 
 # -------------------------------------------------------------------------------------------
 KERNEL_OF = {
-    "rgcn": "fused_rgcn_kernel (gather ring -> TMA -> 3xTF32 tcgen05.mma cta_group::2 -> epilogue) + 2 weight-pack kernels",
-    "ggnn": "fused_rgcn_kernel (messages) + gemm_tc_kernel x2 (GRU gates) + gru_gate_kernel",
-    "rgat": "gemm_tc_kernel (P = h W) + rgat_scores_kernel + rgat_warp_kernel / hub kernels (segment softmax + weighted sum)",
+    "rgcn": "fused_rgcn_kernel (gather ring -> TMA -> 3xTF32 tcgen05.mma cta_group::2 -> epilogue from registers) + 1 weight-pack kernel",
+    "ggnn": "fused_rgcn_kernel (messages) + gemm_tc_kernel over [agg | h] with the GRU gate math in its epilogue",
+    "rgat": "gemm_tc_kernel (P = h W, attention score halves in its epilogue) + rgat_warp_kernel / hub kernels (online segment softmax + weighted sum)",
     "gnn_film": "edge_reduce_kernel (A_l) + gemm_tc_kernel (FiLM parameters, messages) with the modulation in the GEMM epilogue",
 }
 

@@ -70,7 +70,8 @@ struct FusedParams {
   int n_peer;
   float* C_mc;   // multicast mapping of all replicas (NVSwitch replicates one multimem.st), or null
   uint32_t sleep_crit, sleep_long;   // nanosleep between barrier probes (0 = spin): K-loop waits / once-per-tile waits
-  int epi_direct;    // 1: epilogue stores straight from registers (each thread its row's 64 B pieces), 0: through the staging tile
+  int epi_direct;    // epilogue stores straight from registers: 1 = each thread its own row's 16 B pieces, 2 = lane pairs write
+                     // 32 contiguous bytes, 3 = lane quads write 64 contiguous bytes per row; 0 = through the staging tile
   int epi_helpers;   // 1: single accumulator and direct stores -> the splitter warps drain the upper half of the columns
   long long* trace;   // debug (TFGNN_B200_FUSED_TRACE=file): kFuTraceSlots clock64 stamps per CTA, see fu_trace()
   GemmEpilogue epi;
@@ -507,7 +508,36 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         float v[16];
         load_chunk(col, v);
         if (ln) ln_affine(col, v);
-        if (row_ok) {
+        if (p.epi_direct == 3) {
+          // 64 contiguous bytes per row and store instruction: 4x4 float4 transpose over lane quads (sm100_ptx.cuh)
+          const int t = lane & 3;
+          float4 C0, C1, C2, C3;
+          ptx::quad_transpose_f4(v, lane, C0, C1, C2, C3);
+          float* base = crow - (long long)t * p.ldc + col + 4 * t;
+          const long long r_base = row - t;
+          if (r_base < p.V) ptx::st_f4_hint(base, C0, pol_stream);
+          if (r_base + 1 < p.V) ptx::st_f4_hint(base + p.ldc, C1, pol_stream);
+          if (r_base + 2 < p.V) ptx::st_f4_hint(base + 2 * (long long)p.ldc, C2, pol_stream);
+          if (r_base + 3 < p.V) ptx::st_f4_hint(base + 3 * (long long)p.ldc, C3, pol_stream);
+        } else if (p.epi_direct == 2) {
+          // full 32 B sectors per store instruction: lanes 2i / 2i+1 swap every second float4 and write 32 contiguous bytes
+          // of one of their two rows (gemm_tc.cu: tc_store_pairwise)
+          const bool odd = lane & 1;
+          float* pe = (odd ? crow - p.ldc : crow) + col + (odd ? 4 : 0);
+          float* po = (odd ? crow : crow + p.ldc) + col + (odd ? 4 : 0);
+          const bool ok_e = (odd ? row - 1 : row) < p.V, ok_o = (odd ? row : row + 1) < p.V;
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            const float rx = __shfl_xor_sync(0xffffffffu, odd ? v[j] : v[j + 4], 1);
+            const float ry = __shfl_xor_sync(0xffffffffu, odd ? v[j + 1] : v[j + 5], 1);
+            const float rz = __shfl_xor_sync(0xffffffffu, odd ? v[j + 2] : v[j + 6], 1);
+            const float rw = __shfl_xor_sync(0xffffffffu, odd ? v[j + 3] : v[j + 7], 1);
+            const float4 mine = odd ? make_float4(v[j + 4], v[j + 5], v[j + 6], v[j + 7]) : make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            const float4 got = make_float4(rx, ry, rz, rw);
+            if (ok_e) ptx::st_f4_hint(pe + j, odd ? got : mine, pol_stream);
+            if (ok_o) ptx::st_f4_hint(po + j, odd ? mine : got, pol_stream);
+          }
+        } else if (row_ok) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
             ptx::st_f4_hint(crow + col + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]), pol_stream);
@@ -923,7 +953,7 @@ int launch_fused_rgcn(const float* h, int D, const int* row_ptr, const int* src,
   {
     const char* ed = getenv("TFGNN_B200_EPI_DIRECT");
     const char* eh = getenv("TFGNN_B200_EPI_HELPERS");
-    p.epi_direct = (p.n_peer == 0 && p.C_mc == nullptr && !(ed && atoi(ed) == 0)) ? 1 : 0;
+    p.epi_direct = (p.n_peer == 0 && p.C_mc == nullptr && !(ed && atoi(ed) == 0)) ? (ed ? atoi(ed) : 3) : 0;   // 1: own 16 B pieces, 2: lane pairs (32 B), 3: lane quads (64 B)
     p.epi_helpers = (p.epi_direct && p.block_n > 128 && !want_ln && !(eh && atoi(eh) == 0)) ? 1 : 0;
     const char* sc = getenv("TFGNN_B200_SLEEP_CRIT");
     const char* sl = getenv("TFGNN_B200_SLEEP_LONG");

@@ -14,11 +14,14 @@
 //   warp 0      TMA producer: raw fp32 A tile + pre-split B_hi / B_lo tiles (K-major, SWIZZLE_128B)
 //   warps 2-5   splitters: A tile -> A_hi (in place) and A_lo (position-preserving, so layout-agnostic)
 //   warp 1      MMA issuer: 12 tcgen05.mma.kind::tf32 per K block, fp32 accumulators in TMEM (2 stages)
-//   warps 6-9   epilogue: tcgen05.ld -> row normalisation / bias / activation -> global
+//   warps 6-13  epilogue, two groups of four: tcgen05.ld -> row normalisation / bias / activation (or the chained / GRU /
+//               RGAT-score forms) -> global, each thread its own row's 64 B pieces straight from registers
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <vector>
 
 #include "gemm.cuh"
 #include "sm100_ptx.cuh"
@@ -28,12 +31,10 @@ namespace tfgnn {
 constexpr int kTcBM = 128;
 constexpr int kTcBK = 32;                       // floats per K block = 128 bytes
 constexpr int kTcATileBytes = kTcBM * 128;      // 16 KiB
-constexpr int kTcThreads = 320;
+constexpr int kTcThreads = 448;               // TMA, MMA, 4 splitter warps, 8 epilogue warps
 constexpr int kTcTmemCols = 512;
 constexpr int kTcAccStride = 256;               // TMEM columns per accumulator stage (main + correction)
 constexpr int kTcSmemLimit = 227 * 1024;
-constexpr int kTcEpiPitch = 36;                 // floats per staged row (32 + 4 pad, keeps 16 B alignment)
-constexpr int kTcEpiBytes = 4 * 32 * kTcEpiPitch * 4;  // 4 epilogue warps x 32 rows
 
 struct TcParams {
   long long M;
@@ -47,6 +48,8 @@ struct TcParams {
   int ldc;
   // K blocks [0, kb_split) come from map_a, the rest from map_a2 (A = [A1 | A2] without materialising the concatenation)
   int kb_split;
+  int store_quad;     // epilogue stores: 1 = 64 B per row and instruction (lane quads), 0 = 32 B (lane pairs)
+  long long* trace;   // debug (TFGNN_B200_GEMM_TRACE=file): kTcTraceSlots clock64 stamps per CTA, see tc_trace()
   // GRU mode (launch_gemm_tc_gru): the N tile of 128 columns holds the pre-activations [z | r | x_h | h_h] of 32 hidden units;
   // the epilogue applies the Keras GRUCell gate math (reset_after) and writes the 32 new states of each row.
   int gru;
@@ -55,6 +58,60 @@ struct TcParams {
   const float* gru_bias;   // [N] in the tile layout: b0_z + b1_z | b0_r + b1_r | b0_h | b1_h per 32 units
   GemmEpilogue epi;
 };
+
+// Debug timeline of the first kTcTraceKb K blocks of a CTA (SM-local clock64): per K block i
+//   4i+0 TMA issued, 4i+1 splitter saw the bytes, 4i+2 MMA thread saw bytes + split and issues, 4i+3 TMA saw the stage free again
+// (slot of the block that reuses the stage); 240+ : 240 kernel entry, 241 first tile's epilogue start, 242 its end, 243 exit.
+constexpr int kTcTraceSlots = 256;
+constexpr int kTcTraceKb = 60;
+__device__ __forceinline__ void tc_trace(const TcParams& p, int idx) {
+  if (p.trace) p.trace[(size_t)blockIdx.x * kTcTraceSlots + idx] = clock64();
+}
+
+// Epilogue stores straight from registers, full 32 B sectors per instruction: every thread holds NF4 consecutive float4 of ITS
+// row; lanes 2i / 2i+1 swap every second float4, so that in each store instruction the pair writes 32 contiguous bytes of one
+// of its two rows.  (Each lane storing its own 16 B pieces wrote half sectors: the wide-output shapes lost 10-14 %,
+// [500k,128]x[128,384] 0.456 -> 0.507 ms, gpurun r2v.)  Must be called by all 32 lanes.
+template <int NF4>
+__device__ __forceinline__ void tc_store_pairwise(float* own, long long ld, const float (&v)[4 * NF4], long long row,
+                                                  long long M, int lane) {
+  static_assert(NF4 % 2 == 0, "pairs of float4");
+  const bool odd = lane & 1;
+  float* pe = odd ? own - ld : own;            // row of the even lane of the pair
+  float* po = odd ? own : own + ld;            // row of the odd lane
+  const bool ok_e = (odd ? row - 1 : row) < M, ok_o = (odd ? row : row + 1) < M;
+  const int off = odd ? 4 : 0;
+#pragma unroll
+  for (int j = 0; j < NF4; j += 2) {
+    // even lane gives its float4 j+1 and gets the partner's float4 j; odd lane the other way round
+    float sx = odd ? v[4 * j] : v[4 * j + 4], sy = odd ? v[4 * j + 1] : v[4 * j + 5];
+    float sz = odd ? v[4 * j + 2] : v[4 * j + 6], sw = odd ? v[4 * j + 3] : v[4 * j + 7];
+    const float rx = __shfl_xor_sync(0xffffffffu, sx, 1), ry = __shfl_xor_sync(0xffffffffu, sy, 1);
+    const float rz = __shfl_xor_sync(0xffffffffu, sz, 1), rw = __shfl_xor_sync(0xffffffffu, sw, 1);
+    const float4 mine = odd ? make_float4(v[4 * j + 4], v[4 * j + 5], v[4 * j + 6], v[4 * j + 7])
+                            : make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    const float4 got = make_float4(rx, ry, rz, rw);
+    if (ok_e) *reinterpret_cast<float4*>(pe + 4 * j + off) = odd ? got : mine;
+    if (ok_o) *reinterpret_cast<float4*>(po + 4 * j + off) = odd ? mine : got;
+  }
+}
+
+// The same idea over lane QUADS for the 16-column chunks: a 4x4 transpose of float4 in two shuffle rounds (xor 1, xor 2), after
+// which lane t of a quad holds float4 number t of all four rows of the quad - every store instruction then writes 64 contiguous
+// bytes per row (8 rows per instruction), half as many L2 requests as the pairwise form.  TFGNN_B200_GEMM_STORE=2 (default) /
+// 1 (pairwise): wide outputs ([1M,256]x[256,1024]) measured 3.09 ms with the old 128 B staging-tile stores, 3.36 pairwise.
+__device__ __forceinline__ void tc_store_quadwise(float* own, long long ld, const float (&v)[16], long long row, long long M,
+                                                  int lane) {
+  const int t = lane & 3;
+  float4 C0, C1, C2, C3;
+  ptx::quad_transpose_f4(v, lane, C0, C1, C2, C3);
+  float* base = own - (long long)t * ld + 4 * t;     // row of the quad's lane 0, this lane's 16-byte column
+  const long long r_base = row - t;
+  if (r_base < M) *reinterpret_cast<float4*>(base) = C0;
+  if (r_base + 1 < M) *reinterpret_cast<float4*>(base + ld) = C1;
+  if (r_base + 2 < M) *reinterpret_cast<float4*>(base + 2 * ld) = C2;
+  if (r_base + 3 < M) *reinterpret_cast<float4*>(base + 3 * ld) = C3;
+}
 
 __device__ __forceinline__ float tc_row_norm(const GemmEpilogue& e, long long row) {
   if (e.row_norm == 0) return 1.0f;
@@ -82,9 +139,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tmem_full = bars + 3 * S;    // accumulator complete
   uint64_t* tmem_empty = bars + 3 * S + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * S + 4);
-  float* epi_stage = reinterpret_cast<float*>(bars + ((3 * S + 7) & ~1));  // 16 B aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) tc_trace(p, 240);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&map_a);
@@ -97,7 +154,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 128);
+      ptx::mbar_init(&tmem_empty[a], p.block_n <= 128 ? 128 : 256);   // one group per stage / both groups on the one stage
     }
     ptx::fence_barrier_init();
   }
@@ -121,6 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const int s = it % S;
           const uint32_t ph = (it / S) & 1;
           ptx::mbar_wait(&empty[s], ph ^ 1);
+          if (it < kTcTraceKb) { tc_trace(p, 4 * it + 3); tc_trace(p, 4 * it); }
           uint8_t* st = smem + (size_t)s * stage_bytes;
           ptx::mbar_arrive_expect_tx(&full[s], kTcATileBytes + 2 * b_tile_bytes);
           if (p.prefetch_a) {
@@ -157,6 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         ptx::mbar_wait(&split[s], ph);
         ptx::tc_fence_after_sync();
         if (lane == 0) {
+          if (it < kTcTraceKb) tc_trace(p, 4 * it + 2);
           const uint32_t st = ptx::smem_u32(smem + (size_t)s * stage_bytes);
           const uint64_t a_hi = ptx::umma_desc_k_sw128(st);
           const uint64_t a_lo = ptx::umma_desc_k_sw128(st + kTcATileBytes);
@@ -188,6 +247,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int s = it % S;
         const uint32_t ph = (it / S) & 1;
         ptx::mbar_wait(&full[s], ph);
+        if (tid == 0 && it < kTcTraceKb) tc_trace(p, 4 * it + 1);
         // All eight 16-byte loads first, through explicit shared-space instructions: with generic pointers the compiler
         // could not hoist a load above the previous iteration's stores (possible aliasing), so every thread paid one
         // shared-memory round trip per 16 bytes: ~20 % of all stall samples sat on the LOP3 waiting for its LD (ncu r2c).
@@ -222,24 +282,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ================= epilogue (warps 6..9 -> TMEM lane quarters 2,3,0,1) =================
+    // ================= epilogue: warps 6..13, two groups of four (TMEM lane quarter = warp & 3) =================
+    // Two accumulator stages (block_n <= 128): group g drains the tiles that use stage g, so a tile's drain may take as long as
+    // two K loops (the GRU gate epilogue takes 8 us against 6.4 us of K loop: gpurun r2u trace).  One stage: the next tile's
+    // MMAs wait for the drain, and the groups split its columns.  Every thread owns one row and stores its 64 B pieces
+    // straight from registers: no staging tile (its 18 KB buy a 4th pipeline stage at 80-column tiles), no warp barriers.
     const int q = warp & 3;
+    const int grp = (warp - 6) >> 2;
     uint32_t tile_count = 0;
     const uint32_t n_acc = p.block_n <= 128 ? 2 : 1;
     const uint32_t corr_off = p.block_n <= 128 ? 128 : 256;
+    const int half_cols = ((p.block_n / 16 + 1) / 2) * 16;
+    const int col_lo = n_acc == 2 ? 0 : (grp == 0 ? 0 : half_cols);
+    const int col_hi = n_acc == 2 ? p.block_n : (grp == 0 ? half_cols : p.block_n);
+    const bool chained = p.epi.mul != nullptr || p.epi.accumulate || !p.epi.finalize;
     for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_count) {
+      if (n_acc == 2 && (int)(tile_count & 1) != grp) continue;
       const long long m0 = (tile / p.n_tiles) * kTcBM;
       const int n0 = (int)(tile % p.n_tiles) * p.block_n;
       const uint32_t acc = tile_count % n_acc, acc_ph = (tile_count / n_acc) & 1;
       ptx::mbar_wait(&tmem_full[acc], acc_ph);
       ptx::tc_fence_after_sync();
+      if (tile_count == 0 && warp == 6 && lane == 0) tc_trace(p, 241);
       const long long row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
       const float inv_rn = row_ok ? 1.0f / tc_row_norm(p.epi, row) : 1.0f;
-      const bool chained = p.epi.mul != nullptr || p.epi.accumulate || !p.epi.finalize;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * kTcAccStride;
-      float* stage = epi_stage + (size_t)(warp - 6) * 32 * kTcEpiPitch;
-      float sc_s = 0.f, sc_t = 0.f;   // RGAT score accumulators of the current head (epi.score_src)
       if (p.gru) {
         // Keras GRUCell, reset_after (ggnn.py:84-87) on the 32 hidden units of this tile, 8 at a time, straight from TMEM:
         //   z = sigmoid(acc_z + bz), r = sigmoid(acc_r + br), hh = tanh(acc_x + bx + r * (acc_h + bh)), h' = z h + (1 - z) hh
@@ -264,11 +332,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 8; ++j) pre[t][j] = (__uint_as_float(m[t][j]) + __uint_as_float(c[t][j])) + bb[j];
           }
+          float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
           if (row_ok) {
             const float4 h0 = __ldg(reinterpret_cast<const float4*>(hrow + g));
             const float4 h1 = __ldg(reinterpret_cast<const float4*>(hrow + g + 4));
             const float hp[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-            float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float z = 1.0f / (1.0f + expf(-pre[0][j]));
@@ -276,127 +344,94 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               const float hh = tanhf(pre[2][j] + r * pre[3][j]);
               o[j] = z * hp[j] + (1.0f - z) * hh;
             }
-            *reinterpret_cast<float4*>(orow + g) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(orow + g + 4) = make_float4(o[4], o[5], o[6], o[7]);
           }
+          tc_store_pairwise<2>(orow + g, p.ldc, o, row, p.M, lane);
         }
         ptx::tc_fence_before_sync();
+        if (tile_count == 0 && warp == 6 && lane == 0) tc_trace(p, 242);
         ptx::mbar_arrive(&tmem_empty[acc]);
         continue;
       }
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        const int ncols = min(32, p.block_n - c0);     // 32 or 16
-        // TMEM -> registers (row = lane), epilogue math, -> smem staging tile [32 rows][ncols]
-        {
-          // TMEM -> registers: main and correction accumulators of up to 32 columns, ONE wait
-          uint32_t mv[2][16], cv[2][16];
-          const int nh = ncols > 16 ? 2 : 1;
+      float sc_s = 0.f, sc_t = 0.f;   // RGAT score accumulators of the current head (epi.score_src)
+      float* crow = p.C + row * p.ldc + n0;
+      const float* mrow = p.epi.mul ? p.epi.mul + row * p.epi.ldm + n0 : nullptr;
+      for (int col = col_lo; col < col_hi; col += 16) {
+        uint32_t mv[16], cv[16];
+        ptx::tmem_ld_x16_nowait(taddr + col, mv);
+        ptx::tmem_ld_x16_nowait(taddr + corr_off + col, cv);
+        ptx::tmem_wait_ld();
+        float v[16];
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            if (half < nh) {
-              ptx::tmem_ld_x16_nowait(taddr + c0 + half * 16, mv[half]);
-              ptx::tmem_ld_x16_nowait(taddr + corr_off + c0 + half * 16, cv[half]);
+        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(mv[j]) + __uint_as_float(cv[j]);
+        if (p.epi.score_src) {
+          // RGAT: this row's attention score halves, head by head, while its 16-column chunks pass (a chunk lies inside one
+          // head: d % 16 == 0; a tile - and each group's column range - holds whole heads, visited in ascending column order)
+          const int gc = n0 + col;
+          const int l = gc / p.epi.score_H, ct = gc - l * p.epi.score_H;
+          const int k = ct / p.epi.score_d, i0 = ct - k * p.epi.score_d;
+          const float* a = reinterpret_cast<const float*>(p.epi.score_att.p[l]) + (size_t)k * 2 * p.epi.score_d + i0;
+          if (i0 == 0) { sc_s = 0.f; sc_t = 0.f; }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 as = __ldg(reinterpret_cast<const float4*>(a) + j);
+            const float4 at = __ldg(reinterpret_cast<const float4*>(a + p.epi.score_d) + j);
+            sc_s = fmaf(as.x, v[4 * j], sc_s); sc_s = fmaf(as.y, v[4 * j + 1], sc_s);
+            sc_s = fmaf(as.z, v[4 * j + 2], sc_s); sc_s = fmaf(as.w, v[4 * j + 3], sc_s);
+            sc_t = fmaf(at.x, v[4 * j], sc_t); sc_t = fmaf(at.y, v[4 * j + 1], sc_t);
+            sc_t = fmaf(at.z, v[4 * j + 2], sc_t); sc_t = fmaf(at.w, v[4 * j + 3], sc_t);
+          }
+          if (i0 + 16 == p.epi.score_d && row_ok) {
+            const long long o = row * (long long)(p.N / p.epi.score_d) + (long long)l * p.epi.score_K + k;
+            p.epi.score_src[o] = sc_s;
+            p.epi.score_tgt[o] = sc_t;
+          }
+        }
+        if (chained && row_ok) {
+          // FiLM-style chained contractions: val = (accumulate ? C_old : 0) + (mul ? mul * acc : acc)
+          if (mrow) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 m = __ldg(reinterpret_cast<const float4*>(mrow + col) + j);
+              v[4 * j] *= m.x; v[4 * j + 1] *= m.y; v[4 * j + 2] *= m.z; v[4 * j + 3] *= m.w;
             }
           }
-          ptx::tmem_wait_ld();
+          if (p.epi.accumulate) {
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            if (half < nh) {
-              float v[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(mv[half][j]) + __uint_as_float(cv[half][j]);
-              // uniform branches hoisted out of the element loops (predicated-off code still costs issue slots
-              // and instruction-cache space: the epilogue was ~48 us per 128x256 tile before)
-              if (!chained) {
-                if (p.epi.row_norm) {
-#pragma unroll
-                  for (int j = 0; j < 16; ++j) v[j] *= inv_rn;
-                }
-                if (p.epi.bias) {
-                  const float4* bp = reinterpret_cast<const float4*>(p.epi.bias + n0 + c0 + half * 16);
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const float4 bb = __ldg(bp + j);
-                    v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
-                  }
-                }
-                apply_act_vec<16>(v, p.epi.act);
-              }
-              if (p.epi.score_src) {
-                // RGAT: this row's attention score halves, head by head, while its 16-column chunks pass (a chunk lies inside
-                // one head: d % 16 == 0; a tile holds whole heads, visited in ascending column order)
-                const int col = n0 + c0 + half * 16;
-                const int l = col / p.epi.score_H, ct = col - l * p.epi.score_H;
-                const int k = ct / p.epi.score_d, i0 = ct - k * p.epi.score_d;
-                const float* a = reinterpret_cast<const float*>(p.epi.score_att.p[l]) + (size_t)k * 2 * p.epi.score_d + i0;
-                if (i0 == 0) { sc_s = 0.f; sc_t = 0.f; }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float4 as = __ldg(reinterpret_cast<const float4*>(a) + j);
-                  const float4 at = __ldg(reinterpret_cast<const float4*>(a + p.epi.score_d) + j);
-                  sc_s = fmaf(as.x, v[4 * j], sc_s); sc_s = fmaf(as.y, v[4 * j + 1], sc_s);
-                  sc_s = fmaf(as.z, v[4 * j + 2], sc_s); sc_s = fmaf(as.w, v[4 * j + 3], sc_s);
-                  sc_t = fmaf(at.x, v[4 * j], sc_t); sc_t = fmaf(at.y, v[4 * j + 1], sc_t);
-                  sc_t = fmaf(at.z, v[4 * j + 2], sc_t); sc_t = fmaf(at.w, v[4 * j + 3], sc_t);
-                }
-                if (i0 + 16 == p.epi.score_d && row_ok) {
-                  const long long o = row * (long long)(p.N / p.epi.score_d) + (long long)l * p.epi.score_K + k;
-                  p.epi.score_src[o] = sc_s;
-                  p.epi.score_tgt[o] = sc_t;
-                }
-              }
-#pragma unroll
-              for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(stage + lane * kTcEpiPitch + half * 16 + j) =
-                    make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            for (int j = 0; j < 4; ++j) {
+              const float4 c = *(reinterpret_cast<const float4*>(crow + col) + j);
+              v[4 * j] += c.x; v[4 * j + 1] += c.y; v[4 * j + 2] += c.z; v[4 * j + 3] += c.w;
             }
           }
         }
-        __syncwarp();
-        // coalesced stores: 8 lanes cover one row's 128 B, 4 rows per instruction
-        const int f4_per_row = ncols / 4;                 // 8 or 4
-        const int rows_per_it = 32 / f4_per_row;          // 4 or 8
-        const int rr = lane / f4_per_row, cc = (lane % f4_per_row) * 4;
-        for (int r0 = 0; r0 < 32; r0 += rows_per_it) {
-          const int r = r0 + rr;
-          const long long grow = m0 + q * 32 + r;
-          // chained contractions: the row-norm factor of row r lives in lane r (shuffle before the row guard)
-          const float rn_r = chained ? __shfl_sync(0xffffffffu, inv_rn, r) : 1.0f;
-          if (grow < p.M) {
-            float4 val = *reinterpret_cast<const float4*>(stage + r * kTcEpiPitch + cc);
-            float* cptr = p.C + grow * p.ldc + n0 + c0 + cc;
-            if (chained) {
-              float o[4] = {val.x, val.y, val.z, val.w};
-              if (p.epi.mul) {
-                const float4 m = __ldg(reinterpret_cast<const float4*>(p.epi.mul + grow * p.epi.ldm + n0 + c0 + cc));
-                o[0] *= m.x; o[1] *= m.y; o[2] *= m.z; o[3] *= m.w;
-              }
-              if (p.epi.accumulate) {
-                const float4 c = *reinterpret_cast<const float4*>(cptr);
-                o[0] += c.x; o[1] += c.y; o[2] += c.z; o[3] += c.w;
-              }
-              if (p.epi.finalize) {
-                if (p.epi.row_norm) { o[0] *= rn_r; o[1] *= rn_r; o[2] *= rn_r; o[3] *= rn_r; }
-                if (p.epi.bias) {
-                  const float4 bb = __ldg(reinterpret_cast<const float4*>(p.epi.bias + n0 + c0 + cc));
-                  o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
-                }
-                apply_act_vec<4>(o, p.epi.act);
-              }
-              val = make_float4(o[0], o[1], o[2], o[3]);
-            }
-            *reinterpret_cast<float4*>(cptr) = val;
+        if (!chained || p.epi.finalize) {
+          // uniform branches hoisted out of the element loops (predicated-off code still costs issue slots
+          // and instruction-cache space: the epilogue was ~48 us per 128x256 tile before)
+          if (p.epi.row_norm) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] *= inv_rn;
           }
+          if (p.epi.bias) {
+            const float4* bp = reinterpret_cast<const float4*>(p.epi.bias + n0 + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 bb = __ldg(bp + j);
+              v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+            }
+          }
+          apply_act_vec<16>(v, p.epi.act);
         }
-        __syncwarp();
+        if (p.store_quad) tc_store_quadwise(crow + col, p.ldc, v, row, p.M, lane);
+        else tc_store_pairwise<4>(crow + col, p.ldc, v, row, p.M, lane);
       }
       ptx::tc_fence_before_sync();
+      if (tile_count == 0 && warp == 6 && lane == 0) tc_trace(p, 242);
       ptx::mbar_arrive(&tmem_empty[acc]);
     }
   }
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) tc_trace(p, 243);
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_base, kTcTmemCols);
@@ -544,7 +579,8 @@ bool gemm_tc_supported(long long M, int N, int K, const float* A, int lda, const
 
 bool gemm_tc_scores_supported(int N, int H, int d) {
   const int bn = pick_block_n(N);
-  return bn > 0 && d % 16 == 0 && H % d == 0 && bn % d == 0 && N % H == 0 && (bn % H == 0 || H % bn == 0);
+  if (!(bn > 0 && d % 16 == 0 && H % d == 0 && bn % d == 0 && N % H == 0 && (bn % H == 0 || H % bn == 0))) return false;
+  return bn <= 128 || (((bn / 16 + 1) / 2) * 16) % d == 0;   // one accumulator stage: the two epilogue groups split the columns
 }
 size_t gemm_tc_packed_bytes(int N, int K) { return (size_t)2 * N * round_up(K, kTcBK) * sizeof(float); }
 
@@ -588,7 +624,7 @@ static int launch_gemm_tc_impl(const float* A, int lda, const float* packedB, fl
   p.total_tiles = p.m_tiles * p.n_tiles;
   p.num_k_blocks = Kp / kTcBK;
   const int stage_bytes = 2 * kTcATileBytes + 2 * p.block_n * 128;
-  int stages = (kTcSmemLimit - 2048 - kTcEpiBytes) / stage_bytes;
+  int stages = (kTcSmemLimit - 2048) / stage_bytes;
   if (stages > 4) stages = 4;
   TFGNN_REQUIRE(stages >= 2, "tcgen05 GEMM: tile does not fit shared memory");
   p.num_stages = stages;
@@ -601,6 +637,10 @@ static int launch_gemm_tc_impl(const float* A, int lda, const float* packedB, fl
   const int K1 = ex.A2 ? ex.K1 : K;
   p.kb_split = ex.A2 ? K1 / kTcBK : p.num_k_blocks;
   p.gru = ex.gru_h ? 1 : 0;
+  {
+    const char* e = getenv("TFGNN_B200_GEMM_STORE");   // read per call (A/B experiments)
+    p.store_quad = e ? (atoi(e) == 2) : 1;
+  }
   if (p.gru) p.corr_bf16 = 0;   // pack_gru_weights_kernel writes the two-MMA (tf32 lo) correction operand
   p.gru_h = ex.gru_h; p.gru_ldh = ex.gru_ldh; p.gru_bias = ex.gru_bias;
 
@@ -645,7 +685,7 @@ static int launch_gemm_tc_impl(const float* A, int lda, const float* packedB, fl
       return TFGNN_ERR_CUDA;
     }
   }
-  const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 8) * sizeof(uint64_t) + kTcEpiBytes + 1024;
+  const size_t smem_bytes = (size_t)stages * stage_bytes + (3 * stages + 8) * sizeof(uint64_t) + 1024;
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
@@ -656,8 +696,26 @@ static int launch_gemm_tc_impl(const float* A, int lda, const float* packedB, fl
   TFGNN_CUDA(cudaGetDevice(&dev));
   TFGNN_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int grid = (int)(p.total_tiles < sms ? p.total_tiles : sms);
+  p.trace = nullptr;
+  const char* tr = getenv("TFGNN_B200_GEMM_TRACE");
+  if (tr && *tr) {
+    TFGNN_CUDA(cudaMalloc(&p.trace, (size_t)grid * kTcTraceSlots * sizeof(long long)));
+    TFGNN_CUDA(cudaMemset(p.trace, 0, (size_t)grid * kTcTraceSlots * sizeof(long long)));
+  }
   gemm_tc_kernel<<<grid, kTcThreads, smem_bytes, st>>>(map_a, map_a2, map_b, p);
   TFGNN_LAUNCH_CHECK();
+  if (p.trace) {   // debug only: synchronous dump of the LAST launch (grid x kTcTraceSlots int64 after a 4-word header)
+    std::vector<long long> host((size_t)grid * kTcTraceSlots);
+    TFGNN_CUDA(cudaStreamSynchronize(st));
+    TFGNN_CUDA(cudaMemcpy(host.data(), p.trace, host.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    cudaFree(p.trace);
+    if (FILE* f = fopen(tr, "wb")) {
+      const long long hdr[4] = {grid, kTcTraceSlots, p.num_k_blocks, p.num_stages};
+      fwrite(hdr, sizeof(long long), 4, f);
+      fwrite(host.data(), sizeof(long long), host.size(), f);
+      fclose(f);
+    }
+  }
   return 0;
 }
 

@@ -62,6 +62,26 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
   }
 }
 
+// 4x4 transpose of float4 over a lane quad in two shuffle rounds (xor 1, xor 2): every lane comes in with the four float4
+// v[0..15] of ITS row and leaves with float4 number (lane & 3) of the quad's four rows (C_k = row k of the quad).  Epilogues
+// use it to store 64 contiguous bytes per row and instruction straight from registers.  All 32 lanes must call it.
+__device__ __forceinline__ float4 shfl_xor_f4(float4 x, int m) {
+  return make_float4(__shfl_xor_sync(0xffffffffu, x.x, m), __shfl_xor_sync(0xffffffffu, x.y, m),
+                     __shfl_xor_sync(0xffffffffu, x.z, m), __shfl_xor_sync(0xffffffffu, x.w, m));
+}
+__device__ __forceinline__ void quad_transpose_f4(const float (&v)[16], int lane, float4& C0, float4& C1, float4& C2,
+                                                  float4& C3) {
+  const bool b0 = lane & 1, b1 = lane & 2;
+  const float4 A0 = make_float4(v[0], v[1], v[2], v[3]), A1 = make_float4(v[4], v[5], v[6], v[7]);
+  const float4 A2 = make_float4(v[8], v[9], v[10], v[11]), A3 = make_float4(v[12], v[13], v[14], v[15]);
+  // round 1 (pairs): afterwards B0,B1 = float4 number (lane & 1) of the pair's two rows, B2,B3 = number (lane & 1) + 2
+  const float4 r0 = shfl_xor_f4(b0 ? A0 : A1, 1), r1 = shfl_xor_f4(b0 ? A2 : A3, 1);
+  const float4 B0 = b0 ? r0 : A0, B1 = b0 ? A1 : r0, B2 = b0 ? r1 : A2, B3 = b0 ? A3 : r1;
+  // round 2 (pairs of pairs): lanes 0,1 keep B0,B1 and get the other pair's B0,B1; lanes 2,3 keep B2,B3 and get B2,B3
+  const float4 s0 = shfl_xor_f4(b1 ? B0 : B2, 2), s1 = shfl_xor_f4(b1 ? B1 : B3, 2);
+  C0 = b1 ? s0 : B0; C1 = b1 ? s1 : B1; C2 = b1 ? B2 : s0; C3 = b1 ? B3 : s1;
+}
+
 // ---- proxy fences ----------------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
