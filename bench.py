@@ -55,6 +55,7 @@ WORKLOADS = {
     "tiny": dict(V=20_000, E=[100_000] * 4, H=256, kind="rgcn", graph="er", desc="smoke-sized cfg2"),
 }
 METRIC = "edges/sec (fused gather-msg-scatter)"
+E2E_DEPTH = int(os.environ.get("TFGNN_B200_E2E_DEPTH", "3"))   # steps in flight in the end-to-end leg (runtime.HostPipeline)
 
 
 def algorithmic_bytes(kind, V, E_list, D, H, params):
@@ -543,13 +544,13 @@ def measure_workload(name, args, rank, world, local, dev, headline):
     if not args.skip_e2e:
         out_host = torch.empty((V, H), dtype=torch.float32).pin_memory()
         e2e_steps = max(4, min(args.steps, 10))
-        dt = time_e2e(layer, h_host, adj_host, out_host, e2e_steps, world, depth=2)
+        dt = time_e2e(layer, h_host, adj_host, out_host, e2e_steps, world, depth=E2E_DEPTH)
         res["e2e"] = {"value": world * M * e2e_steps / dt, "unit": "edges/s",
                       "h2d_bytes_per_step": int(h_host.numel() * 4 + sum(a.numel() * 4 for a in adj_host)),
                       "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps,
-                      "ms_per_step": dt / e2e_steps * 1e3, "pipeline_depth": 2,
+                      "ms_per_step": dt / e2e_steps * 1e3, "pipeline_depth": E2E_DEPTH,
                       "what": "public layer call on pinned HOST buffers: H2D(node states + adjacency) -> CSR prepare -> "
-                              "layer -> D2H(new node states) every step; steps software-pipelined 2 deep on CUDA streams "
+                              f"layer -> D2H(new node states) every step; steps software-pipelined {E2E_DEPTH} deep on CUDA streams "
                               "(runtime.HostPipeline), wall clock over all steps"}
     res["_inputs"] = (h_np, adjs_np, w_np)
     return res

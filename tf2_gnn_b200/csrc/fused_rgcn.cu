@@ -768,9 +768,6 @@ fused_rgcn_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     // same-box A/B (gpurun r2l): the compile-time variant wins at D = 256 (4.56 vs 4.77 ms) but loses at D = 320, where the
     // third column group is half empty (6.84 with the generic loop vs 6.95 with a <4, false> instantiation)
     if (p.gather_q == 4 && p.D == 128 * NV) TFGNN_FU_GATHER(4, true);
-#ifdef TFGNN_FU_GATHER_Q4_ALL
-    else if (p.gather_q == 4) TFGNN_FU_GATHER(4, false);
-#endif
     else TFGNN_FU_GATHER(0, false);
 #undef TFGNN_FU_GATHER
   }
