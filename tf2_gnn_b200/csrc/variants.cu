@@ -53,7 +53,10 @@ extern "C" int tfgnn_b200_ggnn_fwd(tfgnn_batch_t* b, const float* h, int32_t D, 
     const bool want = !(e && atoi(e) == 0) &&
                       (path == TFGNN_PATH_AUTO || path == TFGNN_PATH_SORTED_TC || path == TFGNN_PATH_FUSED_TC);
     const float* h_tgt0 = h + (size_t)b->tgt_off * D;
-    if (want && gemm_tc_gru_supported(V, H, (const float*)agg, H, h_tgt0, D, out, H)) {
+    // the contraction reads whole rows of h for every 32-unit column tile while earlier tiles' epilogues already store new
+    // states: an in-place update (out overlapping h; the gate kernel below tolerates it) must not take this form
+    const bool in_place = out < h + (size_t)b->V_src * D && h < out + (size_t)V * H;
+    if (want && !in_place && gemm_tc_gru_supported(V, H, (const float*)agg, H, h_tgt0, D, out, H)) {
       void* packed = nullptr;
       rc = batch_scratch(b, 6, gemm_tc_gru_packed_bytes(H), &packed);
       if (rc) return rc;
